@@ -1,0 +1,182 @@
+// nr_headless — headless driver for NRenderer render components (the reference ships only a GUI).
+//
+// It reproduces what the GUI does when the user clicks "Render"
+// (reference code/app/src/ui/views/SceneView.cpp:97-102): import files into an Asset
+// (ScnImporter/ObjImporter::import, code/app/include/importer/Importer.hpp:16), build the Scene
+// (SceneBuilder::build, code/app/src/asset/SceneBuilder.cpp:100-110), look the component up by
+// name (ComponentFactory::createComponent, code/include/component/ComponentFactory.hpp:30-33) and
+// call RenderComponent::exec (code/server/component/RenderComponent.cpp:5-9); the frame is read
+// back from getServer().screen (code/server/server/Screen.cpp:54-66).
+//
+// It is linked against the reference's own importer/SceneBuilder/server sources (built by
+// oracle/build_ref.py into oracle/_ref/), so it is both the parity oracle runner and the CPU
+// baseline timer, and it can host the CUDA plugin exactly like the GUI would.  Scenes can also be
+// read from / written to `.nrsc` flat-scene fixtures so that it works where /root/reference is absent.
+#include <dlfcn.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "server/Server.hpp"
+#include "component/RenderComponent.hpp"
+#include "asset/Asset.hpp"
+#include "asset/SceneBuilder.hpp"
+#include "importer/ScnImporter.hpp"
+#include "importer/ObjImporter.hpp"
+#include "utilities/ImageLoader.hpp"
+
+#include "../plugin/scene_bridge.hpp"
+
+// The importers call these after a successful parse to build OpenGL preview buffers
+// (code/app/src/importer/ScnImporter.cpp:508-514, ObjImporter.cpp:396-398); headless: no-ops.
+namespace NRenderer {
+void Asset::genPreviewGlBuffersPerNode(NodeItem&) {}
+void Asset::genPreviewGlBuffersPerLight(LightItem&) {}
+void Asset::updateNodeGlDrawData(NodeItem&) {}
+void Asset::updateLightGlDrawData(LightItem&) {}
+}  // namespace NRenderer
+
+using namespace NRenderer;
+
+static void usage() {
+    std::fprintf(stderr,
+        "usage: nr_headless [--scn F|--obj F]... | --flat F.nrsc\n"
+        "         [--mesh-material K] [--texture IMG] [--env-map TEXIDX]\n"
+        "         [--w W --h H --depth D --spp S --aspect A --ambient R G B]\n"
+        "         [--dump-flat OUT.nrsc]\n"
+        "         [--plugin LIB.so]... [--component NAME --out FRAME.f32] [--repeat N] [--list]\n");
+}
+
+int main(int argc, char** argv) {
+    std::vector<std::pair<std::string, std::string>> imports;
+    std::vector<std::string> plugins, textures;
+    std::string flat_in, flat_out, component, out;
+    int mesh_material = -1, env_map = -1, repeat = 1;
+    bool list = false;
+    long w = -1, h = -1, depth = -1, spp = -1;
+    float aspect = -1.f;
+    bool have_ambient = false;
+    float ambient[3] = {0, 0, 0};
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> std::string {
+            if (i + 1 >= argc) { usage(); std::exit(2); }
+            return argv[++i];
+        };
+        if (a == "--scn") imports.push_back({"scn", next()});
+        else if (a == "--obj") imports.push_back({"obj", next()});
+        else if (a == "--flat") flat_in = next();
+        else if (a == "--dump-flat") flat_out = next();
+        else if (a == "--plugin") plugins.push_back(next());
+        else if (a == "--component") component = next();
+        else if (a == "--out") out = next();
+        else if (a == "--mesh-material") mesh_material = std::atoi(next().c_str());
+        else if (a == "--texture") textures.push_back(next());
+        else if (a == "--env-map") env_map = std::atoi(next().c_str());
+        else if (a == "--w") w = std::atol(next().c_str());
+        else if (a == "--h") h = std::atol(next().c_str());
+        else if (a == "--depth") depth = std::atol(next().c_str());
+        else if (a == "--spp") spp = std::atol(next().c_str());
+        else if (a == "--aspect") aspect = (float)std::atof(next().c_str());
+        else if (a == "--repeat") repeat = std::atoi(next().c_str());
+        else if (a == "--ambient") { have_ambient = true; for (int k = 0; k < 3; k++) ambient[k] = (float)std::atof(next().c_str()); }
+        else if (a == "--list") list = true;
+        else { usage(); return 2; }
+    }
+
+    SharedScene scene;
+    if (!flat_in.empty()) {
+        nrb200::FlatScene f;
+        try { f = nrb200::load_flat_scene(flat_in); }
+        catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+        scene = nrb200::unflatten(f);
+    } else if (!imports.empty()) {
+        Asset asset;
+        for (auto& [kind, path] : imports) {
+            bool ok; std::string err;
+            if (kind == "scn") { ScnImporter imp; ok = imp.import(asset, path); err = imp.getErrorInfo(); }
+            else { ObjImporter imp; ok = imp.import(asset, path); err = imp.getErrorInfo(); }
+            if (!ok) { std::fprintf(stderr, "import of %s failed: %s\n", path.c_str(), err.c_str()); return 1; }
+        }
+        if (mesh_material >= 0)
+            for (auto& m : asset.meshes) m->material.setIndex((unsigned)mesh_material);
+        RenderSettings rs; AmbientSettings as; Camera cam;   // GUI defaults (RenderSettingsManager.hpp:9-45)
+        SceneBuilder sb{asset, rs, as, cam};
+        scene = sb.build();
+        if (!scene) { std::fprintf(stderr, "SceneBuilder::build failed (a node has no material)\n"); return 1; }
+    }
+    if (scene) {
+        if (w > 0) scene->renderOption.width = (unsigned)w;
+        if (h > 0) scene->renderOption.height = (unsigned)h;
+        if (depth >= 0) scene->renderOption.depth = (unsigned)depth;
+        if (spp > 0) scene->renderOption.samplesPerPixel = (unsigned)spp;
+        if (aspect > 0) scene->camera.aspect = aspect;
+        if (have_ambient) scene->ambient.constant = {ambient[0], ambient[1], ambient[2]};
+        for (auto& path : textures) {   // TextureImporter semantics minus the GL upload (TextureImporter.cpp:7-21)
+            ImageLoader loader;
+            Image* img = loader.load(path);
+            if (!img || !img->data) { std::fprintf(stderr, "cannot load texture %s\n", path.c_str()); return 1; }
+            Texture t; t.width = img->width; t.height = img->height;
+            t.rgba = new RGBA[(size_t)t.width * t.height];
+            std::memcpy((void*)t.rgba, img->data, sizeof(float) * 4 * (size_t)t.width * t.height);
+            scene->textures.push_back(std::move(t));
+            delete img;
+        }
+        if (env_map >= 0) {
+            scene->ambient.type = Ambient::Type::ENVIROMENT_MAP;
+            scene->ambient.environmentMap = Handle{(unsigned)env_map};
+        }
+    }
+    if (!flat_out.empty()) {
+        if (!scene) { std::fprintf(stderr, "--dump-flat needs a scene\n"); return 2; }
+        nrb200::save_flat_scene(nrb200::flatten(*scene), flat_out);
+    }
+
+    for (auto& p : plugins) {
+        // Same effect as the GUI's LoadLibrary loop (code/app/src/manager/ComponentManager.cpp:15-30):
+        // the library's static ComponentRegister object registers the component.
+        if (!dlopen(p.c_str(), RTLD_NOW | RTLD_GLOBAL)) { std::fprintf(stderr, "dlopen %s: %s\n", p.c_str(), dlerror()); return 1; }
+    }
+    if (list) {
+        for (auto& ci : getServer().componentFactory.getComponentsInfo("Render"))
+            std::printf("%s\n", ci.name.c_str());
+    }
+    if (component.empty()) return 0;
+    if (!scene) { std::fprintf(stderr, "no scene\n"); return 2; }
+
+    double best = 1e300, total = 0;
+    for (int r = 0; r < repeat; r++) {
+        // The reference components mutate the Scene in place, so every run gets a fresh copy
+        // (the GUI builds a new Scene per click, SceneView.cpp:100-101).
+        SharedScene run_scene = std::make_shared<Scene>(*scene);
+        auto comp = getServer().componentFactory.createComponent<RenderComponent>("Render", component);
+        if (!comp) { std::fprintf(stderr, "component %s is not registered\n", component.c_str()); return 1; }
+        auto t0 = std::chrono::steady_clock::now();
+        comp->exec([] {}, [] {}, run_scene);
+        double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        best = std::min(best, s); total += s;
+    }
+    auto& screen = getServer().screen;
+    unsigned sw = screen.getWidth(), sh = screen.getHeight();
+    if (!out.empty()) {
+        std::ofstream o(out, std::ios::binary);
+        o.write((const char*)screen.getPixels(), sizeof(float) * 4 * (size_t)sw * sh);
+    }
+    std::string last_log;
+    {
+        auto logs = getServer().logger.get();
+        for (unsigned i = 0; i < logs.nums; i++) last_log = logs.msgs[i].message;
+    }
+    for (auto& c : last_log) if (c == '"' || c == '\n' || c == '\\') c = ' ';
+    std::printf("{\"component\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %u, \"depth\": %u, "
+                "\"seconds\": %.6f, \"seconds_mean\": %.6f, \"repeat\": %d, \"host_threads\": %u, \"last_log\": \"%s\"}\n",
+                component.c_str(), sw, sh, scene->renderOption.samplesPerPixel, scene->renderOption.depth,
+                best, total / repeat, repeat, std::thread::hardware_concurrency(), last_log.c_str());
+    return 0;
+}
