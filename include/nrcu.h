@@ -81,7 +81,7 @@ enum nrcu_material_prop {
 /*
  * POD mirror of NRenderer::Material (include/scene/Material.hpp:98-168) with the
  * property look-ups the reference shaders perform at construction already resolved
- * (ray_cast/src/shaders/{Lambertian,Phong}.cpp, acc_path_tracing/src/shaders/*.cpp,
+ * (ray_cast/src/shaders/{Lambertian,Phong}.cpp, acc_path_tracing/src/shaders/ *.cpp,
  * acc_path_tracing/include/shaders/{Conductor,Glass}.hpp).  A property that is absent
  * has its bit cleared in `present`; the library then applies the reference's default
  * where it has one ((1,1,1) colours, specularEx 1, roughness 0.2, F0 0.04) and ZERO where

@@ -1,0 +1,169 @@
+"""ctypes binding of libnrcuda.so (the C ABI in include/nrcu.h).
+
+Host plumbing for tests and bench.py: it owns no rendering arithmetic and has NO fallback — if the
+CUDA library is missing, or no CUDA device is present, every entry point raises `NrcuError`.
+The product's host side proper is the C++ RenderComponent adapter in nrenderer_b200/plugin/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flatscene import FlatScene, MODE_ACC, MODE_RAYCAST, MODE_SIMPLE  # noqa: F401
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libnrcuda.so")
+
+ABI_SYMBOLS = [
+    "nrcu_abi_version", "nrcu_device_count", "nrcu_create", "nrcu_destroy", "nrcu_last_error", "nrcu_upload_scene",
+    "nrcu_primitive_count", "nrcu_download_primitives", "nrcu_render", "nrcu_render_accumulate", "nrcu_resolve",
+    "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
+]
+
+
+class NrcuError(RuntimeError):
+    pass
+
+
+class NrcuRenderParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
+                ("glass_mode", C.c_uint32), ("samples_per_wave", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class NrcuStats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_setup", C.c_float),
+                ("bvh_nodes", C.c_uint32), ("n_primitives", C.c_uint32), ("max_queue", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_LIB = None
+
+
+def load_library() -> C.CDLL:
+    """Load libnrcuda.so from the package directory; raise if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise NrcuError(f"{LIB_PATH} is missing: build it with `python -m nrenderer_b200.build` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+    L.nrcu_abi_version.restype = i32
+    L.nrcu_device_count.restype = i32
+    L.nrcu_create.argtypes = [i32, C.POINTER(vp)]
+    L.nrcu_destroy.argtypes = [vp]
+    L.nrcu_last_error.restype = C.c_char_p
+    L.nrcu_last_error.argtypes = [vp]
+    L.nrcu_upload_scene.argtypes = [vp, vp, i32]
+    L.nrcu_primitive_count.argtypes = [vp, C.POINTER(u32)]
+    L.nrcu_download_primitives.argtypes = [vp, vp, vp, vp]
+    L.nrcu_render.argtypes = [vp, vp, vp, vp]
+    L.nrcu_render_accumulate.argtypes = [vp, vp, vp, vp]
+    L.nrcu_resolve.argtypes = [vp, vp, vp]
+    L.nrcu_trace_batch.argtypes = [vp, vp, u32, vp, vp]
+    L.nrcu_set_stream.argtypes = [vp, vp]
+    L.nrcu_synchronize.argtypes = [vp]
+    L.nrcu_philox4x32.argtypes = [vp, vp, vp]
+    L.nrcu_philox4x32.restype = None
+    _LIB = L
+    return L
+
+
+def device_count() -> int:
+    return int(load_library().nrcu_device_count())
+
+
+def philox4x32(counter, key) -> np.ndarray:
+    c, k, o = np.asarray(counter, np.uint32), np.asarray(key, np.uint32), np.zeros(4, np.uint32)
+    load_library().nrcu_philox4x32(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+    return o
+
+
+class Context:
+    """One nrcu_ctx: a CUDA device + stream + the uploaded scene."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.nrcu_create(device, C.byref(h))
+        if rc != 0:
+            raise NrcuError(f"nrcu_create failed ({rc}): {self._lib.nrcu_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+        self.width = self.height = 0
+        self.mode = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nrcu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NrcuError(f"{what} failed ({rc}): {self._lib.nrcu_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._lib.nrcu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "nrcu_set_stream")
+
+    def synchronize(self):
+        self._check(self._lib.nrcu_synchronize(self._h), "nrcu_synchronize")
+
+    def upload(self, flat: FlatScene, mode: int):
+        view, keep = flat.c_view()
+        self._check(self._lib.nrcu_upload_scene(self._h, C.addressof(view), mode), "nrcu_upload_scene")
+        del keep
+        self.width, self.height, self.mode = flat.width, flat.height, mode
+        self.spp = flat.samples_per_pixel
+
+    @property
+    def n_primitives(self) -> int:
+        n = C.c_uint32(0)
+        self._check(self._lib.nrcu_primitive_count(self._h, C.byref(n)), "nrcu_primitive_count")
+        return int(n.value)
+
+    def primitives(self):
+        n = self.n_primitives
+        kind, data, mat = np.zeros(n, np.uint32), np.zeros((n, 16), np.float32), np.zeros(n, np.int32)
+        self._check(self._lib.nrcu_download_primitives(self._h, kind.ctypes.data, data.ctypes.data, mat.ctypes.data),
+                    "nrcu_download_primitives")
+        return kind, data, mat
+
+    @staticmethod
+    def _params(seed, s0, s1, glass_mode, samples_per_wave):
+        return NrcuRenderParams(seed=seed, sample_begin=s0, sample_end=s1, glass_mode=glass_mode,
+                                samples_per_wave=samples_per_wave, flags=0)
+
+    def render(self, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None):
+        """Whole frame into HOST memory (what Screen::set takes). Returns (rgba[h,w,4], stats dict)."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        assert out.dtype == np.float32 and out.size == self.width * self.height * 4 and out.flags.c_contiguous
+        p, st = self._params(seed, 0, 0, glass_mode, samples_per_wave), NrcuStats()
+        self._check(self._lib.nrcu_render(self._h, C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render")
+        return out, st.as_dict()
+
+    def render_accumulate(self, d_accum_ptr: int, s0=0, s1=0, seed=0, glass_mode=0, samples_per_wave=0, want_stats=True):
+        """Add linear sums of samples [s0,s1) into the DEVICE buffer at d_accum_ptr (w*h*4 floats)."""
+        p, st = self._params(seed, s0, s1, glass_mode, samples_per_wave), NrcuStats()
+        self._check(self._lib.nrcu_render_accumulate(self._h, C.addressof(p), C.c_void_p(d_accum_ptr),
+                                                     C.addressof(st) if want_stats else None), "nrcu_render_accumulate")
+        return st.as_dict() if want_stats else None
+
+    def resolve(self, d_accum_ptr: int, d_rgba_ptr: int):
+        self._check(self._lib.nrcu_resolve(self._h, C.c_void_p(d_accum_ptr), C.c_void_p(d_rgba_ptr)), "nrcu_resolve")
+
+    def trace_batch(self, rays: np.ndarray):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = len(rays)
+        pid, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        self._check(self._lib.nrcu_trace_batch(self._h, rays.ctypes.data, n, pid.ctypes.data, t.ctypes.data), "nrcu_trace_batch")
+        return pid, t

@@ -1,0 +1,563 @@
+// nrcu_api.cu — implementation of the C ABI in include/nrcu.h (libnrcuda.so).
+//
+// Host orchestration only: buffers in HBM, kernel launches on one stream, CUDA-event timing.
+// No rendering arithmetic happens on the host except the handful of per-scene scalars the
+// reference also computes once on the CPU (Camera ctor, per-node translation of the few explicit
+// spheres/triangles/planes, Microfacet's constant Sampler(6) draws).  There is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nrcu.h"
+#include "nrcu_kernels.cuh"
+#include "nrcu_host_prep.hpp"
+
+using namespace nrcu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes && p) return cudaSuccess;
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n; else p = nullptr;
+        return e;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct nrcu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string error;
+    bool have_scene = false;
+    int mode = 0;
+    uint32_t spp = 0;
+    DScene ds{};
+    // scene buffers
+    DevBuf prim_geom, prim_shade, prim_box, prim_meta, nodes, leaf_prims, materials, area_lights, env;
+    // scene-prep sources kept for nrcu_download_primitives
+    DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
+        mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
+    PrimSources ps{};
+    // wavefront state
+    DevBuf qa[2], qb[2], qc[2], hits, L, counters, accum_own, rgba_dev;
+    uint32_t queue_capacity = 0, wave_slots = 0;
+    unsigned long long* d_ray_counter = nullptr;   // inside `counters`
+    // stats
+    float ms_setup = 0.f;
+    uint32_t bvh_nodes = 0;
+    uint64_t launches = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+};
+
+#define CTX_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ctx->error = std::string(#call) + ": " + cudaGetErrorString(_e);                        \
+            return NRCU_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+#define CTX_LAUNCH_CHECK(name)                                                                      \
+    do {                                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        ctx->launches++;                                                                            \
+        if (_e != cudaSuccess) {                                                                    \
+            ctx->error = std::string("launch of ") + name + ": " + cudaGetErrorString(_e);          \
+            return NRCU_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)std::max<size_t>(1, (n + block - 1) / block); }
+
+template <typename T>
+static int upload(nrcu_ctx* ctx, DevBuf& buf, const T* src, size_t count) {
+    CTX_CUDA(buf.ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) CTX_CUDA(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return NRCU_OK;
+}
+
+extern "C" {
+
+int nrcu_abi_version(void) { return NRCU_ABI_VERSION; }
+
+int nrcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* nrcu_last_error(const nrcu_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int nrcu_create(int device, nrcu_ctx** out) {
+    if (!out) { g_create_error = "nrcu_create: out is null"; return NRCU_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        cudaGetLastError();
+        return NRCU_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { g_create_error = "nrcu_create: device index out of range"; return NRCU_ERR_INVALID; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return NRCU_ERR_CUDA; }
+    nrcu_ctx* ctx = new nrcu_ctx();
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return NRCU_ERR_CUDA; }
+    ctx->own_stream = true;
+    cudaEventCreate(&ctx->ev_begin); cudaEventCreate(&ctx->ev_end);
+    *out = ctx;
+    return NRCU_OK;
+}
+
+int nrcu_destroy(nrcu_ctx* ctx) {
+    if (!ctx) return NRCU_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return NRCU_OK;
+}
+
+int nrcu_set_stream(nrcu_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return NRCU_OK;
+}
+
+int nrcu_synchronize(nrcu_ctx* ctx) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    CTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NRCU_OK;
+}
+
+void nrcu_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    u32x4 r = philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene upload
+// ---------------------------------------------------------------------------------------------
+static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord);
+
+int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    if (!sc || mode < NRCU_MODE_RAYCAST || mode > NRCU_MODE_ACC) { ctx->error = "nrcu_upload_scene: bad arguments"; return NRCU_ERR_INVALID; }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    ctx->have_scene = false;
+    HostPrep hp;
+    std::string why = host_prepare(sc, mode, hp);
+    if (!why.empty()) { ctx->error = "nrcu_upload_scene: " + why; return NRCU_ERR_INVALID; }
+    cudaEvent_t e0, e1;
+    CTX_CUDA(cudaEventCreate(&e0)); CTX_CUDA(cudaEventCreate(&e1));
+    CTX_CUDA(cudaEventRecord(e0, ctx->stream));
+    const uint32_t n = (uint32_t)hp.src_a.size();
+
+    // ---- upload sources -----------------------------------------------------------------------------
+    const uint32_t zero_off = 0;
+    int rc;
+#define UP(buf, ptr, cnt) if ((rc = upload(ctx, ctx->buf, ptr, cnt)) != NRCU_OK) return rc
+    UP(src_a, hp.src_a.data(), n); UP(src_b, hp.src_b.data(), n);
+    UP(sph_pos, hp.sph.data(), hp.sph.size()); UP(sph_rad, sc->sphere_radius, sc->n_spheres); UP(sph_mat, sc->sphere_material, sc->n_spheres);
+    UP(tri_v, hp.tri.data(), hp.tri.size()); UP(tri_n, sc->triangle_normal, 3 * (size_t)sc->n_triangles); UP(tri_mat, sc->triangle_material, sc->n_triangles);
+    UP(pl_n, sc->plane_normal, 3 * (size_t)sc->n_planes); UP(pl_p, hp.pln.data(), hp.pln.size());
+    UP(pl_u, sc->plane_u, 3 * (size_t)sc->n_planes); UP(pl_v, sc->plane_v, 3 * (size_t)sc->n_planes); UP(pl_mat, sc->plane_material, sc->n_planes);
+    UP(mesh_voff, sc->n_meshes ? sc->mesh_vertex_offset : &zero_off, (size_t)sc->n_meshes + 1);
+    UP(mesh_ioff, sc->n_meshes ? sc->mesh_index_offset : &zero_off, (size_t)sc->n_meshes + 1);
+    UP(mesh_pos, sc->mesh_positions, 3 * (size_t)hp.total_vertices); UP(mesh_idx, sc->mesh_indices, hp.total_indices); UP(mesh_mat, sc->mesh_material, sc->n_meshes);
+    UP(materials, hp.materials.data(), hp.materials.size());
+    UP(area_lights, hp.lights.data(), hp.lights.size());
+#undef UP
+    DScene& ds = ctx->ds;
+    fill_scene_scalars(ds, sc, mode, hp);
+    if (sc->ambient_type == NRCU_AMBIENT_ENVIRONMENT_MAP && sc->ambient_environment_map >= 0 &&
+        (uint32_t)sc->ambient_environment_map < sc->n_textures) {
+        uint32_t ti = (uint32_t)sc->ambient_environment_map;
+        size_t cnt = (size_t)sc->texture_width[ti] * sc->texture_height[ti];
+        if (cnt) {
+            if ((rc = upload(ctx, ctx->env, reinterpret_cast<const f4*>(sc->texture_rgba + sc->texture_offset[ti]), cnt)) != NRCU_OK) return rc;
+            ds.env_rgba = ctx->env.as<f4>(); ds.env_w = (int)sc->texture_width[ti]; ds.env_h = (int)sc->texture_height[ti];
+        }
+    }
+    // ---- mesh world transform on the device, once per MESH node, in node order --------------------------
+    for (uint32_t e : hp.mesh_nodes) {
+        uint32_t first = sc->mesh_vertex_offset[e], cnt = sc->mesh_vertex_offset[e + 1] - first;
+        if (!cnt) continue;
+        k_mesh_transform<<<grid_for(cnt, 256), 256, 0, ctx->stream>>>(ctx->mesh_pos.as<float>(), first, cnt);
+        CTX_LAUNCH_CHECK("k_mesh_transform");
+    }
+    // ---- flatten into the packed primitive records ----------------------------------------------------
+    PrimSources& ps = ctx->ps;
+    ps.src_a = ctx->src_a.as<uint32_t>(); ps.src_b = ctx->src_b.as<uint32_t>();
+    ps.sphere_position = ctx->sph_pos.as<float>(); ps.sphere_radius = ctx->sph_rad.as<float>(); ps.sphere_material = ctx->sph_mat.as<int>();
+    ps.triangle_vertices = ctx->tri_v.as<float>(); ps.triangle_normal = ctx->tri_n.as<float>(); ps.triangle_material = ctx->tri_mat.as<int>();
+    ps.plane_normal = ctx->pl_n.as<float>(); ps.plane_position = ctx->pl_p.as<float>(); ps.plane_u = ctx->pl_u.as<float>();
+    ps.plane_v = ctx->pl_v.as<float>(); ps.plane_material = ctx->pl_mat.as<int>();
+    ps.mesh_vertex_offset = ctx->mesh_voff.as<uint32_t>(); ps.mesh_index_offset = ctx->mesh_ioff.as<uint32_t>();
+    ps.mesh_positions = ctx->mesh_pos.as<float>(); ps.mesh_indices = ctx->mesh_idx.as<uint32_t>(); ps.mesh_material = ctx->mesh_mat.as<int>();
+    CTX_CUDA(ctx->prim_geom.ensure(sizeof(f4) * 3 * (size_t)std::max(n, 1u)));
+    CTX_CUDA(ctx->prim_shade.ensure(sizeof(f4) * (size_t)std::max(n, 1u)));
+    CTX_CUDA(ctx->prim_box.ensure(sizeof(f4) * 2 * (size_t)std::max(n, 1u)));
+    CTX_CUDA(ctx->prim_meta.ensure(sizeof(uint32_t) * (size_t)std::max(n, 1u)));
+    if (n) {
+        k_build_prims<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ps, n, mode == NRCU_MODE_RAYCAST, ctx->prim_geom.as<f4>(),
+                                                                 ctx->prim_shade.as<f4>(), ctx->prim_box.as<f4>(), ctx->prim_meta.as<uint32_t>(), nullptr);
+        CTX_LAUNCH_CHECK("k_build_prims");
+    }
+    ds.prim_geom = ctx->prim_geom.as<f4>(); ds.prim_shade = ctx->prim_shade.as<f4>(); ds.prim_box = ctx->prim_box.as<f4>();
+    ds.prim_meta = ctx->prim_meta.as<uint32_t>();
+    ds.materials = ctx->materials.as<DMaterial>();
+    ds.area_lights = ctx->area_lights.as<f4>();
+    ctx->spp = sc->samples_per_pixel;
+    ctx->mode = mode;
+    CTX_CUDA(cudaStreamSynchronize(ctx->stream));   // the pageable staging vectors in `hp` die with this scope
+
+    // ---- BVH ----------------------------------------------------------------------------------------
+    ctx->bvh_nodes = 0;
+    if (mode != NRCU_MODE_RAYCAST && n > 0) {
+        if ((rc = build_bvh(ctx, n, hp.max_abs_coord)) != NRCU_OK) return rc;
+    }
+    CTX_CUDA(cudaEventRecord(e1, ctx->stream));
+    CTX_CUDA(cudaEventSynchronize(e1));
+    CTX_CUDA(cudaEventElapsedTime(&ctx->ms_setup, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->have_scene = true;
+    return NRCU_OK;
+}
+
+static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
+    const int cap = 2 * (int)n + 2;
+    const int bin_nodes = std::max(64, (int)(0.4 * n) + 8);
+    DevBuf prim_node, nbox, cbox, ncount, nidmin, nidmax, nstate, nchild, nsplit_axis, nsplit_pos, ndepth, nleaf_first, nleaf_fill,
+        nwide, bins, counters, nbin_slot, wide_tmp;
+    CTX_CUDA(prim_node.ensure(sizeof(int) * (size_t)n));
+    CTX_CUDA(nbox.ensure(sizeof(int) * 6 * (size_t)cap)); CTX_CUDA(cbox.ensure(sizeof(int) * 6 * (size_t)cap));
+    DevBuf* per_node[] = {&ncount, &nidmin, &nidmax, &nstate, &nchild, &nsplit_axis, &nsplit_pos, &ndepth, &nleaf_first, &nleaf_fill, &nwide, &nbin_slot};
+    for (DevBuf* b : per_node) CTX_CUDA(b->ensure(sizeof(int) * (size_t)cap));
+    CTX_CUDA(bins.ensure(sizeof(int) * (size_t)bin_nodes * 3 * NRCU_NBINS * NRCU_BIN_WORDS));
+    CTX_CUDA(counters.ensure(sizeof(int) * 8));
+    CTX_CUDA(ctx->leaf_prims.ensure(sizeof(uint32_t) * (size_t)n));
+    CTX_CUDA(wide_tmp.ensure(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1u, n)));
+
+    BvhBuild b{};
+    b.n_prims = n; b.prim_box = ctx->prim_box.as<f4>(); b.prim_meta = ctx->prim_meta.as<uint32_t>();
+    b.prim_node = prim_node.as<int>(); b.nbox = nbox.as<int>(); b.cbox = cbox.as<int>(); b.ncount = ncount.as<int>();
+    b.nidmin = nidmin.as<int>(); b.nidmax = nidmax.as<int>(); b.nstate = nstate.as<int>(); b.nchild = nchild.as<int>();
+    b.nsplit_axis = nsplit_axis.as<int>(); b.nsplit_pos = nsplit_pos.as<float>(); b.ndepth = ndepth.as<int>();
+    b.nleaf_first = nleaf_first.as<int>(); b.nleaf_fill = nleaf_fill.as<int>(); b.nwide = nwide.as<int>();
+    b.bins = bins.as<int>(); b.bin_nodes = bin_nodes; b.counters = counters.as<int>(); b.nbin_slot = nbin_slot.as<int>();
+    b.leaf_prims = ctx->leaf_prims.as<uint32_t>(); b.wide_nodes = wide_tmp.as<f4>();
+    b.inflate = max_abs_coord * (1.0f / 65536.0f);
+    cudaStream_t st = ctx->stream;
+    const int T = 128;
+
+    int h_counters[8] = {1, 0, 0, 0, 0, 0, 0, 0};   // node count starts at 1 (the root)
+    CTX_CUDA(cudaMemcpyAsync(counters.p, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
+    k_bvh_clear<<<grid_for(cap, T), T, 0, st>>>(b, 0, cap); CTX_LAUNCH_CHECK("k_bvh_clear");
+    k_bvh_init_prim<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_init_prim");
+    int begin = 0, end = 1;
+    for (int level = 0; level < 128; level++) {
+        b.level_begin = begin; b.level_end = end;
+        CTX_CUDA(cudaMemsetAsync(counters.as<int>() + 3, 0, 2 * sizeof(int), st));
+        k_bvh_level_prepare<<<grid_for(end - begin, T), T, 0, st>>>(b, begin, end - begin); CTX_LAUNCH_CHECK("k_bvh_level_prepare");
+        k_bvh_bin<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_bin");
+        k_bvh_split<<<grid_for(end - begin, T), T, 0, st>>>(b, begin, end - begin); CTX_LAUNCH_CHECK("k_bvh_split");
+        CTX_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        CTX_CUDA(cudaStreamSynchronize(st));
+        if (h_counters[3] == 0) break;
+        k_bvh_partition<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_partition");
+        begin = end; end = h_counters[0];
+    }
+    const int n_nodes = h_counters[0];
+    k_bvh_leaf_alloc<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_leaf_alloc");
+    k_bvh_leaf_fill<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_leaf_fill");
+    k_bvh_leaf_sort<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_leaf_sort");
+    k_bvh_wide_index<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_wide_index");
+    k_bvh_wide_emit<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_wide_emit");
+    // root reference: wide index of node 0, or a leaf reference when the whole scene fits one leaf
+    int root_state = 0, root_wide = -1, root_cnt = 0, root_first = 0;
+    CTX_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaMemcpyAsync(&root_state, nstate.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaMemcpyAsync(&root_wide, nwide.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaMemcpyAsync(&root_cnt, ncount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaMemcpyAsync(&root_first, nleaf_first.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaStreamSynchronize(st));
+    const int n_wide = h_counters[2];
+    CTX_CUDA(ctx->nodes.ensure(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1, n_wide)));
+    if (n_wide) CTX_CUDA(cudaMemcpyAsync(ctx->nodes.p, wide_tmp.p, sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)n_wide, cudaMemcpyDeviceToDevice, st));
+    CTX_CUDA(cudaStreamSynchronize(st));
+    ctx->ds.nodes = ctx->nodes.as<f4>();
+    ctx->ds.leaf_prims = ctx->leaf_prims.as<uint32_t>();
+    ctx->ds.root_ref = root_state == BNODE_LEAF ? ~((root_first << 4) | (root_cnt - 1)) : root_wide;
+    ctx->bvh_nodes = (uint32_t)n_wide;
+    return NRCU_OK;
+}
+
+int nrcu_primitive_count(const nrcu_ctx* ctx, uint32_t* out) {
+    if (!ctx || !out) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) return NRCU_ERR_STATE;
+    *out = ctx->ds.n_prims;
+    return NRCU_OK;
+}
+
+int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16, int32_t* material) {
+    nrcu_ctx* ctx = const_cast<nrcu_ctx*>(cctx);
+    if (!ctx) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) { ctx->error = "no scene uploaded"; return NRCU_ERR_STATE; }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->ds.n_prims;
+    if (!n) return NRCU_OK;
+    if (data16) {
+        DevBuf ex, g, s, bx, mt;   // scratch outputs so the live scene is not disturbed
+        CTX_CUDA(ex.ensure(sizeof(float) * 16 * (size_t)n)); CTX_CUDA(g.ensure(sizeof(f4) * 3 * (size_t)n));
+        CTX_CUDA(s.ensure(sizeof(f4) * (size_t)n)); CTX_CUDA(bx.ensure(sizeof(f4) * 2 * (size_t)n)); CTX_CUDA(mt.ensure(sizeof(uint32_t) * (size_t)n));
+        k_build_prims<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->ps, n, ctx->mode == NRCU_MODE_RAYCAST, g.as<f4>(), s.as<f4>(), bx.as<f4>(), mt.as<uint32_t>(), ex.as<float>());
+        CTX_LAUNCH_CHECK("k_build_prims");
+        CTX_CUDA(cudaMemcpyAsync(data16, ex.p, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (kind || material) {
+        std::vector<uint32_t> meta(n);
+        CTX_CUDA(cudaMemcpyAsync(meta.data(), ctx->prim_meta.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t i = 0; i < n; i++) { if (kind) kind[i] = meta[i] & 3u; if (material) material[i] = (int32_t)(meta[i] >> 2); }
+    }
+    return NRCU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rendering
+// ---------------------------------------------------------------------------------------------
+enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, then [depth+1] fetch cursors */ };
+
+static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth) {
+    for (int k = 0; k < 2; k++) {
+        CTX_CUDA(ctx->qa[k].ensure(sizeof(f4) * (size_t)capacity));
+        CTX_CUDA(ctx->qb[k].ensure(sizeof(f4) * (size_t)capacity));
+        CTX_CUDA(ctx->qc[k].ensure(sizeof(f4) * (size_t)capacity));
+    }
+    CTX_CUDA(ctx->hits.ensure(sizeof(float2) * (size_t)capacity));
+    CTX_CUDA(ctx->L.ensure(sizeof(f4) * (size_t)slots));
+    CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 2 * (size_t)depth + 8)));
+    ctx->queue_capacity = capacity; ctx->wave_slots = slots;
+    return NRCU_OK;
+}
+
+static int sm_count(int device) {
+    static int cached[64] = {0};
+    if (device < 64 && cached[device]) return cached[device];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (device < 64) cached[device] = n;
+    return n;
+}
+
+static cudaEvent_t pool_event(nrcu_ctx* ctx, size_t i) {
+    while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+    return ctx->ev_pool[i];
+}
+
+static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats) {
+    const DScene& ds = ctx->ds;
+    const uint32_t npix = ds.width * ds.height;
+    uint32_t s0 = params ? params->sample_begin : 0, s1 = params ? params->sample_end : 0;
+    if (s0 == 0 && s1 == 0) s1 = ctx->spp;
+    if (s1 < s0) { ctx->error = "sample_end < sample_begin"; return NRCU_ERR_INVALID; }
+    const uint64_t seed = params ? params->seed : 0;
+    const int glass_branch = params && params->glass_mode == NRCU_GLASS_BRANCH;
+    // wave size: k samples of every pixel, about 8M paths in flight
+    uint32_t k = params ? params->samples_per_wave : 0;
+    if (k == 0) k = std::max<uint32_t>(1, (8u << 20) / npix);
+    k = std::min<uint32_t>(k, std::max<uint32_t>(1, s1 - s0));
+    if ((uint64_t)k * npix > 0x7fffffffull) k = std::max<uint32_t>(1, (uint32_t)(0x7fffffffull / npix));
+    const uint32_t slots = k * npix;
+    const uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
+    int rc;
+    if ((rc = ensure_wave(ctx, slots, capacity, ds.depth)) != NRCU_OK) return rc;
+    PathQueue q[2] = {{ctx->qa[0].as<f4>(), ctx->qb[0].as<f4>(), ctx->qc[0].as<f4>()}, {ctx->qa[1].as<f4>(), ctx->qb[1].as<f4>(), ctx->qc[1].as<f4>()}};
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    unsigned long long* d_rays = reinterpret_cast<unsigned long long*>(cnt + CNT_RAYS);
+    uint32_t* d_qn = cnt + CNT_QUEUE0;                 // queue size entering bounce d
+    uint32_t* d_fetch = cnt + CNT_QUEUE0 + ds.depth + 2;  // work-fetch cursor of bounce d
+    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 2 * (size_t)ds.depth + 8);
+    cudaStream_t st = ctx->stream;
+    const int sms = sm_count(ctx->device);
+    const unsigned trace_grid = (unsigned)sms * 8, shade_grid = (unsigned)sms * 4;
+    const bool timing = stats != nullptr;
+    size_t ev_i = 0;
+    struct Span { size_t a, b; int kind; };
+    std::vector<Span> spans;
+    CTX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * CNT_QUEUE0, st));
+    if (timing) CTX_CUDA(cudaEventRecord(ctx->ev_begin, st));
+    uint64_t launches0 = ctx->launches;
+    for (uint32_t w0 = s0; w0 < s1; w0 += k) {
+        const uint32_t kw = std::min(k, s1 - w0), n_slots = kw * npix;
+        CTX_CUDA(cudaMemsetAsync(cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
+        k_raygen<<<grid_for(n_slots, 256), 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn);
+        CTX_LAUNCH_CHECK("k_raygen");
+        for (uint32_t d = 0; d < ds.depth; d++) {
+            PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
+            if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
+            if (ctx->mode == NRCU_MODE_ACC)
+                k_trace<true><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
+            else
+                k_trace<false><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
+            CTX_LAUNCH_CHECK("k_trace");
+            if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
+            k_shade<<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, ctx->hits.as<float2>(), qo, d_qn + d + 1, capacity, ctx->L.as<f4>());
+            CTX_LAUNCH_CHECK("k_shade");
+            if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
+            k_clamp_count<<<1, 1, 0, st>>>(d_qn + d + 1, capacity, cnt + CNT_HIGH_WATER);
+            CTX_LAUNCH_CHECK("k_clamp_count");
+        }
+        k_accumulate<<<grid_for(npix, 256), 256, 0, st>>>(ctx->L.as<f4>(), d_accum, npix, kw);
+        CTX_LAUNCH_CHECK("k_accumulate");
+    }
+    if (timing) {
+        CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
+        uint32_t h_cnt[CNT_QUEUE0];
+        CTX_CUDA(cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        CTX_CUDA(cudaStreamSynchronize(st));
+        std::memset(stats, 0, sizeof(*stats));
+        CTX_CUDA(cudaEventElapsedTime(&stats->ms_total, ctx->ev_begin, ctx->ev_end));
+        for (auto& sp : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]);
+            (sp.kind == 0 ? stats->ms_trace : stats->ms_shade) += ms;
+        }
+        unsigned long long rays; std::memcpy(&rays, h_cnt + CNT_RAYS, 8);
+        stats->rays = rays; stats->paths = (uint64_t)npix * (s1 - s0);
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
+        stats->max_queue = h_cnt[CNT_HIGH_WATER];
+    }
+    return NRCU_OK;
+}
+
+int nrcu_render_accumulate(nrcu_ctx* ctx, const nrcu_render_params* params, float* d_accum, nrcu_stats* stats) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) { ctx->error = "nrcu_render_accumulate: no scene uploaded"; return NRCU_ERR_STATE; }
+    if (!d_accum) { ctx->error = "d_accum is null"; return NRCU_ERR_INVALID; }
+    if (ctx->mode == NRCU_MODE_RAYCAST) { ctx->error = "RayCast mode has no sample accumulation; use nrcu_render"; return NRCU_ERR_STATE; }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    return render_pt(ctx, params, reinterpret_cast<f4*>(d_accum), stats);
+}
+
+int nrcu_resolve(nrcu_ctx* ctx, const float* d_accum, float* d_rgba) {
+    if (!ctx || !d_accum || !d_rgba) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) { ctx->error = "nrcu_resolve: no scene uploaded"; return NRCU_ERR_STATE; }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t npix = ctx->ds.width * ctx->ds.height;
+    k_resolve<<<grid_for(npix, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const f4*>(d_accum), reinterpret_cast<f4*>(d_rgba), npix);
+    CTX_LAUNCH_CHECK("k_resolve");
+    return NRCU_OK;
+}
+
+int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out, nrcu_stats* stats) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) { ctx->error = "nrcu_render: no scene uploaded"; return NRCU_ERR_STATE; }
+    if (!rgba_out) { ctx->error = "rgba_out is null"; return NRCU_ERR_INVALID; }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    const DScene& ds = ctx->ds;
+    const uint32_t npix = ds.width * ds.height;
+    cudaStream_t st = ctx->stream;
+    CTX_CUDA(ctx->rgba_dev.ensure(sizeof(f4) * (size_t)npix));
+    if (ctx->mode == NRCU_MODE_RAYCAST) {
+        CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * 64));
+        unsigned long long* d_rays = ctx->counters.as<unsigned long long>();
+        CTX_CUDA(cudaMemsetAsync(d_rays, 0, 8, st));
+        uint64_t launches0 = ctx->launches;
+        CTX_CUDA(cudaEventRecord(ctx->ev_begin, st));
+        k_raycast<<<grid_for(npix, 128), 128, 0, st>>>(ds, ctx->rgba_dev.as<f4>(), d_rays);
+        CTX_LAUNCH_CHECK("k_raycast");
+        CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
+        CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+        unsigned long long rays = 0;
+        CTX_CUDA(cudaMemcpyAsync(&rays, d_rays, 8, cudaMemcpyDeviceToHost, st));
+        CTX_CUDA(cudaStreamSynchronize(st));
+        if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
+            CTX_CUDA(cudaEventElapsedTime(&stats->ms_total, ctx->ev_begin, ctx->ev_end));
+            stats->ms_trace = stats->ms_total; stats->rays = rays; stats->paths = npix;
+            stats->kernel_launches = ctx->launches - launches0; stats->ms_setup = ctx->ms_setup; stats->n_primitives = ds.n_prims;
+        }
+        return NRCU_OK;
+    }
+    CTX_CUDA(ctx->accum_own.ensure(sizeof(f4) * (size_t)npix));
+    CTX_CUDA(cudaMemsetAsync(ctx->accum_own.p, 0, sizeof(f4) * (size_t)npix, st));
+    nrcu_render_params p{};
+    if (params) p = *params;
+    p.sample_begin = 0; p.sample_end = 0;   // whole frame
+    int rc = render_pt(ctx, &p, ctx->accum_own.as<f4>(), stats);
+    if (rc != NRCU_OK) return rc;
+    k_resolve<<<grid_for(npix, 256), 256, 0, st>>>(ctx->accum_own.as<f4>(), ctx->rgba_dev.as<f4>(), npix);
+    CTX_LAUNCH_CHECK("k_resolve");
+    if (stats) stats->kernel_launches++;
+    CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaStreamSynchronize(st));
+    return NRCU_OK;
+}
+
+int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim_id, float* t) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) { ctx->error = "nrcu_trace_batch: no scene uploaded"; return NRCU_ERR_STATE; }
+    if (n == 0) return NRCU_OK;
+    if (!rays) { ctx->error = "rays is null"; return NRCU_ERR_INVALID; }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf d_rays, qa, qb, hits, cnt;
+    CTX_CUDA(d_rays.ensure(sizeof(float) * 6 * (size_t)n)); CTX_CUDA(qa.ensure(sizeof(f4) * (size_t)n)); CTX_CUDA(qb.ensure(sizeof(f4) * (size_t)n));
+    CTX_CUDA(hits.ensure(sizeof(float2) * (size_t)n)); CTX_CUDA(cnt.ensure(32));
+    CTX_CUDA(cudaMemcpyAsync(d_rays.p, rays, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, st));
+    uint32_t h_cnt[8] = {0, 0, n, 0, 0, 0, 0, 0};   // [0..1] ray counter, [2] n, [3] fetch cursor
+    CTX_CUDA(cudaMemcpyAsync(cnt.p, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
+    PathQueue q{qa.as<f4>(), qb.as<f4>(), nullptr};
+    k_pack_rays<<<grid_for(n, 256), 256, 0, st>>>(d_rays.as<float>(), n, q);
+    CTX_LAUNCH_CHECK("k_pack_rays");
+    uint32_t* c = cnt.as<uint32_t>();
+    const unsigned trace_grid = (unsigned)sm_count(ctx->device) * 8;
+    if (ctx->mode == NRCU_MODE_RAYCAST) k_trace_linear_rc<<<grid_for(n, 128), 128, 0, st>>>(ctx->ds, q, n, hits.as<float2>());
+    else if (ctx->mode == NRCU_MODE_ACC) k_trace<true><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
+    else k_trace<false><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
+    CTX_LAUNCH_CHECK("k_trace");
+    std::vector<float2> h(n);
+    CTX_CUDA(cudaMemcpyAsync(h.data(), hits.p, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n; i++) {
+        int id; std::memcpy(&id, &h[i].y, 4);
+        if (prim_id) prim_id[i] = id;
+        if (t) t[i] = h[i].x;
+    }
+    return NRCU_OK;
+}
+
+}  // extern "C"

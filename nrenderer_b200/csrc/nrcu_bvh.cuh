@@ -1,0 +1,282 @@
+// nrcu_bvh.cuh — GPU binned-SAH BVH build + emission of the 4-wide node layout.
+//
+// Replaces BVHTree::build (reference code/components/acc_path_tracing/include/BVH.hpp:166-222:
+// recursive median split, one primitive per leaf, never pruned by t).  Input: the per-primitive
+// boxes (the reference's own Bounds3 definitions, Bounds3.hpp:35-103).  The build is breadth
+// first, one level per round of three kernels, primitives are never moved — each carries the id
+// of the binary node it currently belongs to:
+//   bin       every primitive of a node with > LEAF_MAX primitives adds its box to 3 x NBINS bins
+//             of that node (atomic min/max on order-preserving int keys)
+//   split     one thread per node of the level sweeps the bins, picks the minimum-SAH plane over
+//             the three axes (falls back to a primitive-id median when all centroids coincide)
+//             and allocates two children
+//   partition every primitive moves to its child and grows the child's box / centroid box
+// Then leaves get contiguous ranges of `leaf_prims`, and every binary inner node at even depth
+// becomes one BVH4 node whose slots are its grandchildren (or children that are leaves).
+// Each step body is a __host__ __device__ function of the work-item index so that
+// tests/host_emu can run the identical code sequentially on the CPU.
+#pragma once
+#include "nrcu_scene.cuh"
+
+namespace nrcu {
+
+#define NRCU_NBINS 16
+#define NRCU_BIN_WORDS 7   // 6 encoded bounds + count
+
+// order-preserving float <-> int key (so that integer atomicMin/Max order floats)
+NR_HD int fkey(float f) { int i = f2i(f); return i >= 0 ? i : (i ^ 0x7fffffff); }
+NR_HD float fkey_inv(int k) { return i2f(k >= 0 ? k : (k ^ 0x7fffffff)); }
+#define NRCU_KEY_POS_INF 0x7f800000
+#define NRCU_KEY_NEG_INF ((int)(0xff800000u ^ 0x7fffffffu))
+
+NR_HD int atomic_add_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    int o = *p; *p = o + v; return o;
+#endif
+}
+NR_HD void atomic_min_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+NR_HD void atomic_max_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+
+enum { BNODE_OPEN = 0, BNODE_LEAF = 1, BNODE_INNER = 2 };
+
+struct BvhBuild {
+    uint32_t n_prims;
+    const f4* prim_box;        // 2 per primitive
+    const uint32_t* prim_meta; // kind | material << 2
+    int* prim_node;            // [n_prims] binary node of each primitive
+    // binary nodes, capacity 2*n_prims + 2
+    int* nbox;                 // [cap*6] encoded bounds  (min xyz, max xyz)
+    int* cbox;                 // [cap*6] encoded centroid bounds
+    int* ncount;               // [cap]
+    int* nidmin; int* nidmax;  // [cap] primitive id range (fallback split)
+    int* nstate;               // [cap] BNODE_*
+    int* nchild;               // [cap] index of the left child (right = +1)
+    int* nsplit_axis;          // [cap] 0..2 spatial, 3 = id median
+    float* nsplit_pos;         // [cap] centroid threshold: left iff centroid[axis] < pos (or id <= pos bits)
+    int* ndepth;               // [cap]
+    int* nleaf_first;          // [cap] first slot in leaf_prims
+    int* nleaf_fill;           // [cap]
+    int* nwide;                // [cap] wide node index of even-depth inner nodes
+    int* bins;                 // [bin_nodes * 3 * NBINS * BIN_WORDS]
+    int bin_nodes;             // capacity of `bins` in nodes
+    int* counters;             // [0] node count, [1] leaf cursor, [2] wide count, [3] splits in this level, [4] bin-slot cursor
+    int* nbin_slot;            // [cap] bin slot of a node in the current level
+    int level_begin, level_end;
+    // outputs
+    uint32_t* leaf_prims;      // [n_prims]
+    f4* wide_nodes;            // [wide capacity * 7]
+    float inflate;             // absolute padding of wide-node boxes
+};
+
+NR_HD vec3 box_centroid(f4 lo, f4 hi) { return mk3(0.5f * lo.x + 0.5f * hi.x, 0.5f * lo.y + 0.5f * hi.y, 0.5f * lo.z + 0.5f * hi.z); }
+
+NR_HD void node_clear(const BvhBuild& b, int n) {
+    for (int k = 0; k < 3; k++) {
+        b.nbox[n * 6 + k] = NRCU_KEY_POS_INF; b.nbox[n * 6 + 3 + k] = NRCU_KEY_NEG_INF;
+        b.cbox[n * 6 + k] = NRCU_KEY_POS_INF; b.cbox[n * 6 + 3 + k] = NRCU_KEY_NEG_INF;
+    }
+    b.ncount[n] = 0; b.nidmin[n] = 0x7fffffff; b.nidmax[n] = -1; b.nstate[n] = BNODE_OPEN; b.nchild[n] = -1;
+    b.nsplit_axis[n] = 0; b.nsplit_pos[n] = 0.f; b.nleaf_first[n] = 0; b.nleaf_fill[n] = 0; b.nwide[n] = -1; b.nbin_slot[n] = -1;
+    if (n == 0) b.ndepth[n] = 0;
+}
+
+NR_HD void node_add_prim(const BvhBuild& b, int n, int i) {
+    f4 lo = b.prim_box[2 * i], hi = b.prim_box[2 * i + 1];
+    vec3 c = box_centroid(lo, hi);
+    atomic_min_i(&b.nbox[n * 6 + 0], fkey(lo.x)); atomic_min_i(&b.nbox[n * 6 + 1], fkey(lo.y)); atomic_min_i(&b.nbox[n * 6 + 2], fkey(lo.z));
+    atomic_max_i(&b.nbox[n * 6 + 3], fkey(hi.x)); atomic_max_i(&b.nbox[n * 6 + 4], fkey(hi.y)); atomic_max_i(&b.nbox[n * 6 + 5], fkey(hi.z));
+    atomic_min_i(&b.cbox[n * 6 + 0], fkey(c.x)); atomic_min_i(&b.cbox[n * 6 + 1], fkey(c.y)); atomic_min_i(&b.cbox[n * 6 + 2], fkey(c.z));
+    atomic_max_i(&b.cbox[n * 6 + 3], fkey(c.x)); atomic_max_i(&b.cbox[n * 6 + 4], fkey(c.y)); atomic_max_i(&b.cbox[n * 6 + 5], fkey(c.z));
+    atomic_add_i(&b.ncount[n], 1);
+    atomic_min_i(&b.nidmin[n], i); atomic_max_i(&b.nidmax[n], i);
+}
+
+// step 0: one work item per primitive
+NR_HD void bvh_init_prim(const BvhBuild& b, int i) { b.prim_node[i] = 0; node_add_prim(b, 0, i); }
+
+// step A (per node of the level): decide leaf / open and hand out a bin slot
+NR_HD void bvh_level_prepare(const BvhBuild& b, int n) {
+    if (b.ncount[n] <= NRCU_LEAF_MAX) { b.nstate[n] = BNODE_LEAF; return; }
+    int slot = atomic_add_i(&b.counters[4], 1);
+    b.nbin_slot[n] = slot;
+    if (slot < b.bin_nodes) {
+        int* bn = b.bins + (size_t)slot * 3 * NRCU_NBINS * NRCU_BIN_WORDS;
+        for (int k = 0; k < 3 * NRCU_NBINS; k++) {
+            int* w = bn + k * NRCU_BIN_WORDS;
+            w[0] = w[1] = w[2] = NRCU_KEY_POS_INF; w[3] = w[4] = w[5] = NRCU_KEY_NEG_INF; w[6] = 0;
+        }
+    }
+}
+
+NR_HD int bin_of(float c, float lo, float hi) {
+    float ext = hi - lo;
+    if (!(ext > 0.f)) return 0;
+    int k = (int)((c - lo) * ((float)NRCU_NBINS / ext));
+    return k < 0 ? 0 : (k > NRCU_NBINS - 1 ? NRCU_NBINS - 1 : k);
+}
+
+// step B (per primitive)
+NR_HD void bvh_bin(const BvhBuild& b, int i) {
+    int n = b.prim_node[i];
+    if (n < b.level_begin || b.nstate[n] != BNODE_OPEN) return;
+    int slot = b.nbin_slot[n];
+    if (slot < 0 || slot >= b.bin_nodes) return;
+    f4 lo = b.prim_box[2 * i], hi = b.prim_box[2 * i + 1];
+    vec3 c = box_centroid(lo, hi);
+    int* bn = b.bins + (size_t)slot * 3 * NRCU_NBINS * NRCU_BIN_WORDS;
+    for (int a = 0; a < 3; a++) {
+        float clo = fkey_inv(b.cbox[n * 6 + a]), chi = fkey_inv(b.cbox[n * 6 + 3 + a]);
+        int k = bin_of(comp(c, a), clo, chi);
+        int* w = bn + (a * NRCU_NBINS + k) * NRCU_BIN_WORDS;
+        atomic_min_i(&w[0], fkey(lo.x)); atomic_min_i(&w[1], fkey(lo.y)); atomic_min_i(&w[2], fkey(lo.z));
+        atomic_max_i(&w[3], fkey(hi.x)); atomic_max_i(&w[4], fkey(hi.y)); atomic_max_i(&w[5], fkey(hi.z));
+        atomic_add_i(&w[6], 1);
+    }
+}
+
+NR_HD float half_area(const float* lo, const float* hi) {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// step C (per node of the level): choose the split and allocate the children
+NR_HD void bvh_split(const BvhBuild& b, int n) {
+    if (b.nstate[n] != BNODE_OPEN) return;
+    int slot = b.nbin_slot[n];
+    int best_axis = -1, best_k = 0;
+    float best_cost = NRCU_INF;
+    if (slot >= 0 && slot < b.bin_nodes) {
+        const int* bn = b.bins + (size_t)slot * 3 * NRCU_NBINS * NRCU_BIN_WORDS;
+        for (int a = 0; a < 3; a++) {
+            float clo = fkey_inv(b.cbox[n * 6 + a]), chi = fkey_inv(b.cbox[n * 6 + 3 + a]);
+            if (!(chi > clo)) continue;
+            // suffix sweep: right_area[k] = SAH term of bins [k, NBINS)
+            float r_area[NRCU_NBINS]; int r_cnt[NRCU_NBINS];
+            float lo[3] = {NRCU_INF, NRCU_INF, NRCU_INF}, hi[3] = {-NRCU_INF, -NRCU_INF, -NRCU_INF};
+            int cnt = 0;
+            for (int k = NRCU_NBINS - 1; k >= 1; k--) {
+                const int* w = bn + (a * NRCU_NBINS + k) * NRCU_BIN_WORDS;
+                if (w[6] > 0) {
+                    for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], fkey_inv(w[c])); hi[c] = fmaxf(hi[c], fkey_inv(w[3 + c])); }
+                    cnt += w[6];
+                }
+                r_cnt[k] = cnt; r_area[k] = cnt > 0 ? half_area(lo, hi) : 0.f;
+            }
+            float llo[3] = {NRCU_INF, NRCU_INF, NRCU_INF}, lhi[3] = {-NRCU_INF, -NRCU_INF, -NRCU_INF};
+            int lcnt = 0;
+            for (int k = 0; k < NRCU_NBINS - 1; k++) {   // split after bin k
+                const int* w = bn + (a * NRCU_NBINS + k) * NRCU_BIN_WORDS;
+                if (w[6] > 0) {
+                    for (int c = 0; c < 3; c++) { llo[c] = fminf(llo[c], fkey_inv(w[c])); lhi[c] = fmaxf(lhi[c], fkey_inv(w[3 + c])); }
+                    lcnt += w[6];
+                }
+                int rc = r_cnt[k + 1];
+                if (lcnt == 0 || rc == 0) continue;
+                float cost = half_area(llo, lhi) * (float)lcnt + r_area[k + 1] * (float)rc;
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_k = k; }
+            }
+        }
+    }
+    int c = atomic_add_i(&b.counters[0], 2);
+    b.nchild[n] = c; b.nstate[n] = BNODE_INNER;
+    b.ndepth[c] = b.ndepth[n] + 1; b.ndepth[c + 1] = b.ndepth[n] + 1;
+    atomic_add_i(&b.counters[3], 1);
+    if (best_axis >= 0) {
+        float clo = fkey_inv(b.cbox[n * 6 + best_axis]), chi = fkey_inv(b.cbox[n * 6 + 3 + best_axis]);
+        b.nsplit_axis[n] = best_axis;
+        b.nsplit_pos[n] = (float)(best_k + 1);   // bin boundary: left iff bin_of(c) <= best_k
+        (void)clo; (void)chi;
+    } else {
+        b.nsplit_axis[n] = 3;
+        b.nsplit_pos[n] = i2f((b.nidmin[n] >> 1) + (b.nidmax[n] >> 1));   // id median, stored as bits
+    }
+}
+
+// step D (per primitive)
+NR_HD void bvh_partition(const BvhBuild& b, int i) {
+    int n = b.prim_node[i];
+    if (n < b.level_begin || b.nstate[n] != BNODE_INNER) return;
+    int side;
+    int a = b.nsplit_axis[n];
+    if (a == 3) side = (i <= f2i(b.nsplit_pos[n])) ? 0 : 1;
+    else {
+        f4 lo = b.prim_box[2 * i], hi = b.prim_box[2 * i + 1];
+        vec3 c = box_centroid(lo, hi);
+        float clo = fkey_inv(b.cbox[n * 6 + a]), chi = fkey_inv(b.cbox[n * 6 + 3 + a]);
+        side = ((float)bin_of(comp(c, a), clo, chi) < b.nsplit_pos[n]) ? 0 : 1;
+    }
+    int child = b.nchild[n] + side;
+    b.prim_node[i] = child;
+    node_add_prim(b, child, i);
+}
+
+// leaves: per node, then per primitive, then per node (sort ids for a deterministic layout)
+NR_HD void bvh_leaf_alloc(const BvhBuild& b, int n) {
+    if (b.nstate[n] != BNODE_LEAF) return;
+    b.nleaf_first[n] = atomic_add_i(&b.counters[1], b.ncount[n]);
+}
+NR_HD void bvh_leaf_fill(const BvhBuild& b, int i) {
+    int n = b.prim_node[i];
+    int pos = b.nleaf_first[n] + atomic_add_i(&b.nleaf_fill[n], 1);
+    b.leaf_prims[pos] = ((uint32_t)i << 2) | (b.prim_meta[i] & 3u);
+}
+NR_HD void bvh_leaf_sort(const BvhBuild& b, int n) {
+    if (b.nstate[n] != BNODE_LEAF) return;
+    uint32_t* p = b.leaf_prims + b.nleaf_first[n];
+    int c = b.ncount[n];
+    for (int i = 1; i < c; i++) { uint32_t v = p[i]; int j = i - 1; while (j >= 0 && p[j] > v) { p[j + 1] = p[j]; j--; } p[j + 1] = v; }
+}
+
+NR_HD int leaf_ref(const BvhBuild& b, int n) { return ~((b.nleaf_first[n] << 4) | (b.ncount[n] - 1)); }
+
+// wide emission, pass 1 (per binary node): hand out wide indices
+NR_HD void bvh_wide_index(const BvhBuild& b, int n) {
+    if (b.nstate[n] == BNODE_INNER && (b.ndepth[n] & 1) == 0) b.nwide[n] = atomic_add_i(&b.counters[2], 1);
+}
+// pass 2 (per binary node): fill the node
+NR_HD void bvh_wide_emit(const BvhBuild& b, int n) {
+    if (b.nwide[n] < 0) return;
+    int slots[4]; int ns = 0;
+    for (int s = 0; s < 2; s++) {
+        int c = b.nchild[n] + s;
+        if (b.nstate[c] == BNODE_LEAF) { if (b.ncount[c] > 0) slots[ns++] = c; }
+        else { for (int g = 0; g < 2; g++) { int gc = b.nchild[c] + g; if (b.nstate[gc] != BNODE_LEAF || b.ncount[gc] > 0) slots[ns++] = gc; } }
+    }
+    float lo[3][4], hi[3][4]; int ref[4];
+    for (int k = 0; k < 4; k++) {
+        if (k < ns) {
+            int c = slots[k];
+            for (int a = 0; a < 3; a++) {
+                float l = fkey_inv(b.nbox[c * 6 + a]), h = fkey_inv(b.nbox[c * 6 + 3 + a]);
+                float pad = b.inflate + 1e-6f * fmaxf(fabsf(l), fabsf(h));
+                lo[a][k] = l - pad; hi[a][k] = h + pad;
+            }
+            ref[k] = b.nstate[c] == BNODE_LEAF ? leaf_ref(b, c) : b.nwide[c];
+        } else {
+            for (int a = 0; a < 3; a++) { lo[a][k] = NRCU_INF; hi[a][k] = NRCU_INF; }   // never entered (see closest_hit_bvh)
+            ref[k] = NRCU_REF_EMPTY;
+        }
+    }
+    f4* w = b.wide_nodes + (size_t)b.nwide[n] * NRCU_BVH_NODE_F4;
+    for (int a = 0; a < 3; a++) {
+        w[2 * a] = mk4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+        w[2 * a + 1] = mk4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    }
+    w[6] = mk4(i2f(ref[0]), i2f(ref[1]), i2f(ref[2]), i2f(ref[3]));
+}
+
+}  // namespace nrcu

@@ -1,0 +1,223 @@
+// nrcu_intersect.cuh — ray/primitive tests on the packed device records + wide-BVH traversal.
+//
+// The primitive tests reproduce, operation for operation, the reference's
+//   Intersection::xTriangle / xSphere / xPlane / xAreaLight
+//     RayCast variant : code/components/ray_cast/src/intersections/intersections.cpp:5-93
+//     path tracers    : code/components/acc_path_tracing/src/intersections/intersections.cpp:5-94
+// (template parameter RC selects the RayCast variant: exclusive lower bound t <= tMin), so hit
+// decisions and t values are bit-identical to the CPU components.  Only t is returned: the hit point
+// (ray.at(t)) and the normal are recomputed from the same ray by the shading kernel.
+//
+// closest_hit_bvh() is the replacement for closestHitObject (SimplePathTracer.cpp:104-129,
+// AccPathTracer.cpp:87-99 -> BVHTree::getIntersect BVH.hpp:93-164): inner nodes are culled with a
+// conservative slab test, the exact reference tests run only at the leaves, and equal-t ties go to
+// the lowest primitive id, which is what the reference's in-order loops produce.
+#pragma once
+#include "nrcu_scene.cuh"
+
+namespace nrcu {
+
+// ---- exact primitive tests -------------------------------------------------------------------
+template <bool RC>
+NR_HD bool t_in_range(float t, float tmin, float tmax) {
+    if (RC) return !(t >= tmax || t <= tmin);
+    return !(t >= tmax || t < tmin);
+}
+
+template <bool RC>
+NR_HD bool x_triangle(const Ray& ray, f4 g0, f4 g1, f4 g2, float tmin, float tmax, float& t_out) {
+    vec3 v1 = mk3(g0.x, g0.y, g0.z), e1 = mk3(g0.w, g1.x, g1.y), e2 = mk3(g1.z, g1.w, g2.x);
+    vec3 P = cross(ray.d, e2);
+    float det = dot(e1, P);
+    vec3 T;
+    if (det > 0) T = ray.o - v1; else { T = v1 - ray.o; det = -det; }
+    if (det < 0.000001f) return false;
+    float u = dot(T, P);
+    if (u > det || u < 0.f) return false;
+    vec3 Q = cross(T, e1);
+    float v = dot(ray.d, Q);
+    if (v < 0.f || v + u > det) return false;
+    float w = dot(e2, Q);
+    float inv_det = 1.f / det;
+    w *= inv_det;
+    if (!t_in_range<RC>(w, tmin, tmax)) return false;
+    t_out = w;
+    return true;
+}
+
+template <bool RC>
+NR_HD bool x_sphere(const Ray& ray, f4 g0, float tmin, float tmax, float& t_out) {
+    vec3 position = mk3(g0.x, g0.y, g0.z);
+    float r = g0.w;
+    vec3 oc = ray.o - position;
+    float a = dot(ray.d, ray.d);
+    float b = dot(oc, ray.d);
+    float c = dot(oc, oc) - r * r;
+    float disc = b * b - a * c;
+    if (!(disc > 0)) return false;
+    float sq = sqrtf(disc);
+    float temp = (-b - sq) / a;
+    if (temp < tmax && (RC ? temp > tmin : temp >= tmin)) { t_out = temp; return true; }
+    temp = (-b + sq) / a;
+    if (temp < tmax && (RC ? temp > tmin : temp >= tmin)) { t_out = temp; return true; }
+    return false;
+}
+
+// xPlane / xAreaLight: n is the normal the variant uses (normalised for RayCast, as stored for the
+// path tracers, cross(u,v) for lights), folded into the record at upload time.
+template <bool RC>
+NR_HD bool x_quad(const Ray& ray, f4 g0, f4 g1, f4 g2, float tmin, float tmax, float& t_out) {
+    vec3 n = mk3(g0.x, g0.y, g0.z), p = mk3(g0.w, g1.x, g1.y);
+    float nd = dot(ray.d, n);
+    if (nd < 0.0000001f && nd > -0.00000001f) return false;
+    float dp = -dot(p, n);
+    float t = (-dp - dot(n, ray.o)) / nd;
+    if (!t_in_range<RC>(t, tmin, tmax)) return false;
+    vec3 q = ray_at(ray, t) - p;
+    // glm mat3*vec3 (type_mat3x3.inl:468-474): m[0][r]*v.x + m[1][r]*v.y + m[2][r]*v.z
+    float ru = g1.z * q.x + g1.w * q.y + g2.x * q.z;
+    float rv = g2.y * q.x + g2.z * q.y + g2.w * q.z;
+    if ((ru <= 1 && ru >= 0) && (rv <= 1 && rv >= 0)) { t_out = t; return true; }
+    return false;
+}
+
+// First two rows of glm::inverse(mat3(u, v, cross(u,v))) (glm/detail/func_matrix.inl compute_inverse<3,3>).
+NR_HD void quad_inverse_rows(vec3 u, vec3 v, float r0[3], float r1[3]) {
+    vec3 w = cross(u, v);
+    float m00 = u.x, m01 = u.y, m02 = u.z, m10 = v.x, m11 = v.y, m12 = v.z, m20 = w.x, m21 = w.y, m22 = w.z;
+    float ood = 1.0f / (+m00 * (m11 * m22 - m21 * m12) - m10 * (m01 * m22 - m21 * m02) + m20 * (m01 * m12 - m11 * m02));
+    r0[0] = +(m11 * m22 - m21 * m12) * ood;
+    r0[1] = -(m10 * m22 - m20 * m12) * ood;
+    r0[2] = +(m10 * m21 - m20 * m11) * ood;
+    r1[0] = -(m01 * m22 - m21 * m02) * ood;
+    r1[1] = +(m00 * m22 - m20 * m02) * ood;
+    r1[2] = -(m00 * m21 - m20 * m01) * ood;
+}
+
+template <bool RC>
+NR_HD bool x_prim(const DScene& s, const Ray& ray, uint32_t id, uint32_t kind, float tmin, float tmax, float& t_out) {
+    const f4* g = s.prim_geom + 3 * (size_t)id;
+    f4 g0 = ldg4(g);
+    if (kind == KIND_SPHERE) return x_sphere<RC>(ray, g0, tmin, tmax, t_out);
+    f4 g1 = ldg4(g + 1), g2 = ldg4(g + 2);
+    if (kind == KIND_PLANE) return x_quad<RC>(ray, g0, g1, g2, tmin, tmax, t_out);
+    return x_triangle<RC>(ray, g0, g1, g2, tmin, tmax, t_out);
+}
+
+// Bounds3::IntersectP, acc_path_tracing/include/Bounds3.hpp:141-168, with invDir as built in
+// BVHTree::getIntersect (BVH.hpp:97: double 1./d narrowed to float; identical to 1.f/d because
+// IEEE division is correctly rounded in both widths for float operands... the double quotient is
+// rounded twice, so it is evaluated in double here as well).
+NR_HD bool bounds_intersectp(f4 lo, f4 hi, const Ray& ray) {
+    vec3 o = ray.o, d = ray.d;
+    if (o.x >= lo.x && o.x <= hi.x && o.y >= lo.y && o.y <= hi.y && o.z >= lo.z && o.z <= hi.z) return true;
+    float ix = (float)(1. / (double)d.x), iy = (float)(1. / (double)d.y), iz = (float)(1. / (double)d.z);
+    float t1n = (lo.x - o.x) * ix, t2n = (lo.y - o.y) * iy, t3n = (lo.z - o.z) * iz;
+    float t1x = (hi.x - o.x) * ix, t2x = (hi.y - o.y) * iy, t3x = (hi.z - o.z) * iz;
+    if (d.x < 0) { float t = t1n; t1n = t1x; t1x = t; }
+    if (d.y < 0) { float t = t2n; t2n = t2x; t2x = t; }
+    if (d.z < 0) { float t = t3n; t3n = t3x; t3x = t; }
+    // std::max(a,b) = (a < b) ? b : a;  std::min(a,b) = (b < a) ? b : a   (NaN behaviour preserved)
+    float in1 = (t2n < t3n) ? t3n : t2n, t_near = (t1n < in1) ? in1 : t1n;
+    float in2 = (t3x < t2x) ? t3x : t2x, t_far = (in2 < t1x) ? in2 : t1x;
+    return t_far >= 0 && t_near < t_far;
+}
+
+// ---- traversal -------------------------------------------------------------------------------
+// Per-thread stack held in local memory: used by the host emulation and as the overflow area of
+// the shared-memory stack in the device kernels.
+#define NRCU_LOCAL_STACK 96
+struct LocalStack {
+    float t[NRCU_LOCAL_STACK]; int ref[NRCU_LOCAL_STACK]; int sp;
+    NR_HD LocalStack() : sp(0) {}
+    NR_HD void push(float tt, int r) { if (sp < NRCU_LOCAL_STACK) { t[sp] = tt; ref[sp] = r; sp++; } }
+    NR_HD bool pop(float& tt, int& r) { if (sp == 0) return false; sp--; tt = t[sp]; r = ref[sp]; return true; }
+};
+
+struct RayPrep { vec3 inv, oinv; };
+NR_HD RayPrep prep_ray(const Ray& ray) {
+    // Reciprocal with the zero/denormal components replaced by a huge finite value: the inner-node
+    // test only has to be conservative, the exact tests never see `inv`.
+    RayPrep p;
+    float dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+    p.inv.x = fabsf(dx) > 1e-18f ? 1.0f / dx : copysignf(1e18f, dx);
+    p.inv.y = fabsf(dy) > 1e-18f ? 1.0f / dy : copysignf(1e18f, dy);
+    p.inv.z = fabsf(dz) > 1e-18f ? 1.0f / dz : copysignf(1e18f, dz);
+    p.oinv = ray.o * p.inv;
+    return p;
+}
+
+#define NRCU_CSWAP(ta, ra, tb, rb) do { if (tb < ta) { float _t = ta; ta = tb; tb = _t; int _r = ra; ra = rb; rb = _r; } } while (0)
+
+// Closest hit over the BVH4.  GATE = AccPathTracer leaf gate (a primitive counts only if its
+// reference leaf box passes Bounds3::IntersectP, which silently drops zero-thickness boxes).
+template <bool GATE, class Stack>
+NR_HD void closest_hit_bvh(const DScene& s, const Ray& ray, Stack& stack, float& best_t, int& best_id) {
+    best_t = NRCU_INF; best_id = -1;
+    const float tmin = (float)0.000001;
+    int cur = s.root_ref;
+    if (cur == NRCU_REF_EMPTY) return;
+    RayPrep rp = prep_ray(ray);
+    for (;;) {
+        if (cur >= 0) {
+            const f4* n = s.nodes + (size_t)cur * NRCU_BVH_NODE_F4;
+            f4 lox = ldg4(n), hix = ldg4(n + 1), loy = ldg4(n + 2), hiy = ldg4(n + 3), loz = ldg4(n + 4), hiz = ldg4(n + 5);
+            i4 refs = ldg4i(n + 6);
+            float t0, t1, t2, t3;
+#define NRCU_SLAB(k, out) do { \
+            float ax = fmaf(lox.k, rp.inv.x, -rp.oinv.x), bx = fmaf(hix.k, rp.inv.x, -rp.oinv.x); \
+            float ay = fmaf(loy.k, rp.inv.y, -rp.oinv.y), by = fmaf(hiy.k, rp.inv.y, -rp.oinv.y); \
+            float az = fmaf(loz.k, rp.inv.z, -rp.oinv.z), bz = fmaf(hiz.k, rp.inv.z, -rp.oinv.z); \
+            float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
+            float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
+            out = (tn <= tf) ? tn : NRCU_INF; } while (0)
+            NRCU_SLAB(x, t0); NRCU_SLAB(y, t1); NRCU_SLAB(z, t2); NRCU_SLAB(w, t3);
+#undef NRCU_SLAB
+            int r0 = refs.x, r1 = refs.y, r2 = refs.z, r3 = refs.w;
+            // 5-comparator sorting network: nearest child first
+            NRCU_CSWAP(t0, r0, t1, r1); NRCU_CSWAP(t2, r2, t3, r3);
+            NRCU_CSWAP(t0, r0, t2, r2); NRCU_CSWAP(t1, r1, t3, r3);
+            NRCU_CSWAP(t1, r1, t2, r2);
+            if (t3 < NRCU_INF) stack.push(t3, r3);
+            if (t2 < NRCU_INF) stack.push(t2, r2);
+            if (t1 < NRCU_INF) stack.push(t1, r1);
+            if (t0 < NRCU_INF) { cur = r0; continue; }
+        } else {
+            uint32_t code = (uint32_t)(~cur);
+            uint32_t first = code >> 4, count = (code & 15u) + 1u;
+            for (uint32_t j = 0; j < count; j++) {
+                uint32_t pk = ldg_u32(s.leaf_prims + first + j);
+                uint32_t id = pk >> 2, kind = pk & 3u;
+                float t;
+                if (!x_prim<false>(s, ray, id, kind, tmin, NRCU_INF, t)) continue;
+                if (t < best_t || (t == best_t && (int)id < best_id)) {
+                    if (GATE) {
+                        f4 lo = ldg4(s.prim_box + 2 * (size_t)id), hi = ldg4(s.prim_box + 2 * (size_t)id + 1);
+                        if (!bounds_intersectp(lo, hi, ray)) continue;
+                    }
+                    best_t = t; best_id = (int)id;
+                }
+            }
+        }
+        // pop the next node that can still contain a hit at t <= best_t
+        float pt;
+        for (;;) {
+            if (!stack.pop(pt, cur)) return;
+            if (pt <= best_t) break;
+        }
+    }
+}
+
+// Brute force in primitive order with shrinking tMax (RayCastRenderer.cpp:66-91).
+template <bool RC>
+NR_HD void closest_hit_linear(const DScene& s, const Ray& ray, float& best_t, int& best_id) {
+    best_t = NRCU_INF; best_id = -1;
+    const float tmin = RC ? (float)0.01 : (float)0.000001;
+    for (uint32_t i = 0; i < s.n_prims; i++) {
+        uint32_t kind = ldg_u32(s.prim_meta + i) & 3u;
+        float t;
+        if (x_prim<RC>(s, ray, i, kind, tmin, best_t, t) && t < best_t) { best_t = t; best_id = (int)i; }
+    }
+}
+
+}  // namespace nrcu

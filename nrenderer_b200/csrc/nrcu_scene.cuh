@@ -1,0 +1,109 @@
+// nrcu_scene.cuh — device-side scene layout (HBM-resident, read through 128-bit __ldg loads).
+//
+// Primitive i (ids in the order nrcu_primitive_count documents) owns
+//   prim_geom[3i..3i+2]  what the intersection test reads (48 B, three LDG.128):
+//       sphere   : (c.x c.y c.z r) - -
+//       triangle : (v1.x v1.y v1.z e1.x) (e1.y e1.z e2.x e2.y) (e2.z - - -)      e1 = v2-v1, e2 = v3-v1
+//       plane    : (n.x n.y n.z p.x) (p.y p.z r0.x r0.y) (r0.z r1.x r1.y r1.z)   r0,r1 = first two rows of
+//                  inverse(mat3(u, v, cross(u,v))) — the reference inverts this matrix per test
+//                  (intersections.cpp:64-66); the rows are a pure function of (u,v), so they are
+//                  precomputed with the same operation order and give bit-identical results.
+//   prim_shade[i]        (normal.xyz, material index bits) read once per hit by the shading kernel
+//   prim_box[2i..2i+1]   (min.xyz -)(max.xyz -): the reference's Bounds3 of the leaf (Bounds3.hpp:35-103),
+//                        used for the AccPathTracer leaf gate and as BVH build input
+//   prim_meta[i]         kind | material << 2
+#pragma once
+#include "nrcu_math.cuh"
+
+namespace nrcu {
+
+struct alignas(16) f4 { float x, y, z, w; };
+NR_HD f4 mk4(float x, float y, float z, float w) { f4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+struct alignas(16) i4 { int x, y, z, w; };
+
+NR_HD f4 ldg4(const f4* p) {
+#if defined(__CUDA_ARCH__)
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return mk4(v.x, v.y, v.z, v.w);
+#else
+    return *p;
+#endif
+}
+NR_HD i4 ldg4i(const f4* p) {
+#if defined(__CUDA_ARCH__)
+    int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    i4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    i4 r; const int* q = reinterpret_cast<const int*>(p); r.x = q[0]; r.y = q[1]; r.z = q[2]; r.w = q[3]; return r;
+#endif
+}
+NR_HD uint32_t ldg_u32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+NR_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    int i; __builtin_memcpy(&i, &f, 4); return i;
+#endif
+}
+NR_HD float i2f(int i) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    float f; __builtin_memcpy(&f, &i, 4); return f;
+#endif
+}
+
+enum { KIND_SPHERE = 0, KIND_TRIANGLE = 1, KIND_PLANE = 2, KIND_MESH = 3 };
+enum { MODE_RAYCAST = 0, MODE_SIMPLE = 1, MODE_ACC = 2 };
+
+// nrcu_material with the shader-constructor defaults applied (same 24-word layout)
+struct DMaterial {
+    uint32_t type, present;
+    float diffuse_color[3], specular_color[3], specular_ex, albedo[3], eta_r[3], eta_i[3], ior, absorbed[3], roughness, f0;
+};
+
+struct DCamera {   // Camera ctor results, ray_cast/include/Camera.hpp:25-46
+    vec3 position, lower_left, horizontal, vertical, u, v;
+    float lens_radius;
+};
+
+#define NRCU_BVH_NODE_F4 7   // float4s per BVH4 node: lox hix loy hiy loz hiz (4 children each) + 4 child refs
+#define NRCU_LEAF_MAX 4      // primitives per leaf the builder aims for
+// child ref encoding: >= 0 inner node index; < 0 leaf: ~ref = (first << 4) | (count - 1), count <= 16;
+// empty slots carry an inverted box (lo = +inf, hi = -inf) and are never entered.
+#define NRCU_REF_EMPTY 0x7fffffff
+
+struct DScene {
+    int mode;
+    uint32_t width, height, depth;
+    uint32_t n_prims;
+    const f4* prim_geom;
+    const f4* prim_shade;
+    const f4* prim_box;
+    const uint32_t* prim_meta;
+    // wide BVH
+    const f4* nodes;
+    const uint32_t* leaf_prims;   // (prim id << 2) | kind, grouped by leaf
+    int root_ref;                 // child-ref encoding; NRCU_REF_EMPTY for an empty scene
+    // shading
+    const DMaterial* materials;
+    uint32_t n_materials;
+    const f4* area_lights;        // 4 float4 per light: quad record (as a plane with n = cross(u,v)) + radiance
+    uint32_t n_area_lights;
+    uint32_t n_point_lights;
+    vec3 point_position, point_intensity;   // pointLightBuffer[0] (RayCastRenderer.cpp:41-42)
+    DCamera cam;
+    vec3 ambient;
+    const f4* env_rgba; int env_w, env_h;   // ambient environment map (extension) or null
+    // Microfacet: the half-vector in the local frame is a constant because the reference reseeds
+    // minstd_rand with 6 on every call (Microfacet.cpp:65-76); computed on the host with libm.
+    float mf_u1, mf_u2, mf_cos_phi, mf_sin_phi;
+};
+
+}  // namespace nrcu

@@ -1,0 +1,342 @@
+// nrcu_shade.cuh — camera rays, material shading and the per-bounce path update.
+//
+// Device restatement (also compiled for the host emulation in tests/host_emu) of
+//   Camera::shoot            ray_cast/include/Camera.hpp:49-57, acc_path_tracing/include/Camera.hpp:51-63
+//   RayCastRenderer::trace   ray_cast/src/RayCastRenderer.cpp:40-64  + shaders/{Lambertian,Phong}.cpp
+//   *PathTracerRenderer::trace  simple_path_tracing/src/SimplePathTracer.cpp:144-177,
+//                               acc_path_tracing/src/AccPathTracer.cpp:121-181
+//   Lambertian / Conductor / Glass / Microfacet ::shade  acc_path_tracing/src/shaders/*.cpp
+//   samplers                 acc_path_tracing/include/samplers/{UniformInSquare,UniformInCircle,Hemisphere}.hpp
+// (paths relative to /root/reference/code/components).  The recursion of trace() is a product of
+// per-bounce factors, so it is run forward: throughput *= factor, radiance added when the path ends.
+#pragma once
+#include <float.h>
+#include "nrcu_intersect.cuh"
+
+namespace nrcu {
+
+#define NRCU_PT_PI 3.1415926535898f   // acc_path_tracing/include/shaders/Shader.hpp:17
+
+// RayCast: pixel corner, no jitter (RayCastRenderer.cpp:27-35).  p = output pixel index (row 0 = top).
+NR_HD Ray raycast_camera_ray(const DScene& s, uint32_t p) {
+    int w = (int)s.width, h = (int)s.height;
+    int row = (int)(p / (uint32_t)w), j = (int)(p % (uint32_t)w), i = h - 1 - row;
+    float sx = (float)j / (float)w, ty = (float)i / (float)h;
+    Ray r; r.o = s.cam.position;
+    r.d = normalize(s.cam.lower_left + s.cam.horizontal * sx + s.cam.vertical * ty - s.cam.position);
+    return r;
+}
+
+// Path tracers: U(-1,1)^2 jitter around the pixel corner (AccPathTracer.cpp:23-29) and the
+// UniformInCircle lens sample (accept iff x*2 + y*2 <= 1, sic).  The lens draws are skipped when
+// the lens radius is 0: the reference multiplies them by zero.
+NR_HD Ray pt_camera_ray(const DScene& s, uint64_t seed, uint32_t p, uint32_t sample) {
+    u32x4 rn = rng_block(seed, p, sample, NRCU_STREAM_CAMERA, 0);
+    float rx = 2.f * u01(rn.x) - 1.f, ry = 2.f * u01(rn.y) - 1.f;
+    int w = (int)s.width, h = (int)s.height;
+    int row = (int)(p / (uint32_t)w), j = (int)(p % (uint32_t)w), i = h - 1 - row;
+    float x = ((float)j + rx) / (float)w;
+    float y = ((float)i + ry) / (float)h;
+    vec3 offset = mk3(0.f);
+    if (s.cam.lens_radius != 0.f) {
+        float lx = 0.f, ly = 0.f;
+        for (uint32_t blk = 1;; blk++) {
+            rn = rng_block(seed, p, sample, NRCU_STREAM_CAMERA, blk);
+            lx = 2.f * u01(rn.x) - 1.f; ly = 2.f * u01(rn.y) - 1.f;
+            if (!((lx * 2 + ly * 2) > 1)) break;
+            lx = 2.f * u01(rn.z) - 1.f; ly = 2.f * u01(rn.w) - 1.f;
+            if (!((lx * 2 + ly * 2) > 1)) break;
+        }
+        offset = s.cam.u * (lx * s.cam.lens_radius) + s.cam.v * (ly * s.cam.lens_radius);
+    }
+    Ray r;
+    r.o = s.cam.position + offset;
+    r.d = normalize(s.cam.lower_left + s.cam.horizontal * x + s.cam.vertical * y - s.cam.position - offset);
+    return r;
+}
+
+// Surface normal of primitive `id` at the hit point.  Spheres: (hit - c)/r, outward even from the
+// inside (intersections.cpp:44-45); everything else: the stored normal (normalised at upload for RayCast).
+NR_HD vec3 hit_normal(const DScene& s, int id, uint32_t kind, vec3 hit_point, int& material) {
+    f4 sh = ldg4(s.prim_shade + id);
+    material = f2i(sh.w);
+    if (kind == KIND_SPHERE) {
+        f4 g0 = ldg4(s.prim_geom + 3 * (size_t)id);
+        return (hit_point - mk3(g0.x, g0.y, g0.z)) / g0.w;
+    }
+    return mk3(sh.x, sh.y, sh.z);
+}
+
+NR_HD float clamp01(float x) { if (x > 1.f) return 1.f; if (x < 0.f) return 0.f; return x; }   // geometry/vec.hpp:86-91
+
+// ---- RayCast ---------------------------------------------------------------------------------
+NR_HD vec3 raycast_shade(const DScene& s, int material, vec3 in, vec3 out, vec3 normal) {
+    const DMaterial& m = s.materials[material];
+    vec3 diffuse_color = ld3(m.diffuse_color);
+    if (m.type == 1) {   // Phong::shade, ray_cast/src/shaders/Phong.cpp:25-31
+        vec3 r = out - (2 * dot(out, normal)) * normal;
+        vec3 diffuse = diffuse_color * dot(out, normal);
+        vec3 specular = ld3(m.specular_color) * fabsf(powf(dot(in, r), m.specular_ex));
+        return diffuse + specular;
+    }
+    return diffuse_color * dot(out, normal);   // Lambertian::shade, ray_cast/src/shaders/Lambertian.cpp:12-14
+}
+
+// One pixel of RayCastRenderer::render: returns the gamma-corrected colour.
+NR_HD vec3 raycast_pixel(const DScene& s, uint32_t p, uint32_t* ray_count) {
+    vec3 c = mk3(0.f);
+    if (s.n_point_lights >= 1) {
+        Ray r = raycast_camera_ray(s, p);
+        float t; int id;
+        closest_hit_linear<true>(s, r, t, id);
+        (*ray_count)++;
+        if (id >= 0) {
+            vec3 hp = ray_at(r, t);
+            int material;
+            vec3 n = hit_normal(s, id, ldg_u32(s.prim_meta + id) & 3u, hp, material);
+            vec3 out = normalize(s.point_position - hp);
+            if (!(dot(out, n) < 0)) {
+                float distance = length(s.point_position - hp);
+                Ray sr; sr.o = hp; sr.d = out;
+                float st; int sid;
+                closest_hit_linear<true>(s, sr, st, sid);
+                (*ray_count)++;
+                vec3 col = raycast_shade(s, material, -r.d, out, n);
+                if (sid < 0 || st > distance) c = col * s.point_intensity;
+            }
+        }
+    }
+    c = mk3(clamp01(c.x), clamp01(c.y), clamp01(c.z));
+    return mk3(sqrtf(c.x), sqrtf(c.y), sqrtf(c.z));
+}
+
+// ---- path tracing ----------------------------------------------------------------------------
+// closestHitLight, AccPathTracer.cpp:101-112
+NR_HD float closest_light(const DScene& s, const Ray& r, vec3& radiance) {
+    float closest = NRCU_INF;
+    radiance = mk3(0.f);
+    for (uint32_t i = 0; i < s.n_area_lights; i++) {
+        const f4* L = s.area_lights + 4 * (size_t)i;
+        float t;
+        if (x_quad<false>(r, ldg4(L), ldg4(L + 1), ldg4(L + 2), (float)0.000001, closest, t) && closest > t) {
+            closest = t;
+            f4 rad = ldg4(L + 3);
+            radiance = mk3(rad.x, rad.y, rad.z);
+        }
+    }
+    return closest;
+}
+
+// Lambertian::shade (Lambertian.cpp:16-34) + HemiSphere::sample3d (Hemisphere.hpp:24-32) + Onb (Onb.hpp:17-27);
+// factor = attenuation * dot(N, dir) / pdf as used at AccPathTracer.cpp:142.
+NR_HD Ray shade_lambertian(vec3 albedo, vec3 hit_point, vec3 normal, float e1, float e2, vec3& factor) {
+    const float C_PI = 3.14159265358979323846264338327950288f;
+    float r = sqrtf(1 - e1 * e1);
+    float x = cosf(2 * C_PI * e2) * r;
+    float y = sinf(2 * C_PI * e2) * r;
+    float z = e1;
+    vec3 w = normal;
+    vec3 a = ((double)fabsf(w.x) > 0.9) ? mk3(0, 1, 0) : mk3(1, 0, 0);
+    vec3 v = normalize(cross(w, a));
+    vec3 u = cross(w, v);
+    vec3 local = x * u + y * v + z * w;
+    Ray out; out.o = hit_point; out.d = normalize(local);
+    float pdf = 1 / (2 * NRCU_PT_PI);
+    vec3 attenuation = albedo / NRCU_PT_PI;
+    float n_dot_in = dot(normal, out.d);
+    factor = attenuation * n_dot_in / pdf;
+    return out;
+}
+
+// Conductor::shade, Conductor.cpp:6-42
+NR_HD Ray shade_conductor(const DMaterial& m, const Ray& ray, vec3 hit_point, vec3 normal, vec3& factor) {
+    vec3 V = -ray.d;
+    vec3 N = normalize(normal);
+    vec3 L = normalize(-V + (2.f * dot(V, N)) * N);
+    float cos_l = fabsf(dot(L, N));
+    float cos2 = cos_l * cos_l, sin2 = 1 - cos2, sin4 = sin2 * sin2;
+    vec3 eta_r = ld3(m.eta_r), eta_i = ld3(m.eta_i), albedo = ld3(m.albedo);
+    vec3 temp1 = eta_r * eta_r - eta_i * eta_i - sin2;
+    vec3 a2pb2 = temp1 * temp1 + ((4.0f * eta_i) * eta_i) * eta_r * eta_r;
+    a2pb2 = mk3(sqrtf(fmaxf(0.0f, a2pb2.x)), sqrtf(fmaxf(0.0f, a2pb2.y)), sqrtf(fmaxf(0.0f, a2pb2.z)));
+    vec3 a = 0.5f * (a2pb2 + temp1);
+    a = mk3(sqrtf(fmaxf(0.f, a.x)), sqrtf(fmaxf(0.f, a.y)), sqrtf(fmaxf(0.f, a.z)));
+    vec3 term1 = a2pb2 + cos2, term2 = (2.f * cos_l) * a;
+    vec3 term3 = a2pb2 * cos2 + sin4, term4 = term2 * sin2;
+    vec3 rs = (term1 - term2) / (term1 + term2);
+    vec3 rp = rs * (term3 - term4) / (term3 + term4);
+    vec3 F = 0.5f * (rs + rp);
+    factor = F * fabsf(dot(L, N)) * albedo;
+    Ray out; out.o = hit_point; out.d = L;
+    return out;
+}
+
+struct GlassSplit { Ray reflex, refraction; vec3 reflex_rate, refraction_rate; };
+NR_HD float pow5(float x) {
+#if defined(__CUDA_ARCH__)
+    float x2 = x * x; return x2 * x2 * x;     // the reference evaluates pow(double(x), 5); <= 1 ulp apart
+#else
+    return (float)pow((double)x, 5.0);
+#endif
+}
+// Glass::shade, Glass.cpp:15-57 (including its non-Snell refraction direction and the x_ > 1 branch
+// that uses the colour `absorbed` as the reflected direction).
+NR_HD GlassSplit shade_glass(const DMaterial& m, const Ray& ray, vec3 hit_point, vec3 normal) {
+    vec3 absorbed = ld3(m.absorbed);
+    float ior = m.ior;
+    vec3 N = normalize(normal), V = normalize(ray.d);
+    float ior_inverse = ior;
+    if (dot(V, N) > 0.f) { N = -N; ior_inverse = 1 / ior; }
+    vec3 reflex = normalize(V + (N * 2.f) * dot(-V, N));
+    float n12 = (ior_inverse - 1.f) / (ior_inverse + 1.f);
+    n12 = n12 * n12;
+    float vdn = fabsf(dot(V, N));
+    float Fs = n12 + (1.f - n12) * pow5(1 - vdn);
+    vec3 F = mk3(Fs);
+    GlassSplit g;
+    g.reflex_rate = F * absorbed;
+    g.refraction_rate = (mk3(1.f) - F) * absorbed;
+    vec3 x = normalize(reflex + V);
+    vec3 y = normalize(-N);
+    // sqrt(pow(1-|V.N|, 2)) / ior_inverse evaluated in double by the reference; 1-|V.N| >= 0 so the
+    // sqrt(pow(.,2)) pair is the identity up to rounding.
+    float x_ = (float)(sqrt((double)(1 - vdn) * (double)(1 - vdn)) / (double)ior_inverse);
+    float y_ = (float)sqrt(1.0 - (double)x_ * (double)x_);
+    vec3 refraction = normalize(x * x_ + y * y_);
+    if (x_ > 1.f) { reflex = absorbed; g.refraction_rate = mk3(0.f); refraction = mk3(0.f); }
+    g.reflex.o = hit_point; g.reflex.d = reflex;
+    g.refraction.o = hit_point; g.refraction.d = refraction;
+    return g;
+}
+
+// SmithG1, Microfacet.cpp:16-32
+NR_HD float smith_g1(vec3 v, vec3 h, vec3 n, float roughness) {
+    double cos_v_n = dot(v, n);
+    if (cos_v_n * dot(v, h) <= 0.0f) return 0.f;
+    if (fabs(cos_v_n - 1.0) < DBL_EPSILON) return 1.0f;
+    float c2 = (float)(cos_v_n * cos_v_n), t2 = (1.0f - c2) / c2, a2 = roughness * roughness;
+    return 2.0f / (1.0f + sqrtf(1.0f + a2 * t2));
+}
+
+// Microfacet::shade with Sample/ToWorld/CoordinateSystem, Microfacet.cpp:71-118, 172-222.
+NR_HD bool shade_microfacet(const DScene& s, const DMaterial& m, const Ray& ray, vec3 hit_point, vec3 normal, Ray& out, vec3& factor) {
+    const float metalness = 0.2f;
+    float roughness = m.roughness, F0 = m.f0;
+    vec3 albedo = ld3(m.albedo);
+    vec3 N = normalize(normal);
+    float alpha_2 = roughness * roughness;
+    float tan_theta_2 = alpha_2 * s.mf_u1 / (1.0f - s.mf_u1);
+    float cos_theta = (float)(1.0 / (double)sqrtf(1.0f + tan_theta_2));
+    float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    vec3 dir = mk3(sin_theta * s.mf_cos_phi, sin_theta * s.mf_sin_phi, cos_theta);
+    vec3 B, C;
+    if (fabsf(N.x) > fabsf(N.y)) {
+        double len_inv = 1.0f / sqrtf(N.x * N.x + N.z * N.z);
+        C = mk3((float)(N.z * len_inv), 0.f, (float)(-N.x * len_inv));
+    } else {
+        double len_inv = 1.0f / sqrtf(N.y * N.y + N.z * N.z);
+        C = mk3(0.f, (float)(N.z * len_inv), (float)(-N.y * len_inv));
+    }
+    B = cross(C, N);
+    vec3 H = normalize(dir.x * B + dir.y * C + dir.z * N);
+    double ct = (double)cos_theta, q = (double)(1.0f + tan_theta_2 / alpha_2);
+    float D = 1.0f / (float)((double)(NRCU_PT_PI * alpha_2) * (ct * ct * ct) * (q * q));
+    H = normalize(H);
+    vec3 V = -ray.d;
+    float pdf = D * fabsf(1.0f / (4.0f * dot(ray.d, H)));
+    vec3 L = normalize(normalize(ray.d - (2.0f * dot(ray.d, H)) * H));
+    float cos_theta_i = dot(L, N);
+    if (pdf == 0.f || dot(ray.d, normal) >= 0.f || cos_theta_i <= 0.f) return false;
+    vec3 specularF0 = (1.f - metalness) * mk3(F0) + metalness * albedo;
+    vec3 F = specularF0 + (mk3(1.0f) - specularF0) * pow5(1.0f - fabsf(dot(L, H)));
+    float cos_theta_o = fabsf(dot(N, V));
+    float G = smith_g1(L, H, N, roughness) * smith_g1(V, H, N, roughness);
+    vec3 att = (F * G * D) / fabsf(4.0f * cos_theta_o);
+    att = att / pdf;
+    att = att * albedo;
+    out.o = hit_point; out.d = L;
+    factor = att;
+    return true;
+}
+
+// Extension: latitude-longitude lookup of the ambient environment map on a miss.
+// A zero or NaN direction (the reference's glass shader produces both) looks up nothing: black.
+NR_HD vec3 env_lookup(const DScene& s, vec3 d) {
+    if (!(dot(d, d) > 0.f) || !(dot(d, d) < NRCU_INF)) return mk3(0.f);
+    vec3 n = normalize(d);
+    float u = 0.5f + atan2f(n.x, n.z) * (0.5f / NRCU_PT_PI);
+    float cy = fminf(1.f, fmaxf(-1.f, n.y));
+    float v = acosf(cy) * (1.0f / NRCU_PT_PI);
+    int x = (int)(u * (float)s.env_w), y = (int)(v * (float)s.env_h);
+    x = x < 0 ? 0 : (x > s.env_w - 1 ? s.env_w - 1 : x);
+    y = y < 0 ? 0 : (y > s.env_h - 1 ? s.env_h - 1 : y);
+    f4 px = ldg4(s.env_rgba + (size_t)y * s.env_w + x);
+    return mk3(px.x, px.y, px.z);
+}
+
+// Result of processing one path vertex.
+enum { PATH_CONTINUE = 0, PATH_TERMINATE = 1, PATH_SPLIT = 2 };
+struct PathStep {
+    int action;
+    vec3 radiance;      // thr * L to add to the pixel when the path ends here (may be zero)
+    Ray next; vec3 thr; // continuation
+    Ray next2; vec3 thr2; // second branch (PATH_SPLIT, glass branch mode)
+};
+
+// One iteration of trace() for a ray at bounce `d` (d < depth) whose closest object hit is
+// (t, id) — AccPathTracer.cpp:121-181.  `branch` = glass branch bits (RNG block).
+NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
+                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode) {
+    PathStep ps; ps.action = PATH_TERMINATE; ps.radiance = mk3(0.f);
+    ps.next = ray; ps.thr = thr; ps.next2 = ray; ps.thr2 = mk3(0.f);
+    vec3 radiance;
+    float tl = closest_light(s, ray, radiance);
+    if (id >= 0 && t < tl) {
+        vec3 hp = ray_at(ray, t);
+        int material;
+        uint32_t kind = ldg_u32(s.prim_meta + id) & 3u;
+        vec3 n = hit_normal(s, id, kind, hp, material);
+        const DMaterial& m = s.materials[material];
+        uint32_t type = s.mode == MODE_ACC ? m.type : 0u;
+        if (type == 2u) {
+            GlassSplit g = shade_glass(m, ray, hp, n);
+            bool refl_zero = is_zero(g.reflex_rate);
+            if (glass_branch_mode) {
+                ps.next = g.reflex; ps.thr = thr * g.reflex_rate; ps.action = PATH_CONTINUE;
+                if (!refl_zero) { ps.next2 = g.refraction; ps.thr2 = thr * g.refraction_rate; ps.action = PATH_SPLIT; }
+            } else {
+                float q = g.reflex_rate.x + g.reflex_rate.y + g.reflex_rate.z;
+                float q2 = g.refraction_rate.x + g.refraction_rate.y + g.refraction_rate.z;
+                if (refl_zero || !(q + q2 > 0.f)) return ps;
+                float pr = q / (q + q2);
+                u32x4 rn = rng_block(seed, pixel, sample, d, branch);
+                if (u01(rn.z) < pr) { ps.thr = thr * (g.reflex_rate / pr); ps.next = g.reflex; }
+                else { ps.thr = thr * (g.refraction_rate / (1.f - pr)); ps.next = g.refraction; }
+                ps.action = PATH_CONTINUE;
+            }
+        } else if (type == 1u) {
+            vec3 f; ps.next = shade_conductor(m, ray, hp, n, f); ps.thr = thr * f; ps.action = PATH_CONTINUE;
+        } else if (type == 3u) {
+            vec3 f; Ray nr;
+            if (shade_microfacet(s, m, ray, hp, n, nr, f)) { ps.next = nr; ps.thr = thr * f; ps.action = PATH_CONTINUE; }
+        } else {
+            // type 0 (any other type falls off the end of the reference's trace(): treated as Lambertian)
+            u32x4 rn = rng_block(seed, pixel, sample, d, branch);
+            vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(rn.y), f);
+            ps.thr = thr * f; ps.action = PATH_CONTINUE;
+        }
+        // the continuation would return ambient at the depth limit (AccPathTracer.cpp:122)
+        if (ps.action != PATH_TERMINATE && d + 1 == s.depth) {
+            vec3 add = ps.thr * s.ambient;
+            if (ps.action == PATH_SPLIT) add = add + ps.thr2 * s.ambient;
+            ps.radiance = add; ps.action = PATH_TERMINATE;
+        }
+    } else if (tl != NRCU_INF) {
+        ps.radiance = thr * radiance;
+    } else if (s.env_rgba && s.mode == MODE_ACC) {
+        ps.radiance = thr * env_lookup(s, ray.d);
+    }
+    return ps;
+}
+
+}  // namespace nrcu

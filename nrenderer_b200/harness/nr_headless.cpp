@@ -140,8 +140,11 @@ int main(int argc, char** argv) {
 
     for (auto& p : plugins) {
         // Same effect as the GUI's LoadLibrary loop (code/app/src/manager/ComponentManager.cpp:15-30):
-        // the library's static ComponentRegister object registers the component.
-        if (!dlopen(p.c_str(), RTLD_NOW | RTLD_GLOBAL)) { std::fprintf(stderr, "dlopen %s: %s\n", p.c_str(), dlerror()); return 1; }
+        // the library's static ComponentRegister object registers the component.  RTLD_LOCAL: every
+        // plugin defines a struct named ComponentRegister (Component.hpp:23-32); with global binding the
+        // second plugin would run the first one's constructor.  getServer() is still shared because all
+        // plugins depend on the one libNRServer.so.
+        if (!dlopen(p.c_str(), RTLD_NOW | RTLD_LOCAL)) { std::fprintf(stderr, "dlopen %s: %s\n", p.c_str(), dlerror()); return 1; }
     }
     if (list) {
         for (auto& ci : getServer().componentFactory.getComponentsInfo("Render"))

@@ -1,0 +1,125 @@
+// NRCudaAdapter.cpp — the CUDA backend as an NRenderer render component.
+//
+// Drop-in for the reference's CPU components behind the unchanged plugin API:
+//   class Adapter : public RenderComponent { void render(SharedScene) }   (code/include/component/RenderComponent.hpp:12-18)
+//   REGISTER_RENDERER(Name, description, Class)                           (code/include/component/Component.hpp:23-34)
+// The reference registers one component per shared library (fixed-name static in the macro), so this
+// file is compiled three times:  -DNRCU_PLUGIN_MODE=0 -> "CudaRayCast"           (replaces RayCast,          ray_cast/src/Adapter.cpp:11-34)
+//                                -DNRCU_PLUGIN_MODE=1 -> "CudaSimplePathTracer"  (replaces SimplePathTracer, simple_path_tracing/src/Adapter.cpp:13-30)
+//                                -DNRCU_PLUGIN_MODE=2 -> "CudaAccPathTracer"     (replaces AccPathTracer,    acc_path_tracing/src/Adapter.cpp:13-30)
+// render() never throws and treats the Scene as read-only (the reference components mutate it in
+// place); the frame is published through getServer().screen.set exactly like ray_cast/src/Adapter.cpp:15-19.
+// It is compiled by g++ against the reference's headers and talks to the kernels only through the
+// C ABI in include/nrcu.h.
+#include <chrono>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "server/Server.hpp"
+#include "component/RenderComponent.hpp"
+
+#include "nrcu.h"
+#include "scene_bridge.hpp"
+
+#ifndef NRCU_PLUGIN_MODE
+#define NRCU_PLUGIN_MODE 2
+#endif
+
+using namespace NRenderer;
+
+namespace NRCuda
+{
+    // One CUDA context per process, created on first use and reused by every render
+    // (the GUI runs render() on a fresh detached thread per click, ComponentManager.hpp:41-64).
+    struct SharedContext {
+        std::mutex mtx;
+        nrcu_ctx* ctx = nullptr;
+        ~SharedContext() { if (ctx) nrcu_destroy(ctx); }
+    };
+    static SharedContext& shared() { static SharedContext s; return s; }
+
+    static void publishBlack(unsigned w, unsigned h) {
+        std::vector<RGBA> px((size_t)w * h, RGBA{0, 0, 0, 1});
+        getServer().screen.set(px.data(), (int)w, (int)h);
+    }
+
+    class Adapter : public RenderComponent
+    {
+        void render(SharedScene spScene) override {
+            auto& logger = getServer().logger;
+            if (!spScene) { logger.error("NRCuda: no scene (SceneBuilder::build failed?)"); return; }
+            const unsigned w = spScene->renderOption.width, h = spScene->renderOption.height;
+            try {
+                auto t0 = std::chrono::steady_clock::now();
+                std::string warn;
+                nrb200::FlatScene flat = nrb200::flatten(*spScene, &warn);
+                if (!warn.empty()) logger.warning("NRCuda: " + warn);
+                nrcu_scene view = flat.view();
+
+                auto& sh = shared();
+                std::lock_guard<std::mutex> lock(sh.mtx);
+                if (!sh.ctx) {
+                    int dev = 0;
+                    if (const char* e = std::getenv("NRCU_DEVICE")) dev = std::atoi(e);
+                    if (nrcu_create(dev, &sh.ctx) != NRCU_OK) {
+                        logger.error(std::string("NRCuda: ") + nrcu_last_error(nullptr));
+                        publishBlack(w, h);
+                        return;
+                    }
+                }
+                if (nrcu_upload_scene(sh.ctx, &view, NRCU_PLUGIN_MODE) != NRCU_OK) {
+                    logger.error(std::string("NRCuda: ") + nrcu_last_error(sh.ctx));
+                    publishBlack(w, h);
+                    return;
+                }
+                nrcu_render_params params{};
+                if (const char* e = std::getenv("NRCU_SEED")) params.seed = std::strtoull(e, nullptr, 10);
+                if (const char* e = std::getenv("NRCU_GLASS_BRANCH")) params.glass_mode = std::atoi(e) ? NRCU_GLASS_BRANCH : NRCU_GLASS_STOCHASTIC;
+                nrcu_stats st{};
+                RGBA* pixels = new RGBA[(size_t)w * h];   // plugin owns the buffer, Screen::set copies it (RayCastRenderer.cpp:7-10)
+                int rc = nrcu_render(sh.ctx, &params, reinterpret_cast<float*>(pixels), &st);
+                if (rc != NRCU_OK) {
+                    logger.error(std::string("NRCuda: ") + nrcu_last_error(sh.ctx));
+                    delete[] pixels;
+                    publishBlack(w, h);
+                    return;
+                }
+                getServer().screen.set(pixels, (int)w, (int)h);
+                delete[] pixels;
+                double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                char buf[320];
+                std::snprintf(buf, sizeof(buf),
+                              "Done... %.3f s (GPU %.1f ms, setup %.2f ms): %.2f Mpath-samples/s, %.1f Mrays/s, %u primitives, %u BVH4 nodes",
+                              wall, st.ms_total, st.ms_setup, st.paths / wall * 1e-6, st.rays / (st.ms_total * 1e-3) * 1e-6,
+                              st.n_primitives, st.bvh_nodes);
+                logger.log(buf);
+            } catch (const std::exception& ex) {
+                logger.error(std::string("NRCuda: ") + ex.what());
+                publishBlack(w, h);
+            } catch (...) {
+                logger.error("NRCuda: unknown failure");
+                publishBlack(w, h);
+            }
+        }
+    };
+}
+
+#if NRCU_PLUGIN_MODE == 0
+const static std::string description =
+    "CUDA (sm_100a) Ray Cast Renderer.\n"
+    "Same image as RayCast: Lambertian and Phong, one point light,\n"
+    "triangle / sphere / plane, pinhole camera.";
+REGISTER_RENDERER(CudaRayCast, description, NRCuda::Adapter);
+#elif NRCU_PLUGIN_MODE == 1
+const static std::string description =
+    "CUDA (sm_100a) wavefront path tracer, SimplePathTracer semantics:\n"
+    "Lambertian only, uniform hemisphere sampling, area lights hit by chance.";
+REGISTER_RENDERER(CudaSimplePathTracer, description, NRCuda::Adapter);
+#else
+const static std::string description =
+    "CUDA (sm_100a) wavefront path tracer, AccPathTracer semantics:\n"
+    "wide BVH, Lambertian / conductor / glass / microfacet materials, environment map.";
+REGISTER_RENDERER(CudaAccPathTracer, description, NRCuda::Adapter);
+#endif
