@@ -127,13 +127,44 @@ NR_HD float closest_light(const DScene& s, const Ray& r, vec3& radiance) {
     return closest;
 }
 
+// sin/cos of an angle in [0, 2*pi] evaluated the same way on the device, in the host emulation and in
+// the oracle: quadrant reduction and a Taylor polynomial in double (no fused multiply-adds, fixed
+// order), rounded once to float.  The reference calls libm's cosf/sinf (Hemisphere.hpp:28-29); CUDA's
+// differ from glibc's in the last ulp, which is enough to flip self-intersection decisions
+// (tMin = 1e-6 with no ray offset) and send a path down another branch.  With a shared, <0.5 ulp + 1e-11
+// accurate implementation the whole diffuse path is reproducible bit for bit across CPU and GPU.
+NR_HD void sincos_det(float a, float& s, float& c) {
+    double x = (double)a;
+    double kd = rint(x * 0.63661977236758134308);        // 2/pi
+    double r = x - kd * 1.57079632679489661923;           // pi/2
+    double r2 = r * r;
+    double sp = -1.0 / 39916800.0;
+    sp = sp * r2 + 1.0 / 362880.0;
+    sp = sp * r2 + -1.0 / 5040.0;
+    sp = sp * r2 + 1.0 / 120.0;
+    sp = sp * r2 + -1.0 / 6.0;
+    double sr = r + (r * r2) * sp;
+    double cp = 1.0 / 479001600.0;
+    cp = cp * r2 + -1.0 / 3628800.0;
+    cp = cp * r2 + 1.0 / 40320.0;
+    cp = cp * r2 + -1.0 / 720.0;
+    cp = cp * r2 + 1.0 / 24.0;
+    double cr = (1.0 - 0.5 * r2) + (r2 * r2) * cp;
+    int k = ((int)kd) & 3;
+    double sd = (k == 0) ? sr : (k == 1) ? cr : (k == 2) ? -sr : -cr;
+    double cd = (k == 0) ? cr : (k == 1) ? -sr : (k == 2) ? -cr : sr;
+    s = (float)sd; c = (float)cd;
+}
+
 // Lambertian::shade (Lambertian.cpp:16-34) + HemiSphere::sample3d (Hemisphere.hpp:24-32) + Onb (Onb.hpp:17-27);
 // factor = attenuation * dot(N, dir) / pdf as used at AccPathTracer.cpp:142.
 NR_HD Ray shade_lambertian(vec3 albedo, vec3 hit_point, vec3 normal, float e1, float e2, vec3& factor) {
     const float C_PI = 3.14159265358979323846264338327950288f;
     float r = sqrtf(1 - e1 * e1);
-    float x = cosf(2 * C_PI * e2) * r;
-    float y = sinf(2 * C_PI * e2) * r;
+    float sn, cs;
+    sincos_det(2 * C_PI * e2, sn, cs);
+    float x = cs * r;
+    float y = sn * r;
     float z = e1;
     vec3 w = normal;
     vec3 a = ((double)fabsf(w.x) > 0.9) ? mk3(0, 1, 0) : mk3(1, 0, 0);
@@ -172,13 +203,9 @@ NR_HD Ray shade_conductor(const DMaterial& m, const Ray& ray, vec3 hit_point, ve
 }
 
 struct GlassSplit { Ray reflex, refraction; vec3 reflex_rate, refraction_rate; };
-NR_HD float pow5(float x) {
-#if defined(__CUDA_ARCH__)
-    float x2 = x * x; return x2 * x2 * x;     // the reference evaluates pow(double(x), 5); <= 1 ulp apart
-#else
-    return (float)pow((double)x, 5.0);
-#endif
-}
+// (float)pow(double(x), 5) of the reference (Glass.cpp:37, Microfacet.cpp:34): four double products
+// round to the same float except on a ~1e-8 measure of inputs.
+NR_HD float pow5(float x) { double d = (double)x; double d2 = d * d; return (float)((d2 * d2) * d); }
 // Glass::shade, Glass.cpp:15-57 (including its non-Snell refraction direction and the x_ > 1 branch
 // that uses the colour `absorbed` as the reflected direction).
 NR_HD GlassSplit shade_glass(const DMaterial& m, const Ray& ray, vec3 hit_point, vec3 normal) {

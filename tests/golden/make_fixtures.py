@@ -56,12 +56,12 @@ def microfacet(fs):
 
 # name: (scene, component, mode, w, h, spp per run, depth, runs, edit)
 PT_CASES = {
-    "simple_cornell_d4": ("path_tracing_cornel", "SimplePathTracer", 1, 48, 48, 2048, 4, 4, None),
-    "acc_cornell_d20": ("path_tracing_cornel", "AccPathTracer", 2, 48, 48, 1024, 20, 4, None),
-    "acc_bunny5k_d20": ("bunny5k_cornel", "AccPathTracer", 2, 48, 48, 512, 20, 4, None),
-    "acc_gold_d20": ("pt_glass", "AccPathTracer", 2, 48, 48, 1024, 20, 4, None),
-    "acc_glass_d6": ("pt_glass", "AccPathTracer", 2, 48, 48, 512, 6, 4, glassify),
-    "acc_microfacet_d8": ("pt_glass_conductors", "AccPathTracer", 2, 48, 48, 1024, 8, 4, microfacet),
+    "simple_cornell_d4": ("path_tracing_cornel", "SimplePathTracer", 1, 48, 48, 2048, 4, 8, None),
+    "acc_cornell_d20": ("path_tracing_cornel", "AccPathTracer", 2, 48, 48, 1024, 20, 8, None),
+    "acc_bunny5k_d20": ("bunny5k_cornel", "AccPathTracer", 2, 48, 48, 512, 20, 8, None),
+    "acc_gold_d20": ("pt_glass", "AccPathTracer", 2, 48, 48, 1024, 20, 8, None),
+    "acc_glass_d6": ("pt_glass", "AccPathTracer", 2, 48, 48, 512, 6, 8, glassify),
+    "acc_microfacet_d8": ("pt_glass_conductors", "AccPathTracer", 2, 48, 48, 1024, 8, 8, microfacet),
 }
 
 

@@ -1,0 +1,60 @@
+"""Flat-scene plumbing: .nrsc round trips in Python and through the C++ harness / reference importers."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REPO, load_scene
+from nrenderer_b200.flatscene import FlatScene
+from oracle import pyoracle as po
+
+
+def test_python_round_trip(tmp_path):
+    fs = load_scene("bunny5k_cornel", width=123, height=45, cam_aspect=2.5)
+    fs.add_texture(np.random.default_rng(0).uniform(0, 1, (4, 8, 4)).astype(np.float32))
+    p = tmp_path / "x.nrsc"
+    fs.save(p)
+    g = FlatScene.load(p)
+    for name in FlatScene._ARRAYS:
+        assert np.array_equal(np.asarray(getattr(fs, name)).reshape(-1), np.asarray(getattr(g, name)).reshape(-1)), name
+    assert (g.width, g.height, g.cam_aspect) == (123, 45, 2.5)
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
+def test_harness_round_trip_through_the_reference_scene_type(tmp_path):
+    """flat -> NRenderer::Scene (unflatten) -> flat (flatten) is the identity."""
+    for name in ["bunny200_cornel", "pt_glass_conductors", "ray_cast_cornel"]:
+        out = tmp_path / f"{name}.nrsc"
+        env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
+        subprocess.run([os.path.join(po.REF_DIR, "nr_headless"), "--flat", os.path.join(GOLDEN, name + ".nrsc"), "--dump-flat", str(out)],
+                       check=True, env=env)
+        a, b = FlatScene.load(os.path.join(GOLDEN, name + ".nrsc")), FlatScene.load(out)
+        for arr in FlatScene._ARRAYS:
+            assert np.array_equal(np.asarray(getattr(a, arr)).reshape(-1), np.asarray(getattr(b, arr)).reshape(-1)), (name, arr)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/resource"), reason="reference resources not mounted")
+def test_fixtures_are_what_the_reference_importers_produce(tmp_path):
+    out = tmp_path / "s.nrsc"
+    env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
+    subprocess.run([os.path.join(po.REF_DIR, "nr_headless"), "--scn", "/root/reference/resource/path_tracing_cornel.scn", "--dump-flat", str(out)],
+                   check=True, env=env)
+    a, b = load_scene("path_tracing_cornel"), FlatScene.load(out)
+    for arr in FlatScene._ARRAYS:
+        assert np.array_equal(np.asarray(getattr(a, arr)).reshape(-1), np.asarray(getattr(b, arr)).reshape(-1)), arr
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
+def test_cuda_plugins_register_through_the_reference_factory():
+    """The adapters load next to the reference's own plugins and register under their names."""
+    from nrenderer_b200 import build
+    plugins = [build.plugin_path(m) for m in (0, 1, 2)]
+    if not all(os.path.exists(p) for p in plugins):
+        pytest.skip("plugin adapters not built")
+    cmd = [os.path.join(po.REF_DIR, "nr_headless"), "--list"]
+    for p in plugins + [os.path.join(po.REF_DIR, n) for n in po.REF_PLUGINS.values()]:
+        cmd += ["--plugin", p]
+    env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
+    names = set(subprocess.run(cmd, capture_output=True, text=True, check=True, env=env).stdout.split())
+    assert {"CudaRayCast", "CudaSimplePathTracer", "CudaAccPathTracer", "RayCast", "SimplePathTracer", "AccPathTracer"} <= names
