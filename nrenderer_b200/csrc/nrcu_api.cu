@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -372,6 +373,22 @@ static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_
     return NRCU_OK;
 }
 
+}  // extern "C"
+
+// Traversal kernel variant and its refill threshold (tuning knobs; NRCU_TRACE_VARIANT=1 selects the
+// first, batch-of-32 kernel kept for A/B measurements).
+static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
+static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
+static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
+
+template <bool GATE>
+static void launch_trace(nrcu_ctx* ctx, unsigned grid, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* fetch, unsigned long long* rays) {
+    if (trace_variant() == 1) k_trace<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_ptr, hits, fetch, rays);
+    else k_trace2<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_ptr, hits, fetch, rays, trace_refill());
+}
+
+extern "C" {
+
 static int sm_count(int device) {
     static int cached[64] = {0};
     if (device < 64 && cached[device]) return cached[device];
@@ -411,7 +428,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 2 * (size_t)ds.depth + 8);
     cudaStream_t st = ctx->stream;
     const int sms = sm_count(ctx->device);
-    const unsigned trace_grid = (unsigned)sms * 8, shade_grid = (unsigned)sms * 4;
+    const unsigned trace_grid = (unsigned)sms * trace_blocks_per_sm(), shade_grid = (unsigned)sms * 4;
     const bool timing = stats != nullptr;
     size_t ev_i = 0;
     struct Span { size_t a, b; int kind; };
@@ -427,10 +444,8 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         for (uint32_t d = 0; d < ds.depth; d++) {
             PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
-            if (ctx->mode == NRCU_MODE_ACC)
-                k_trace<true><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
-            else
-                k_trace<false><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
+            if (ctx->mode == NRCU_MODE_ACC) launch_trace<true>(ctx, trace_grid, ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
+            else launch_trace<false>(ctx, trace_grid, ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
             CTX_LAUNCH_CHECK("k_trace");
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
             k_shade<<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, ctx->hits.as<float2>(), qo, d_qn + d + 1, capacity, ctx->L.as<f4>());
@@ -544,10 +559,10 @@ int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim
     k_pack_rays<<<grid_for(n, 256), 256, 0, st>>>(d_rays.as<float>(), n, q);
     CTX_LAUNCH_CHECK("k_pack_rays");
     uint32_t* c = cnt.as<uint32_t>();
-    const unsigned trace_grid = (unsigned)sm_count(ctx->device) * 8;
+    const unsigned trace_grid = (unsigned)sm_count(ctx->device) * trace_blocks_per_sm();
     if (ctx->mode == NRCU_MODE_RAYCAST) k_trace_linear_rc<<<grid_for(n, 128), 128, 0, st>>>(ctx->ds, q, n, hits.as<float2>());
-    else if (ctx->mode == NRCU_MODE_ACC) k_trace<true><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
-    else k_trace<false><<<trace_grid, NRCU_TRACE_THREADS, 0, st>>>(ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
+    else if (ctx->mode == NRCU_MODE_ACC) launch_trace<true>(ctx, trace_grid, ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
+    else launch_trace<false>(ctx, trace_grid, ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
     CTX_LAUNCH_CHECK("k_trace");
     std::vector<float2> h(n);
     CTX_CUDA(cudaMemcpyAsync(h.data(), hits.p, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, st));

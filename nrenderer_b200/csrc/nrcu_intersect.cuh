@@ -149,62 +149,82 @@ NR_HD RayPrep prep_ray(const Ray& ray) {
 
 #define NRCU_CSWAP(ta, ra, tb, rb) do { if (tb < ta) { float _t = ta; ta = tb; tb = _t; int _r = ra; ra = rb; rb = _r; } } while (0)
 
-// Closest hit over the BVH4.  GATE = AccPathTracer leaf gate (a primitive counts only if its
-// reference leaf box passes Bounds3::IntersectP, which silently drops zero-thickness boxes).
+#define NRCU_REF_DONE ((int)0x80000000)   // "no more work": negative like a leaf so the node loop exits on it
+
+// Pop the next node that can still contain a hit at t <= best_t (ties must stay reachable).
+template <class Stack>
+NR_HD int pop_next(Stack& stack, float best_t) {
+    float pt; int c;
+    for (;;) {
+        if (!stack.pop(pt, c)) return NRCU_REF_DONE;
+        if (pt <= best_t) return c;
+    }
+}
+
+// One BVH4 node: conservative slab test of the four children (explicit fused multiply-adds; the
+// boxes were padded at build time), nearest hit child returned, the other hit children pushed far-to-near.
+template <class Stack>
+NR_HD int node_step(const DScene& s, const RayPrep& rp, int cur, float best_t, Stack& stack) {
+    const f4* n = s.nodes + (size_t)cur * NRCU_BVH_NODE_F4;
+    f4 lox = ldg4(n), hix = ldg4(n + 1), loy = ldg4(n + 2), hiy = ldg4(n + 3), loz = ldg4(n + 4), hiz = ldg4(n + 5);
+    i4 refs = ldg4i(n + 6);
+    float t0, t1, t2, t3;
+#define NRCU_SLAB(k, out) do { \
+    float ax = fmaf(lox.k, rp.inv.x, -rp.oinv.x), bx = fmaf(hix.k, rp.inv.x, -rp.oinv.x); \
+    float ay = fmaf(loy.k, rp.inv.y, -rp.oinv.y), by = fmaf(hiy.k, rp.inv.y, -rp.oinv.y); \
+    float az = fmaf(loz.k, rp.inv.z, -rp.oinv.z), bz = fmaf(hiz.k, rp.inv.z, -rp.oinv.z); \
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
+    out = (tn <= tf) ? tn : NRCU_INF; } while (0)
+    NRCU_SLAB(x, t0); NRCU_SLAB(y, t1); NRCU_SLAB(z, t2); NRCU_SLAB(w, t3);
+#undef NRCU_SLAB
+    int r0 = refs.x, r1 = refs.y, r2 = refs.z, r3 = refs.w;
+    // 5-comparator sorting network: nearest child first
+    NRCU_CSWAP(t0, r0, t1, r1); NRCU_CSWAP(t2, r2, t3, r3);
+    NRCU_CSWAP(t0, r0, t2, r2); NRCU_CSWAP(t1, r1, t3, r3);
+    NRCU_CSWAP(t1, r1, t2, r2);
+    if (t3 < NRCU_INF) stack.push(t3, r3);
+    if (t2 < NRCU_INF) stack.push(t2, r2);
+    if (t1 < NRCU_INF) stack.push(t1, r1);
+    if (t0 < NRCU_INF) return r0;
+    return pop_next(stack, best_t);
+}
+
+// One leaf: the exact reference tests.  GATE = AccPathTracer leaf gate (a primitive counts only if its
+// reference leaf box passes Bounds3::IntersectP, which silently drops zero-thickness boxes); it is
+// evaluated only for candidates that would become the closest hit.
+template <bool GATE>
+NR_HD void leaf_step(const DScene& s, const Ray& ray, int leaf_ref, float& best_t, int& best_id) {
+    const float tmin = (float)0.000001;
+    uint32_t code = (uint32_t)(~leaf_ref);
+    uint32_t first = code >> 4, count = (code & 15u) + 1u;
+    for (uint32_t j = 0; j < count; j++) {
+        uint32_t pk = ldg_u32(s.leaf_prims + first + j);
+        uint32_t id = pk >> 2, kind = pk & 3u;
+        float t;
+        if (!x_prim<false>(s, ray, id, kind, tmin, NRCU_INF, t)) continue;
+        if (t < best_t || (t == best_t && (int)id < best_id)) {
+            if (GATE) {
+                f4 lo = ldg4(s.prim_box + 2 * (size_t)id), hi = ldg4(s.prim_box + 2 * (size_t)id + 1);
+                if (!bounds_intersectp(lo, hi, ray)) continue;
+            }
+            best_t = t; best_id = (int)id;
+        }
+    }
+}
+
+// Closest hit over the BVH4 ("while-while": run inner nodes until a leaf is reached, then the leaf).
 template <bool GATE, class Stack>
 NR_HD void closest_hit_bvh(const DScene& s, const Ray& ray, Stack& stack, float& best_t, int& best_id) {
     best_t = NRCU_INF; best_id = -1;
-    const float tmin = (float)0.000001;
     int cur = s.root_ref;
     if (cur == NRCU_REF_EMPTY) return;
     RayPrep rp = prep_ray(ray);
     for (;;) {
-        if (cur >= 0) {
-            const f4* n = s.nodes + (size_t)cur * NRCU_BVH_NODE_F4;
-            f4 lox = ldg4(n), hix = ldg4(n + 1), loy = ldg4(n + 2), hiy = ldg4(n + 3), loz = ldg4(n + 4), hiz = ldg4(n + 5);
-            i4 refs = ldg4i(n + 6);
-            float t0, t1, t2, t3;
-#define NRCU_SLAB(k, out) do { \
-            float ax = fmaf(lox.k, rp.inv.x, -rp.oinv.x), bx = fmaf(hix.k, rp.inv.x, -rp.oinv.x); \
-            float ay = fmaf(loy.k, rp.inv.y, -rp.oinv.y), by = fmaf(hiy.k, rp.inv.y, -rp.oinv.y); \
-            float az = fmaf(loz.k, rp.inv.z, -rp.oinv.z), bz = fmaf(hiz.k, rp.inv.z, -rp.oinv.z); \
-            float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
-            float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
-            out = (tn <= tf) ? tn : NRCU_INF; } while (0)
-            NRCU_SLAB(x, t0); NRCU_SLAB(y, t1); NRCU_SLAB(z, t2); NRCU_SLAB(w, t3);
-#undef NRCU_SLAB
-            int r0 = refs.x, r1 = refs.y, r2 = refs.z, r3 = refs.w;
-            // 5-comparator sorting network: nearest child first
-            NRCU_CSWAP(t0, r0, t1, r1); NRCU_CSWAP(t2, r2, t3, r3);
-            NRCU_CSWAP(t0, r0, t2, r2); NRCU_CSWAP(t1, r1, t3, r3);
-            NRCU_CSWAP(t1, r1, t2, r2);
-            if (t3 < NRCU_INF) stack.push(t3, r3);
-            if (t2 < NRCU_INF) stack.push(t2, r2);
-            if (t1 < NRCU_INF) stack.push(t1, r1);
-            if (t0 < NRCU_INF) { cur = r0; continue; }
-        } else {
-            uint32_t code = (uint32_t)(~cur);
-            uint32_t first = code >> 4, count = (code & 15u) + 1u;
-            for (uint32_t j = 0; j < count; j++) {
-                uint32_t pk = ldg_u32(s.leaf_prims + first + j);
-                uint32_t id = pk >> 2, kind = pk & 3u;
-                float t;
-                if (!x_prim<false>(s, ray, id, kind, tmin, NRCU_INF, t)) continue;
-                if (t < best_t || (t == best_t && (int)id < best_id)) {
-                    if (GATE) {
-                        f4 lo = ldg4(s.prim_box + 2 * (size_t)id), hi = ldg4(s.prim_box + 2 * (size_t)id + 1);
-                        if (!bounds_intersectp(lo, hi, ray)) continue;
-                    }
-                    best_t = t; best_id = (int)id;
-                }
-            }
-        }
-        // pop the next node that can still contain a hit at t <= best_t
-        float pt;
-        for (;;) {
-            if (!stack.pop(pt, cur)) return;
-            if (pt <= best_t) break;
-        }
+        while (cur >= 0) cur = node_step(s, rp, cur, best_t, stack);
+        if (cur == NRCU_REF_DONE) return;
+        leaf_step<GATE>(s, ray, cur, best_t, best_id);
+        cur = pop_next(stack, best_t);
     }
 }
 

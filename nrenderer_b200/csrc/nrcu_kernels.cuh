@@ -125,6 +125,64 @@ __global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace(DScene s, PathQueu
     }
 }
 
+// v2 of the closest-hit kernel: persistent threads, "while-while" traversal and lane refill.
+// Every lane keeps one ray's traversal state in registers.  When a lane finishes its ray it goes
+// idle; as soon as at least `refill` lanes of the warp are idle (or all of them), the warp claims that
+// many new rays from the queue with ONE atomic (the first idle lane) and hands them out by
+// ballot/popc rank, so warps stay full although path-traced rays have very different lengths.  Leaf
+// work is postponed until every active lane has reached a leaf (Aila & Laine's while-while), which
+// keeps node steps and primitive tests from serialising against each other.
+template <bool GATE>
+__global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace2(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
+                                                               uint32_t* fetch, unsigned long long* ray_counter, uint32_t refill) {
+    __shared__ uint2 stack_mem[NRCU_SMEM_STACK * NRCU_TRACE_THREADS];
+    const uint32_t n = *n_ptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    SmemStack stack; stack.base = stack_mem + threadIdx.x; stack.sp = 0;
+    Ray r; RayPrep rp;
+    r.o = mk3(0.f); r.d = mk3(0.f); rp.inv = mk3(0.f); rp.oinv = mk3(0.f);
+    float best_t = NRCU_INF; int best_id = -1; int cur = NRCU_REF_DONE; uint32_t idx = 0;
+    bool active = false, exhausted = false;
+    for (;;) {
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0xffffffffu && exhausted) break;
+        uint32_t n_idle = __popc(idle);
+        if (!exhausted && n_idle >= (idle == 0xffffffffu ? 1u : refill)) {
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(idle) - 1u;
+            if (lane == leader) {
+                base = atomicAdd(fetch, n_idle);
+                if (base < n) atomicAdd(ray_counter, (unsigned long long)min(n_idle, n - base));
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + n_idle >= n) exhausted = true;
+            if (!active) {
+                uint32_t i = base + __popc(idle & lt);
+                if (i < n) {
+                    f4 a = q.a[i], b = q.b[i];
+                    r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
+                    rp = prep_ray(r);
+                    best_t = NRCU_INF; best_id = -1; stack.sp = 0; idx = i;
+                    cur = s.root_ref == NRCU_REF_EMPTY ? NRCU_REF_DONE : s.root_ref;
+                    active = true;
+                }
+            }
+        }
+        if (active) {
+            while (cur >= 0) cur = node_step(s, rp, cur, best_t, stack);
+            if (cur != NRCU_REF_DONE) {
+                leaf_step<GATE>(s, r, cur, best_t, best_id);
+                cur = pop_next(stack, best_t);
+            }
+            if (cur == NRCU_REF_DONE) {
+                hits[idx] = make_float2(best_t, __int_as_float(best_id));
+                active = false;
+            }
+        }
+    }
+}
+
 // Brute-force variant for the RayCast-mode parity probe (nrcu_trace_batch in NRCU_MODE_RAYCAST).
 __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hits) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

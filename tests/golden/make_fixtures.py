@@ -87,13 +87,20 @@ def make_pt():
         fs.width, fs.height, fs.samples_per_pixel, fs.depth = w, h, spp, depth
         if edit:
             edit(fs)
-        lin, valid, secs = [], np.ones((h, w), bool), []
+        # Validity mask: Screen::set clamps the published sqrt(mean) to [0,1] (Screen.cpp:62-64), so bright pixels
+        # cannot be inverted.  The mask must not depend on the reference's own noise (selecting pixels whose
+        # reference runs happened to stay below 1 biases its mean low): it comes from an independent
+        # high-spp estimate by the oracle (linear mean of every channel < 0.5).
+        osc = po.OracleScene(fs, mode)
+        oacc, _ = osc.render_pt_accum(seed=99, s0=0, s1=2048)
+        valid = ((oacc[..., :3] / oacc[..., 3:4]) < 0.5).all(-1)
+        lin, secs = [], []
         for r in range(runs):
             t0 = time.time()
             img, info = po.run_reference(fs, comp)
             secs.append(info["seconds"])
             rgb = img[..., :3].astype(np.float64)
-            valid &= (rgb < 0.999).all(-1) & np.isfinite(rgb).all(-1)
+            valid &= np.isfinite(rgb).all(-1)
             lin.append(rgb ** 2)
             # the reference seeds its samplers with time(0): make sure the next run sees another second
             time.sleep(max(0.0, 1.1 - (time.time() - t0)))

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""A/B the traversal-kernel knobs on a GPU box: runs bench.py at reduced spp once per setting
+(the knobs are read from the environment when libnrcuda.so first launches a trace kernel)."""
+import json
+import os
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SETTINGS = [
+    {"NRCU_TRACE_VARIANT": "1"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "1"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "4"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "8"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "16"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "24"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "32"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_BLOCKS": "9"},
+    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_BLOCKS": "16"},
+]
+
+
+def main():
+    spp = sys.argv[1] if len(sys.argv) > 1 else "64"
+    extra = sys.argv[2:]
+    for st in SETTINGS:
+        env = dict(os.environ, **st)
+        r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "2", "--warmup", "1", "--spp", spp,
+                            "--no-cpu-baseline", "--e2e-steps", "1"] + extra, capture_output=True, text=True, env=env)
+        try:
+            d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            print(f"{st}: {d['value']:.1f} Mpath/s  {d['mrays_per_s']:.1f} Mrays/s  trace {d['kernel_ms']['trace']:.2f} ms  shade {d['kernel_ms']['shade']:.2f} ms  step {d['ms_per_step']:.2f} ms", flush=True)
+        except Exception:
+            print(st, "FAILED", r.stdout[-500:], r.stderr[-1500:], flush=True)
+
+
+if __name__ == "__main__":
+    main()
