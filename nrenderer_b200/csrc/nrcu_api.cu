@@ -51,18 +51,18 @@ struct nrcu_ctx {
     uint32_t spp = 0;
     DScene ds{};
     // scene buffers
-    DevBuf prim_geom, prim_shade, prim_box, prim_meta, nodes, leaf_prims, materials, area_lights, env;
+    DevBuf prim_geom, prim_shade, prim_box, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_meta, materials, area_lights, env;
     // scene-prep sources kept for nrcu_download_primitives
     DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
     PrimSources ps{};
     // wavefront state
-    DevBuf qa[2], qb[2], qc[2], hits, L, counters, accum_own, rgba_dev;
+    DevBuf qa[2], qb[2], qc[2], hits, surv, L, counters, accum_own, rgba_dev;
     uint32_t queue_capacity = 0, wave_slots = 0;
     unsigned long long* d_ray_counter = nullptr;   // inside `counters`
     // stats
     float ms_setup = 0.f;
-    uint32_t bvh_nodes = 0;
+    uint32_t bvh_nodes = 0, n_big = 0;
     uint64_t launches = 0;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -259,14 +259,17 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     const int cap = 2 * (int)n + 2;
     const int bin_nodes = std::max(64, (int)(0.4 * n) + 8);
     DevBuf prim_node, nbox, cbox, ncount, nidmin, nidmax, nstate, nchild, nsplit_axis, nsplit_pos, ndepth, nleaf_first, nleaf_fill,
-        nwide, bins, counters, nbin_slot, wide_tmp;
+        nwide, bins, counters, nbin_slot, wide_tmp, big_count;
     CTX_CUDA(prim_node.ensure(sizeof(int) * (size_t)n));
     CTX_CUDA(nbox.ensure(sizeof(int) * 6 * (size_t)cap)); CTX_CUDA(cbox.ensure(sizeof(int) * 6 * (size_t)cap));
     DevBuf* per_node[] = {&ncount, &nidmin, &nidmax, &nstate, &nchild, &nsplit_axis, &nsplit_pos, &ndepth, &nleaf_first, &nleaf_fill, &nwide, &nbin_slot};
     for (DevBuf* b : per_node) CTX_CUDA(b->ensure(sizeof(int) * (size_t)cap));
     CTX_CUDA(bins.ensure(sizeof(int) * (size_t)bin_nodes * 3 * NRCU_NBINS * NRCU_BIN_WORDS));
-    CTX_CUDA(counters.ensure(sizeof(int) * 8));
+    CTX_CUDA(counters.ensure(sizeof(int) * 8)); CTX_CUDA(big_count.ensure(sizeof(int)));
     CTX_CUDA(ctx->leaf_prims.ensure(sizeof(uint32_t) * (size_t)n));
+    CTX_CUDA(ctx->leaf_geom.ensure(sizeof(f4) * 3 * (size_t)n)); CTX_CUDA(ctx->leaf_box.ensure(sizeof(f4) * 2 * (size_t)n));
+    CTX_CUDA(ctx->big_geom.ensure(sizeof(f4) * 3 * NRCU_MAX_BIG)); CTX_CUDA(ctx->big_box.ensure(sizeof(f4) * 2 * NRCU_MAX_BIG));
+    CTX_CUDA(ctx->big_meta.ensure(sizeof(uint32_t) * NRCU_MAX_BIG));
     CTX_CUDA(wide_tmp.ensure(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1u, n)));
 
     BvhBuild b{};
@@ -277,6 +280,8 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     b.nleaf_first = nleaf_first.as<int>(); b.nleaf_fill = nleaf_fill.as<int>(); b.nwide = nwide.as<int>();
     b.bins = bins.as<int>(); b.bin_nodes = bin_nodes; b.counters = counters.as<int>(); b.nbin_slot = nbin_slot.as<int>();
     b.leaf_prims = ctx->leaf_prims.as<uint32_t>(); b.wide_nodes = wide_tmp.as<f4>();
+    b.prim_geom = ctx->prim_geom.as<f4>(); b.leaf_geom = ctx->leaf_geom.as<f4>(); b.leaf_box = ctx->leaf_box.as<f4>();
+    b.big_geom = ctx->big_geom.as<f4>(); b.big_box = ctx->big_box.as<f4>(); b.big_meta = ctx->big_meta.as<uint32_t>(); b.big_count = big_count.as<int>();
     b.inflate = max_abs_coord * (1.0f / 65536.0f);
     cudaStream_t st = ctx->stream;
     const int T = 128;
@@ -285,6 +290,24 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     CTX_CUDA(cudaMemcpyAsync(counters.p, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
     k_bvh_clear<<<grid_for(cap, T), T, 0, st>>>(b, 0, cap); CTX_LAUNCH_CHECK("k_bvh_clear");
     k_bvh_init_prim<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_init_prim");
+    // wide primitives leave the tree; node 0 is rebuilt from the rest
+    k_bvh_select_big<<<1, 1, 0, st>>>(b, 0, 1); CTX_LAUNCH_CHECK("k_bvh_select_big");
+    k_bvh_clear<<<1, 1, 0, st>>>(b, 0, 1); CTX_LAUNCH_CHECK("k_bvh_clear");
+    k_bvh_init_prim_rest<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_init_prim_rest");
+    int n_big = 0, root_box[6];
+    CTX_CUDA(cudaMemcpyAsync(&n_big, big_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaMemcpyAsync(root_box, nbox.p, sizeof(root_box), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaStreamSynchronize(st));
+    ctx->n_big = (uint32_t)n_big;
+    DScene& ds = ctx->ds;
+    ds.big_geom = ctx->big_geom.as<f4>(); ds.big_box = ctx->big_box.as<f4>(); ds.big_meta = ctx->big_meta.as<uint32_t>(); ds.n_big = (uint32_t)n_big;
+    ds.nodes = nullptr; ds.leaf_prims = ctx->leaf_prims.as<uint32_t>(); ds.leaf_geom = ctx->leaf_geom.as<f4>(); ds.leaf_box = ctx->leaf_box.as<f4>();
+    ds.root_ref = NRCU_REF_EMPTY; ds.bvh_lo = mk3(NRCU_INF); ds.bvh_hi = mk3(-NRCU_INF);
+    ctx->bvh_nodes = 0;
+    const uint32_t n_rest = n - (uint32_t)n_big;
+    if (n_rest == 0) return NRCU_OK;   // everything is in the wide list
+    bvh_padded_bounds(root_box, b.inflate, ds.bvh_lo, ds.bvh_hi);
+
     int begin = 0, end = 1;
     for (int level = 0; level < 128; level++) {
         b.level_begin = begin; b.level_end = end;
@@ -302,9 +325,10 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     k_bvh_leaf_alloc<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_leaf_alloc");
     k_bvh_leaf_fill<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_leaf_fill");
     k_bvh_leaf_sort<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_leaf_sort");
+    k_bvh_leaf_gather<<<grid_for(n_rest, T), T, 0, st>>>(b, 0, (int)n_rest); CTX_LAUNCH_CHECK("k_bvh_leaf_gather");
     k_bvh_wide_index<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_wide_index");
     k_bvh_wide_emit<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_wide_emit");
-    // root reference: wide index of node 0, or a leaf reference when the whole scene fits one leaf
+    // root reference: wide index of node 0, or a leaf reference when everything left fits one leaf
     int root_state = 0, root_wide = -1, root_cnt = 0, root_first = 0;
     CTX_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
     CTX_CUDA(cudaMemcpyAsync(&root_state, nstate.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -316,9 +340,8 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     CTX_CUDA(ctx->nodes.ensure(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1, n_wide)));
     if (n_wide) CTX_CUDA(cudaMemcpyAsync(ctx->nodes.p, wide_tmp.p, sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)n_wide, cudaMemcpyDeviceToDevice, st));
     CTX_CUDA(cudaStreamSynchronize(st));
-    ctx->ds.nodes = ctx->nodes.as<f4>();
-    ctx->ds.leaf_prims = ctx->leaf_prims.as<uint32_t>();
-    ctx->ds.root_ref = root_state == BNODE_LEAF ? ~((root_first << 4) | (root_cnt - 1)) : root_wide;
+    ds.nodes = ctx->nodes.as<f4>();
+    ds.root_ref = root_state == BNODE_LEAF ? ~((root_first << 4) | (root_cnt - 1)) : root_wide;
     ctx->bvh_nodes = (uint32_t)n_wide;
     return NRCU_OK;
 }
@@ -358,7 +381,7 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
 // ---------------------------------------------------------------------------------------------
 // rendering
 // ---------------------------------------------------------------------------------------------
-enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, then [depth+1] fetch cursors */ };
+enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
 
 static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth) {
     for (int k = 0; k < 2; k++) {
@@ -367,27 +390,14 @@ static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_
         CTX_CUDA(ctx->qc[k].ensure(sizeof(f4) * (size_t)capacity));
     }
     CTX_CUDA(ctx->hits.ensure(sizeof(float2) * (size_t)capacity));
+    CTX_CUDA(ctx->surv.ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(ctx->L.ensure(sizeof(f4) * (size_t)slots));
-    CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 2 * (size_t)depth + 8)));
+    CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 3 * (size_t)depth + 12)));
     ctx->queue_capacity = capacity; ctx->wave_slots = slots;
     return NRCU_OK;
 }
 
 }  // extern "C"
-
-// Traversal kernel variant and its refill threshold (tuning knobs; NRCU_TRACE_VARIANT=1 selects the
-// first, batch-of-32 kernel kept for A/B measurements).
-static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
-static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
-static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
-
-template <bool GATE>
-static void launch_trace(nrcu_ctx* ctx, unsigned grid, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* fetch, unsigned long long* rays) {
-    if (trace_variant() == 1) k_trace<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_ptr, hits, fetch, rays);
-    else k_trace2<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_ptr, hits, fetch, rays, trace_refill());
-}
-
-extern "C" {
 
 static int sm_count(int device) {
     static int cached[64] = {0};
@@ -397,6 +407,32 @@ static int sm_count(int device) {
     if (device < 64) cached[device] = n;
     return n;
 }
+
+// Traversal kernel variant and its refill threshold (tuning knobs; NRCU_TRACE_VARIANT=1 selects the
+// first, batch-of-32 kernel kept for A/B measurements).
+static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
+static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
+static uint32_t env_u32(const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : dflt; }
+static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
+static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
+static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
+
+// Closest hit for the first *n_ptr entries of queue `q` into hits[]: stage 1 (wide primitives, every ray) then
+// stage 2 (BVH traversal of the survivors).  `work` points at three zeroed words: survivor count, fetch cursor, spare.
+template <bool GATE>
+static void launch_closest_hit(nrcu_ctx* ctx, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* surv,
+                               uint32_t* n_surv, uint32_t* fetch, unsigned long long* rays, int* launches) {
+    const unsigned sms = (unsigned)sm_count(ctx->device);
+    k_big<GATE><<<sms * 8, 256, 0, ctx->stream>>>(ds, q, n_ptr, hits, surv, n_surv, rays);
+    (*launches)++;
+    if (ds.root_ref == NRCU_REF_EMPTY) return;
+    const unsigned grid = sms * trace_blocks_per_sm();
+    if (trace_variant() == 3) k_trace3<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill(), trace_w_node(), trace_w_prim());
+    else k_trace2<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
+    (*launches)++;
+}
+
+extern "C" {
 
 static cudaEvent_t pool_event(nrcu_ctx* ctx, size_t i) {
     while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
@@ -425,10 +461,11 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     unsigned long long* d_rays = reinterpret_cast<unsigned long long*>(cnt + CNT_RAYS);
     uint32_t* d_qn = cnt + CNT_QUEUE0;                 // queue size entering bounce d
     uint32_t* d_fetch = cnt + CNT_QUEUE0 + ds.depth + 2;  // work-fetch cursor of bounce d
-    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 2 * (size_t)ds.depth + 8);
+    uint32_t* d_nsurv = cnt + CNT_QUEUE0 + 2 * (ds.depth + 2);  // stage-1 survivors of bounce d
+    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 3 * (size_t)ds.depth + 12);
     cudaStream_t st = ctx->stream;
     const int sms = sm_count(ctx->device);
-    const unsigned trace_grid = (unsigned)sms * trace_blocks_per_sm(), shade_grid = (unsigned)sms * 4;
+    const unsigned shade_grid = (unsigned)sms * 4;
     const bool timing = stats != nullptr;
     size_t ev_i = 0;
     struct Span { size_t a, b; int kind; };
@@ -444,9 +481,11 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         for (uint32_t d = 0; d < ds.depth; d++) {
             PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
-            if (ctx->mode == NRCU_MODE_ACC) launch_trace<true>(ctx, trace_grid, ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
-            else launch_trace<false>(ctx, trace_grid, ds, qi, d_qn + d, ctx->hits.as<float2>(), d_fetch + d, d_rays);
-            CTX_LAUNCH_CHECK("k_trace");
+            int nl = 0;
+            if (ctx->mode == NRCU_MODE_ACC) launch_closest_hit<true>(ctx, ds, qi, d_qn + d, ctx->hits.as<float2>(), ctx->surv.as<uint32_t>(), d_nsurv + d, d_fetch + d, d_rays, &nl);
+            else launch_closest_hit<false>(ctx, ds, qi, d_qn + d, ctx->hits.as<float2>(), ctx->surv.as<uint32_t>(), d_nsurv + d, d_fetch + d, d_rays, &nl);
+            ctx->launches += nl - 1;
+            CTX_LAUNCH_CHECK("k_big/k_trace");
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
             k_shade<<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, ctx->hits.as<float2>(), qo, d_qn + d + 1, capacity, ctx->L.as<f4>());
             CTX_LAUNCH_CHECK("k_shade");
@@ -549,21 +588,22 @@ int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim
     if (!rays) { ctx->error = "rays is null"; return NRCU_ERR_INVALID; }
     CTX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    DevBuf d_rays, qa, qb, hits, cnt;
+    DevBuf d_rays, qa, qb, hits, surv, cnt;
     CTX_CUDA(d_rays.ensure(sizeof(float) * 6 * (size_t)n)); CTX_CUDA(qa.ensure(sizeof(f4) * (size_t)n)); CTX_CUDA(qb.ensure(sizeof(f4) * (size_t)n));
-    CTX_CUDA(hits.ensure(sizeof(float2) * (size_t)n)); CTX_CUDA(cnt.ensure(32));
+    CTX_CUDA(hits.ensure(sizeof(float2) * (size_t)n)); CTX_CUDA(surv.ensure(sizeof(uint32_t) * (size_t)n)); CTX_CUDA(cnt.ensure(32));
     CTX_CUDA(cudaMemcpyAsync(d_rays.p, rays, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, st));
-    uint32_t h_cnt[8] = {0, 0, n, 0, 0, 0, 0, 0};   // [0..1] ray counter, [2] n, [3] fetch cursor
+    uint32_t h_cnt[8] = {0, 0, n, 0, 0, 0, 0, 0};   // [0..1] ray counter, [2] n, [3] fetch cursor, [4] survivors
     CTX_CUDA(cudaMemcpyAsync(cnt.p, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
     PathQueue q{qa.as<f4>(), qb.as<f4>(), nullptr};
     k_pack_rays<<<grid_for(n, 256), 256, 0, st>>>(d_rays.as<float>(), n, q);
     CTX_LAUNCH_CHECK("k_pack_rays");
     uint32_t* c = cnt.as<uint32_t>();
-    const unsigned trace_grid = (unsigned)sm_count(ctx->device) * trace_blocks_per_sm();
-    if (ctx->mode == NRCU_MODE_RAYCAST) k_trace_linear_rc<<<grid_for(n, 128), 128, 0, st>>>(ctx->ds, q, n, hits.as<float2>());
-    else if (ctx->mode == NRCU_MODE_ACC) launch_trace<true>(ctx, trace_grid, ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
-    else launch_trace<false>(ctx, trace_grid, ctx->ds, q, c + 2, hits.as<float2>(), c + 3, reinterpret_cast<unsigned long long*>(c));
-    CTX_LAUNCH_CHECK("k_trace");
+    int nl = 0;
+    if (ctx->mode == NRCU_MODE_RAYCAST) { k_trace_linear_rc<<<grid_for(n, 128), 128, 0, st>>>(ctx->ds, q, n, hits.as<float2>()); nl = 1; }
+    else if (ctx->mode == NRCU_MODE_ACC) launch_closest_hit<true>(ctx, ctx->ds, q, c + 2, hits.as<float2>(), surv.as<uint32_t>(), c + 4, c + 3, reinterpret_cast<unsigned long long*>(c), &nl);
+    else launch_closest_hit<false>(ctx, ctx->ds, q, c + 2, hits.as<float2>(), surv.as<uint32_t>(), c + 4, c + 3, reinterpret_cast<unsigned long long*>(c), &nl);
+    ctx->launches += nl - 1;
+    CTX_LAUNCH_CHECK("k_big/k_trace");
     std::vector<float2> h(n);
     CTX_CUDA(cudaMemcpyAsync(h.data(), hits.p, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CTX_CUDA(cudaStreamSynchronize(st));

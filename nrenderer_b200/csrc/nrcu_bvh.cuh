@@ -78,6 +78,12 @@ struct BvhBuild {
     int level_begin, level_end;
     // outputs
     uint32_t* leaf_prims;      // [n_prims]
+    const f4* prim_geom;       // 3 per primitive (gather source)
+    f4* leaf_geom;             // [n_prims * 3] prim_geom in leaf order
+    f4* leaf_box;              // [n_prims * 2] prim_box in leaf order
+    // wide-primitive list (outputs of bvh_select_big)
+    f4* big_geom; f4* big_box; uint32_t* big_meta;   // capacity NRCU_MAX_BIG
+    int* big_count;            // [1]
     f4* wide_nodes;            // [wide capacity * 7]
     float inflate;             // absolute padding of wide-node boxes
 };
@@ -108,6 +114,56 @@ NR_HD void node_add_prim(const BvhBuild& b, int n, int i) {
 // step 0: one work item per primitive
 NR_HD void bvh_init_prim(const BvhBuild& b, int i) { b.prim_node[i] = 0; node_add_prim(b, 0, i); }
 
+NR_HD float half_area(const float* lo, const float* hi) {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+#define NRCU_PRIM_EXCLUDED (-2)
+NR_HD float box_half_area(f4 lo, f4 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+// step 0b (ONE work item, after step 0 has produced the scene box in node 0): pick the "wide" primitives — box
+// surface area >= NRCU_BIG_AREA_FRACTION of the scene box's, the NRCU_MAX_BIG largest if there are more (ties to
+// the lower id) — copy their records to the wide list in ascending id order and mark them excluded from the BVH.
+// A primitive this large is entered by most rays whatever the tree looks like (its SAH probability is ~1), so it
+// is cheaper to test it once per ray in a warp-uniform loop than to let it bloat the boxes of the top BVH levels.
+NR_HD void bvh_select_big(const BvhBuild& b, int) {
+    float rlo[3], rhi[3];
+    for (int a = 0; a < 3; a++) { rlo[a] = fkey_inv(b.nbox[a]); rhi[a] = fkey_inv(b.nbox[3 + a]); }
+    const float root_area = half_area(rlo, rhi);
+    int ids[NRCU_MAX_BIG]; float areas[NRCU_MAX_BIG]; int cnt = 0;
+    if (root_area > 0.f && root_area < NRCU_INF) {
+        const float thr = NRCU_BIG_AREA_FRACTION * root_area;
+        for (int i = 0; i < (int)b.n_prims; i++) {
+            float ar = box_half_area(b.prim_box[2 * i], b.prim_box[2 * i + 1]);
+            if (!(ar >= thr)) continue;
+            // keep the list sorted by (area desc, id asc); drop the smallest when full
+            int pos = cnt;
+            while (pos > 0 && areas[pos - 1] < ar) pos--;
+            if (pos >= NRCU_MAX_BIG) continue;
+            int last = cnt < NRCU_MAX_BIG ? cnt : NRCU_MAX_BIG - 1;
+            for (int k = last; k > pos; k--) { ids[k] = ids[k - 1]; areas[k] = areas[k - 1]; }
+            ids[pos] = i; areas[pos] = ar;
+            if (cnt < NRCU_MAX_BIG) cnt++;
+        }
+    }
+    // ascending id order (insertion sort, <= 32 entries)
+    for (int i = 1; i < cnt; i++) { int v = ids[i], j = i - 1; while (j >= 0 && ids[j] > v) { ids[j + 1] = ids[j]; j--; } ids[j + 1] = v; }
+    for (int k = 0; k < cnt; k++) {
+        int id = ids[k];
+        for (int q = 0; q < 3; q++) b.big_geom[3 * k + q] = b.prim_geom[3 * (size_t)id + q];
+        for (int q = 0; q < 2; q++) b.big_box[2 * k + q] = b.prim_box[2 * (size_t)id + q];
+        b.big_meta[k] = ((uint32_t)id << 2) | (b.prim_meta[id] & 3u);
+        b.prim_node[id] = NRCU_PRIM_EXCLUDED;
+    }
+    *b.big_count = cnt;
+}
+// step 0c: one work item per primitive — rebuild node 0 from the primitives that stay in the BVH
+// (node 0 must have been cleared again with node_clear first)
+NR_HD void bvh_init_prim_rest(const BvhBuild& b, int i) { if (b.prim_node[i] != NRCU_PRIM_EXCLUDED) node_add_prim(b, 0, i); }
+
 // step A (per node of the level): decide leaf / open and hand out a bin slot
 NR_HD void bvh_level_prepare(const BvhBuild& b, int n) {
     if (b.ncount[n] <= NRCU_LEAF_MAX) { b.nstate[n] = BNODE_LEAF; return; }
@@ -132,7 +188,7 @@ NR_HD int bin_of(float c, float lo, float hi) {
 // step B (per primitive)
 NR_HD void bvh_bin(const BvhBuild& b, int i) {
     int n = b.prim_node[i];
-    if (n < b.level_begin || b.nstate[n] != BNODE_OPEN) return;
+    if (n < 0 || n < b.level_begin || b.nstate[n] != BNODE_OPEN) return;
     int slot = b.nbin_slot[n];
     if (slot < 0 || slot >= b.bin_nodes) return;
     f4 lo = b.prim_box[2 * i], hi = b.prim_box[2 * i + 1];
@@ -148,10 +204,6 @@ NR_HD void bvh_bin(const BvhBuild& b, int i) {
     }
 }
 
-NR_HD float half_area(const float* lo, const float* hi) {
-    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-    return dx * dy + dy * dz + dz * dx;
-}
 
 // step C (per node of the level): choose the split and allocate the children
 NR_HD void bvh_split(const BvhBuild& b, int n) {
@@ -209,7 +261,7 @@ NR_HD void bvh_split(const BvhBuild& b, int n) {
 // step D (per primitive)
 NR_HD void bvh_partition(const BvhBuild& b, int i) {
     int n = b.prim_node[i];
-    if (n < b.level_begin || b.nstate[n] != BNODE_INNER) return;
+    if (n < 0 || n < b.level_begin || b.nstate[n] != BNODE_INNER) return;
     int side;
     int a = b.nsplit_axis[n];
     if (a == 3) side = (i <= f2i(b.nsplit_pos[n])) ? 0 : 1;
@@ -231,6 +283,7 @@ NR_HD void bvh_leaf_alloc(const BvhBuild& b, int n) {
 }
 NR_HD void bvh_leaf_fill(const BvhBuild& b, int i) {
     int n = b.prim_node[i];
+    if (n < 0) return;   // wide primitive, not in the tree
     int pos = b.nleaf_first[n] + atomic_add_i(&b.nleaf_fill[n], 1);
     b.leaf_prims[pos] = ((uint32_t)i << 2) | (b.prim_meta[i] & 3u);
 }
@@ -241,7 +294,25 @@ NR_HD void bvh_leaf_sort(const BvhBuild& b, int n) {
     for (int i = 1; i < c; i++) { uint32_t v = p[i]; int j = i - 1; while (j >= 0 && p[j] > v) { p[j + 1] = p[j]; j--; } p[j + 1] = v; }
 }
 
+// per leaf slot: copy the primitive's intersection record and reference box next to its neighbours in the leaf
+NR_HD void bvh_leaf_gather(const BvhBuild& b, int slot) {
+    uint32_t id = b.leaf_prims[slot] >> 2;
+    for (int k = 0; k < 3; k++) b.leaf_geom[3 * (size_t)slot + k] = b.prim_geom[3 * (size_t)id + k];
+    for (int k = 0; k < 2; k++) b.leaf_box[2 * (size_t)slot + k] = b.prim_box[2 * (size_t)id + k];
+}
+
 NR_HD int leaf_ref(const BvhBuild& b, int n) { return ~((b.nleaf_first[n] << 4) | (b.ncount[n] - 1)); }
+
+// Padded bounds of the whole tree from node 0's encoded box (same padding as the wide-node boxes).
+NR_HD void bvh_padded_bounds(const int* root_box_keys, float inflate, vec3& lo, vec3& hi) {
+    float l[3], h[3];
+    for (int a = 0; a < 3; a++) {
+        float lv = fkey_inv(root_box_keys[a]), hv = fkey_inv(root_box_keys[3 + a]);
+        float pad = inflate + 1e-6f * fmaxf(fabsf(lv), fabsf(hv));
+        l[a] = lv - pad; h[a] = hv + pad;
+    }
+    lo = mk3(l[0], l[1], l[2]); hi = mk3(h[0], h[1], h[2]);
+}
 
 // wide emission, pass 1 (per binary node): hand out wide indices
 NR_HD void bvh_wide_index(const BvhBuild& b, int n) {

@@ -71,7 +71,12 @@ NR_HD bool x_quad(const Ray& ray, f4 g0, f4 g1, f4 g2, float tmin, float tmax, f
     float nd = dot(ray.d, n);
     if (nd < 0.0000001f && nd > -0.00000001f) return false;
     float dp = -dot(p, n);
-    float t = (-dp - dot(n, ray.o)) / nd;
+    float num = -dp - dot(n, ray.o);
+    // |nd| >= 1e-8 here, so |num| < 1e-30 gives |t| < 1e-22 < tMin: rejected exactly like the reference,
+    // without the division (a zero / denormal numerator - a ray leaving the very plane it is tested
+    // against - would otherwise take the slow path of the IEEE division on the device).
+    if (fabsf(num) < 1e-30f) return false;
+    float t = num / nd;
     if (!t_in_range<RC>(t, tmin, tmax)) return false;
     vec3 q = ray_at(ray, t) - p;
     // glm mat3*vec3 (type_mat3x3.inl:468-474): m[0][r]*v.x + m[1][r]*v.y + m[2][r]*v.z
@@ -105,13 +110,12 @@ NR_HD bool x_prim(const DScene& s, const Ray& ray, uint32_t id, uint32_t kind, f
 }
 
 // Bounds3::IntersectP, acc_path_tracing/include/Bounds3.hpp:141-168, with invDir as built in
-// BVHTree::getIntersect (BVH.hpp:97: double 1./d narrowed to float; identical to 1.f/d because
-// IEEE division is correctly rounded in both widths for float operands... the double quotient is
-// rounded twice, so it is evaluated in double here as well).
-NR_HD bool bounds_intersectp(f4 lo, f4 hi, const Ray& ray) {
+// BVHTree::getIntersect (BVH.hpp:97: double 1./d narrowed to float).  Rounding the double quotient
+// to float gives the correctly rounded float quotient (double rounding is innocuous for division
+// when the wide format has >= 2p+2 = 50 bits), so (ix, iy, iz) = IEEE 1.0f/d is bit-identical.
+NR_HD bool bounds_intersectp_inv(f4 lo, f4 hi, const Ray& ray, float ix, float iy, float iz) {
     vec3 o = ray.o, d = ray.d;
     if (o.x >= lo.x && o.x <= hi.x && o.y >= lo.y && o.y <= hi.y && o.z >= lo.z && o.z <= hi.z) return true;
-    float ix = (float)(1. / (double)d.x), iy = (float)(1. / (double)d.y), iz = (float)(1. / (double)d.z);
     float t1n = (lo.x - o.x) * ix, t2n = (lo.y - o.y) * iy, t3n = (lo.z - o.z) * iz;
     float t1x = (hi.x - o.x) * ix, t2x = (hi.y - o.y) * iy, t3x = (hi.z - o.z) * iz;
     if (d.x < 0) { float t = t1n; t1n = t1x; t1x = t; }
@@ -121,6 +125,9 @@ NR_HD bool bounds_intersectp(f4 lo, f4 hi, const Ray& ray) {
     float in1 = (t2n < t3n) ? t3n : t2n, t_near = (t1n < in1) ? in1 : t1n;
     float in2 = (t3x < t2x) ? t3x : t2x, t_far = (in2 < t1x) ? in2 : t1x;
     return t_far >= 0 && t_near < t_far;
+}
+NR_HD bool bounds_intersectp(f4 lo, f4 hi, const Ray& ray) {
+    return bounds_intersectp_inv(lo, hi, ray, 1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
 }
 
 // ---- traversal -------------------------------------------------------------------------------
@@ -190,40 +197,77 @@ NR_HD int node_step(const DScene& s, const RayPrep& rp, int cur, float best_t, S
     return pop_next(stack, best_t);
 }
 
-// One leaf: the exact reference tests.  GATE = AccPathTracer leaf gate (a primitive counts only if its
-// reference leaf box passes Bounds3::IntersectP, which silently drops zero-thickness boxes); it is
-// evaluated only for candidates that would become the closest hit.
+// One primitive record (g0..g2 = its intersection record, box2 = its reference leaf box, pk = id << 2 | kind):
+// the exact reference test.  GATE = AccPathTracer leaf gate (a primitive counts only if its reference leaf box
+// passes Bounds3::IntersectP, which silently drops zero-thickness boxes); it is evaluated only for candidates
+// that would become the closest hit, with the exact reciprocals `ginv` of the ray direction.  Equal-t ties go
+// to the lowest primitive id whatever the visiting order.
 template <bool GATE>
-NR_HD void leaf_step(const DScene& s, const Ray& ray, int leaf_ref, float& best_t, int& best_id) {
+NR_HD void prim_test(const Ray& ray, vec3 ginv, f4 g0, f4 g1, f4 g2, const f4* box2, uint32_t pk, float& best_t, int& best_id) {
     const float tmin = (float)0.000001;
-    uint32_t code = (uint32_t)(~leaf_ref);
-    uint32_t first = code >> 4, count = (code & 15u) + 1u;
-    for (uint32_t j = 0; j < count; j++) {
-        uint32_t pk = ldg_u32(s.leaf_prims + first + j);
-        uint32_t id = pk >> 2, kind = pk & 3u;
-        float t;
-        if (!x_prim<false>(s, ray, id, kind, tmin, NRCU_INF, t)) continue;
-        if (t < best_t || (t == best_t && (int)id < best_id)) {
-            if (GATE) {
-                f4 lo = ldg4(s.prim_box + 2 * (size_t)id), hi = ldg4(s.prim_box + 2 * (size_t)id + 1);
-                if (!bounds_intersectp(lo, hi, ray)) continue;
-            }
-            best_t = t; best_id = (int)id;
+    const uint32_t id = pk >> 2, kind = pk & 3u;
+    float t;
+    bool hit;
+    if (kind == KIND_PLANE) hit = x_quad<false>(ray, g0, g1, g2, tmin, NRCU_INF, t);
+    else if (kind == KIND_SPHERE) hit = x_sphere<false>(ray, g0, tmin, NRCU_INF, t);
+    else hit = x_triangle<false>(ray, g0, g1, g2, tmin, NRCU_INF, t);
+    if (hit && (t < best_t || (t == best_t && (int)id < best_id))) {
+        if (GATE) {
+            f4 lo = box2[0], hi = box2[1];
+            if (!bounds_intersectp_inv(lo, hi, ray, ginv.x, ginv.y, ginv.z)) return;
         }
+        best_t = t; best_id = (int)id;
     }
 }
+// Exact IEEE reciprocals of the direction for the leaf gate (BVH.hpp:97).
+NR_HD vec3 gate_inverse(const Ray& ray) { return mk3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z); }
 
-// Closest hit over the BVH4 ("while-while": run inner nodes until a leaf is reached, then the leaf).
+// The same for leaf slot `slot` of the leaf-ordered arrays.
+template <bool GATE>
+NR_HD void prim_step(const DScene& s, const Ray& ray, vec3 ginv, uint32_t slot, uint32_t pk, float& best_t, int& best_id) {
+    const f4* g = s.leaf_geom + 3 * (size_t)slot;
+    f4 g0 = ldg4(g), g1 = ldg4(g + 1), g2 = ldg4(g + 2);
+    prim_test<GATE>(ray, ginv, g0, g1, g2, s.leaf_box + 2 * (size_t)slot, pk, best_t, best_id);
+}
+
+template <bool GATE>
+NR_HD void leaf_step(const DScene& s, const Ray& ray, vec3 ginv, int leaf_ref, float& best_t, int& best_id) {
+    uint32_t code = (uint32_t)(~leaf_ref);
+    uint32_t first = code >> 4, count = (code & 15u) + 1u;
+    for (uint32_t j = 0; j < count; j++) prim_step<GATE>(s, ray, ginv, first + j, ldg_u32(s.leaf_prims + first + j), best_t, best_id);
+}
+
+// The wide primitives (DScene::big_*), tested in list order by every ray before the traversal.
+template <bool GATE>
+NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const uint32_t* meta, const Ray& ray, vec3 ginv, float& best_t, int& best_id) {
+    for (uint32_t k = 0; k < s.n_big; k++)
+        prim_test<GATE>(ray, ginv, geom[3 * k], geom[3 * k + 1], geom[3 * k + 2], box + 2 * k, meta[k], best_t, best_id);
+}
+// Can anything inside the BVH still beat best_t?  Conservative slab test against the padded BVH bounds.
+NR_HD bool bvh_reachable(const DScene& s, const RayPrep& rp, float best_t) {
+    if (s.root_ref == NRCU_REF_EMPTY) return false;
+    float ax = fmaf(s.bvh_lo.x, rp.inv.x, -rp.oinv.x), bx = fmaf(s.bvh_hi.x, rp.inv.x, -rp.oinv.x);
+    float ay = fmaf(s.bvh_lo.y, rp.inv.y, -rp.oinv.y), by = fmaf(s.bvh_hi.y, rp.inv.y, -rp.oinv.y);
+    float az = fmaf(s.bvh_lo.z, rp.inv.z, -rp.oinv.z), bz = fmaf(s.bvh_hi.z, rp.inv.z, -rp.oinv.z);
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t));
+    return tn <= tf;
+}
+
+// Closest hit: the wide primitives first, then the BVH4 ("while-while": run inner nodes until a leaf is
+// reached, then the leaf).  This is the single-ray statement of what k_big + k_trace* do on the device.
 template <bool GATE, class Stack>
 NR_HD void closest_hit_bvh(const DScene& s, const Ray& ray, Stack& stack, float& best_t, int& best_id) {
     best_t = NRCU_INF; best_id = -1;
-    int cur = s.root_ref;
-    if (cur == NRCU_REF_EMPTY) return;
     RayPrep rp = prep_ray(ray);
+    vec3 ginv = gate_inverse(ray);
+    big_list_step<GATE>(s, s.big_geom, s.big_box, s.big_meta, ray, ginv, best_t, best_id);
+    if (!bvh_reachable(s, rp, best_t)) return;
+    int cur = s.root_ref;
     for (;;) {
         while (cur >= 0) cur = node_step(s, rp, cur, best_t, stack);
         if (cur == NRCU_REF_DONE) return;
-        leaf_step<GATE>(s, ray, cur, best_t, best_id);
+        leaf_step<GATE>(s, ray, ginv, cur, best_t, best_id);
         cur = pop_next(stack, best_t);
     }
 }

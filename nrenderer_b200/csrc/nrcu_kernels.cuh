@@ -29,6 +29,8 @@ __global__ void k_build_prims(PrimSources ps, uint32_t n, int raycast, f4* geom,
         int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= count) return; body(b, first + i); }
 NRCU_STEP_KERNEL(k_bvh_clear, node_clear)
 NRCU_STEP_KERNEL(k_bvh_init_prim, bvh_init_prim)
+NRCU_STEP_KERNEL(k_bvh_select_big, bvh_select_big)
+NRCU_STEP_KERNEL(k_bvh_init_prim_rest, bvh_init_prim_rest)
 NRCU_STEP_KERNEL(k_bvh_level_prepare, bvh_level_prepare)
 NRCU_STEP_KERNEL(k_bvh_bin, bvh_bin)
 NRCU_STEP_KERNEL(k_bvh_split, bvh_split)
@@ -36,6 +38,7 @@ NRCU_STEP_KERNEL(k_bvh_partition, bvh_partition)
 NRCU_STEP_KERNEL(k_bvh_leaf_alloc, bvh_leaf_alloc)
 NRCU_STEP_KERNEL(k_bvh_leaf_fill, bvh_leaf_fill)
 NRCU_STEP_KERNEL(k_bvh_leaf_sort, bvh_leaf_sort)
+NRCU_STEP_KERNEL(k_bvh_leaf_gather, bvh_leaf_gather)
 NRCU_STEP_KERNEL(k_bvh_wide_index, bvh_wide_index)
 NRCU_STEP_KERNEL(k_bvh_wide_emit, bvh_wide_emit)
 
@@ -77,107 +80,244 @@ __global__ void k_raygen(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_s
 }
 
 #define NRCU_TRACE_THREADS 128
-#define NRCU_SMEM_STACK 20
-// Traversal stack: the first NRCU_SMEM_STACK entries of every thread live in shared memory
-// ([entry][thread] so that a warp's accesses are conflict free), deeper ones in local memory.
-struct SmemStack {
-    uint2* base; int sp;
-    float ot[NRCU_LOCAL_STACK - NRCU_SMEM_STACK]; int oref[NRCU_LOCAL_STACK - NRCU_SMEM_STACK];
-    __device__ __forceinline__ void push(float t, int r) {
-        if (sp < NRCU_SMEM_STACK) base[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t), (unsigned)r);
-        else if (sp < NRCU_LOCAL_STACK) { ot[sp - NRCU_SMEM_STACK] = t; oref[sp - NRCU_SMEM_STACK] = r; }
-        else return;
-        sp++;
-    }
-    __device__ __forceinline__ bool pop(float& t, int& r) {
-        if (sp == 0) return false;
-        sp--;
-        if (sp < NRCU_SMEM_STACK) { uint2 v = base[sp * NRCU_TRACE_THREADS]; t = __uint_as_float(v.x); r = (int)v.y; }
-        else { t = ot[sp - NRCU_SMEM_STACK]; r = oref[sp - NRCU_SMEM_STACK]; }
-        return true;
-    }
-};
 
-// Persistent-thread closest-hit kernel: the grid is sized to fill the machine once; each warp
-// fetches 32 rays at a time from the queue with one atomic (lane 0) and a shuffle.
+// ---------------------------------------------------------------------------------------------
+// Closest hit, stage 1: the wide primitives, every ray, warp-uniform
+// ---------------------------------------------------------------------------------------------
+// All lanes walk the same short list (<= NRCU_MAX_BIG records staged in shared memory, read as broadcasts),
+// so there is no traversal divergence at all; only the early exits inside the exact tests diverge.
+// Writes the provisional hit of every ray and appends the rays that can still hit something inside the
+// BVH (conservative test against the BVH bounds with the provisional t) to the survivor list with one
+// atomic per warp.  On the Cornell-box scenes most rays end here.
 template <bool GATE>
-__global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
-                                                              uint32_t* fetch, unsigned long long* ray_counter) {
-    __shared__ uint2 stack_mem[NRCU_SMEM_STACK * NRCU_TRACE_THREADS];
+__global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
+                                            uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+    __shared__ f4 sg[NRCU_MAX_BIG * 3];
+    __shared__ f4 sb[NRCU_MAX_BIG * 2];
+    __shared__ uint32_t sm[NRCU_MAX_BIG];
+    for (uint32_t k = threadIdx.x; k < s.n_big * 3; k += blockDim.x) sg[k] = s.big_geom[k];
+    for (uint32_t k = threadIdx.x; k < s.n_big * 2; k += blockDim.x) sb[k] = s.big_box[k];
+    for (uint32_t k = threadIdx.x; k < s.n_big; k += blockDim.x) sm[k] = s.big_meta[k];
+    __syncthreads();
     const uint32_t n = *n_ptr;
     const uint32_t lane = threadIdx.x & 31u;
-    SmemStack stack; stack.base = stack_mem + threadIdx.x; stack.sp = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
-        uint32_t i = base + lane;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
+        const uint32_t i = base + lane;
+        bool more = false;
         if (i < n) {
             f4 a = q.a[i], b = q.b[i];
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
-            float t; int id;
-            stack.sp = 0;
-            closest_hit_bvh<GATE>(s, r, stack, t, id);
-            hits[i] = make_float2(t, __int_as_float(id));
+            RayPrep rp = prep_ray(r);
+            float best_t = NRCU_INF; int best_id = -1;
+            big_list_step<GATE>(s, sg, sb, sm, r, gate_inverse(r), best_t, best_id);
+            hits[i] = make_float2(best_t, __int_as_float(best_id));
+            more = bvh_reachable(s, rp, best_t);
         }
+        const uint32_t m = __ballot_sync(0xffffffffu, more);
+        uint32_t start = 0;
+        if (lane == 0) {
+            if (m) start = atomicAdd(n_surv, (uint32_t)__popc(m));
+            atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        }
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (more) surv[start + __popc(m & ((1u << lane) - 1u))] = i;
     }
 }
 
-// v2 of the closest-hit kernel: persistent threads, "while-while" traversal and lane refill.
-// Every lane keeps one ray's traversal state in registers.  When a lane finishes its ray it goes
-// idle; as soon as at least `refill` lanes of the warp are idle (or all of them), the warp claims that
-// many new rays from the queue with ONE atomic (the first idle lane) and hands them out by
-// ballot/popc rank, so warps stay full although path-traced rays have very different lengths.  Leaf
-// work is postponed until every active lane has reached a leaf (Aila & Laine's while-while), which
-// keeps node steps and primitive tests from serialising against each other.
+// ---------------------------------------------------------------------------------------------
+// Closest hit, stage 2: BVH4 traversal of the surviving rays
+// ---------------------------------------------------------------------------------------------
+// Traversal stack: 16 (t, ref) entries per thread in shared memory ([entry][thread], conflict free), indexed by
+// a register; deeper entries overflow to local memory (only very deep trees get there).
+#define NRCU_T3_STACK 16
+struct Stack3 {
+    uint2* smem;                                   // this thread's column of the shared stack
+    float ot[NRCU_LOCAL_STACK - NRCU_T3_STACK];
+    int oref[NRCU_LOCAL_STACK - NRCU_T3_STACK];
+};
+__device__ __forceinline__ void push3(Stack3& st, int& sp, float t, int r) {
+    if (sp < NRCU_T3_STACK) st.smem[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t), (unsigned)r);
+    else if (sp < NRCU_LOCAL_STACK) { st.ot[sp - NRCU_T3_STACK] = t; st.oref[sp - NRCU_T3_STACK] = r; }
+    else return;
+    sp++;
+}
+__device__ __forceinline__ int pop3(Stack3& st, int& sp, float best_t) {
+    while (sp > 0) {
+        sp--;
+        float t; int r;
+        if (sp < NRCU_T3_STACK) { uint2 v = st.smem[sp * NRCU_TRACE_THREADS]; t = __uint_as_float(v.x); r = (int)v.y; }
+        else { t = st.ot[sp - NRCU_T3_STACK]; r = st.oref[sp - NRCU_T3_STACK]; }
+        if (t <= best_t) return r;   // ties must stay reachable
+    }
+    return NRCU_REF_DONE;
+}
+// One BVH4 node (same arithmetic as node_step in nrcu_intersect.cuh): conservative slab test of the four
+// children, nearest hit child returned, the others pushed far-to-near with predicated shared-memory stores.
+__device__ __forceinline__ int node_step3(const DScene& s, const RayPrep& rp, int cur, float best_t, Stack3& st, int& sp) {
+    const f4* nd = s.nodes + (size_t)cur * NRCU_BVH_NODE_F4;
+    f4 lox = ldg4(nd), hix = ldg4(nd + 1), loy = ldg4(nd + 2), hiy = ldg4(nd + 3), loz = ldg4(nd + 4), hiz = ldg4(nd + 5);
+    i4 refs = ldg4i(nd + 6);
+    float t0, t1, t2, t3;
+#define NRCU_SLAB(k, out) do { \
+    float ax = fmaf(lox.k, rp.inv.x, -rp.oinv.x), bx = fmaf(hix.k, rp.inv.x, -rp.oinv.x); \
+    float ay = fmaf(loy.k, rp.inv.y, -rp.oinv.y), by = fmaf(hiy.k, rp.inv.y, -rp.oinv.y); \
+    float az = fmaf(loz.k, rp.inv.z, -rp.oinv.z), bz = fmaf(hiz.k, rp.inv.z, -rp.oinv.z); \
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
+    out = (tn <= tf) ? tn : NRCU_INF; } while (0)
+    NRCU_SLAB(x, t0); NRCU_SLAB(y, t1); NRCU_SLAB(z, t2); NRCU_SLAB(w, t3);
+#undef NRCU_SLAB
+    int r0 = refs.x, r1 = refs.y, r2 = refs.z, r3 = refs.w;
+    NRCU_CSWAP(t0, r0, t1, r1); NRCU_CSWAP(t2, r2, t3, r3);
+    NRCU_CSWAP(t0, r0, t2, r2); NRCU_CSWAP(t1, r1, t3, r3);
+    NRCU_CSWAP(t1, r1, t2, r2);
+    if (sp + 3 <= NRCU_T3_STACK) {   // fast path: no overflow checks
+        if (t3 < NRCU_INF) { st.smem[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t3), (unsigned)r3); sp++; }
+        if (t2 < NRCU_INF) { st.smem[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t2), (unsigned)r2); sp++; }
+        if (t1 < NRCU_INF) { st.smem[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t1), (unsigned)r1); sp++; }
+    } else {
+        if (t3 < NRCU_INF) push3(st, sp, t3, r3);
+        if (t2 < NRCU_INF) push3(st, sp, t2, r2);
+        if (t1 < NRCU_INF) push3(st, sp, t1, r1);
+    }
+    return (t0 < NRCU_INF) ? r0 : pop3(st, sp, best_t);
+}
+
+// Work fetching shared by the stage-2 kernels: the idle lanes of a warp claim `n_idle` queue entries with ONE
+// atomic (the first idle lane) and take them by ballot/popc rank.  `surv` (stage-1 survivor list) maps the queue
+// position to the ray index; the provisional hit of stage 1 seeds (best_t, best_id).
+struct Lane {
+    Ray r; RayPrep rp; vec3 ginv;
+    float best_t; int best_id; int cur; int sp; uint32_t idx;
+};
 template <bool GATE>
-__global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace2(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
+__device__ __forceinline__ bool fetch_ray(const DScene& s, const PathQueue& q, const uint32_t* surv, const float2* hits, uint32_t j, Lane& L) {
+    const uint32_t i = surv ? surv[j] : j;
+    f4 a = q.a[i], b = q.b[i];
+    L.r.o = mk3(a.x, a.y, a.z); L.r.d = mk3(a.w, b.x, b.y);
+    L.rp = prep_ray(L.r);
+    if (GATE) L.ginv = gate_inverse(L.r);
+    L.best_t = NRCU_INF; L.best_id = -1;
+    if (surv) { float2 h = hits[i]; L.best_t = h.x; L.best_id = __float_as_int(h.y); }
+    L.sp = 0; L.idx = i;
+    L.cur = s.root_ref == NRCU_REF_EMPTY ? NRCU_REF_DONE : s.root_ref;
+    return true;
+}
+
+// v2: persistent threads, "while-while" traversal and lane refill.  Every lane keeps one ray's traversal state
+// in registers; when at least `refill` lanes of the warp are idle (or all of them) the warp claims that many new
+// rays.  Leaf work is postponed until every active lane has reached a leaf (Aila & Laine's while-while).
+template <bool GATE>
+__global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace2(DScene s, PathQueue q, const uint32_t* n_ptr, const uint32_t* surv, float2* hits,
                                                                uint32_t* fetch, unsigned long long* ray_counter, uint32_t refill) {
-    __shared__ uint2 stack_mem[NRCU_SMEM_STACK * NRCU_TRACE_THREADS];
+    __shared__ uint2 stack_mem[NRCU_T3_STACK * NRCU_TRACE_THREADS];
     const uint32_t n = *n_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
-    SmemStack stack; stack.base = stack_mem + threadIdx.x; stack.sp = 0;
-    Ray r; RayPrep rp;
-    r.o = mk3(0.f); r.d = mk3(0.f); rp.inv = mk3(0.f); rp.oinv = mk3(0.f);
-    float best_t = NRCU_INF; int best_id = -1; int cur = NRCU_REF_DONE; uint32_t idx = 0;
+    Stack3 st; st.smem = stack_mem + threadIdx.x;
+    Lane L; L.r.o = mk3(0.f); L.r.d = mk3(0.f); L.rp.inv = mk3(0.f); L.rp.oinv = mk3(0.f); L.ginv = mk3(0.f);
+    L.best_t = NRCU_INF; L.best_id = -1; L.cur = NRCU_REF_DONE; L.sp = 0; L.idx = 0;
     bool active = false, exhausted = false;
     for (;;) {
-        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle == 0xffffffffu && exhausted) break;
-        uint32_t n_idle = __popc(idle);
+        const uint32_t n_idle = __popc(idle);
         if (!exhausted && n_idle >= (idle == 0xffffffffu ? 1u : refill)) {
             uint32_t base = 0;
             const uint32_t leader = __ffs(idle) - 1u;
             if (lane == leader) {
                 base = atomicAdd(fetch, n_idle);
-                if (base < n) atomicAdd(ray_counter, (unsigned long long)min(n_idle, n - base));
+                if (!surv && base < n) atomicAdd(ray_counter, (unsigned long long)min(n_idle, n - base));
             }
             base = __shfl_sync(0xffffffffu, base, leader);
             if (base + n_idle >= n) exhausted = true;
             if (!active) {
-                uint32_t i = base + __popc(idle & lt);
-                if (i < n) {
-                    f4 a = q.a[i], b = q.b[i];
-                    r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
-                    rp = prep_ray(r);
-                    best_t = NRCU_INF; best_id = -1; stack.sp = 0; idx = i;
-                    cur = s.root_ref == NRCU_REF_EMPTY ? NRCU_REF_DONE : s.root_ref;
-                    active = true;
-                }
+                const uint32_t j = base + __popc(idle & lt);
+                if (j < n) active = fetch_ray<GATE>(s, q, surv, hits, j, L);
             }
         }
         if (active) {
-            while (cur >= 0) cur = node_step(s, rp, cur, best_t, stack);
-            if (cur != NRCU_REF_DONE) {
-                leaf_step<GATE>(s, r, cur, best_t, best_id);
-                cur = pop_next(stack, best_t);
+            while (L.cur >= 0) L.cur = node_step3(s, L.rp, L.cur, L.best_t, st, L.sp);
+            if (L.cur != NRCU_REF_DONE) {
+                leaf_step<GATE>(s, L.r, L.ginv, L.cur, L.best_t, L.best_id);
+                L.cur = pop3(st, L.sp, L.best_t);
             }
-            if (cur == NRCU_REF_DONE) {
-                hits[idx] = make_float2(best_t, __int_as_float(best_id));
+            if (L.cur == NRCU_REF_DONE) {
+                hits[L.idx] = make_float2(L.best_t, __int_as_float(L.best_id));
                 active = false;
+            }
+        }
+    }
+}
+
+// v3: persistent threads with VOTE-SCHEDULED phases.  A lane is a small state machine with up to two kinds of
+// pending work:
+//     cur >= 0   an inner BVH4 node to test                      ("node" work)
+//     pn  >  0   pn primitives of a parked leaf left to test      ("prim" work, one primitive per step)
+// and each warp iteration executes ONE phase, chosen by ballot/popc majority between the lanes that can do a
+// node step and the lanes that can do a primitive test.  A lane that reaches a leaf parks it and keeps walking
+// inner nodes speculatively (Aila & Laine's postponed leaf), so most lanes qualify for either phase.
+template <bool GATE>
+__global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace3(DScene s, PathQueue q, const uint32_t* n_ptr, const uint32_t* surv, float2* hits,
+                                                               uint32_t* fetch, unsigned long long* ray_counter, uint32_t refill,
+                                                               uint32_t w_node, uint32_t w_prim) {
+    __shared__ uint2 stack_mem[NRCU_T3_STACK * NRCU_TRACE_THREADS];
+    const uint32_t n = *n_ptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    Stack3 st; st.smem = stack_mem + threadIdx.x;
+    Lane L; L.r.o = mk3(0.f); L.r.d = mk3(0.f); L.rp.inv = mk3(0.f); L.rp.oinv = mk3(0.f); L.ginv = mk3(0.f);
+    L.best_t = NRCU_INF; L.best_id = -1; L.cur = NRCU_REF_DONE; L.sp = 0; L.idx = 0;
+    uint32_t pl = 0, pn = 0, pk = 0;
+    bool active = false, exhausted = false;
+    for (;;) {
+        // ---- refill idle lanes from the queue ------------------------------------------------------
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle) {
+            if (exhausted) { if (idle == 0xffffffffu) break; }
+            else {
+                const uint32_t n_idle = __popc(idle);
+                if (idle == 0xffffffffu || n_idle >= refill) {
+                    uint32_t base = 0;
+                    const uint32_t leader = __ffs(idle) - 1u;
+                    if (lane == leader) {
+                        base = atomicAdd(fetch, n_idle);
+                        if (!surv && base < n) atomicAdd(ray_counter, (unsigned long long)min(n_idle, n - base));
+                    }
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (base + n_idle >= n) exhausted = true;
+                    if (!active) {
+                        const uint32_t j = base + __popc(idle & lt);
+                        if (j < n) { active = fetch_ray<GATE>(s, q, surv, hits, j, L); pn = 0; }
+                    }
+                }
+            }
+        }
+        // ---- park a reached leaf as pending primitive work, or retire the ray -------------------------
+        if (active && pn == 0 && L.cur < 0) {
+            if (L.cur != NRCU_REF_DONE) {
+                const uint32_t code = (uint32_t)(~L.cur);
+                pl = code >> 4; pn = (code & 15u) + 1u;
+                pk = ldg_u32(s.leaf_prims + pl);
+                L.cur = pop3(st, L.sp, L.best_t);
+            } else {
+                hits[L.idx] = make_float2(L.best_t, __int_as_float(L.best_id));
+                active = false;
+            }
+        }
+        // ---- vote: which phase does this warp iteration run? ------------------------------------------
+        const bool want_node = active && L.cur >= 0;
+        const bool want_prim = active && pn > 0;
+        const uint32_t m_node = __ballot_sync(0xffffffffu, want_node), m_prim = __ballot_sync(0xffffffffu, want_prim);
+        if (__popc(m_node) * w_node >= __popc(m_prim) * w_prim) {
+            if (want_node) L.cur = node_step3(s, L.rp, L.cur, L.best_t, st, L.sp);
+        } else {
+            if (want_prim) {
+                prim_step<GATE>(s, L.r, L.ginv, pl, pk, L.best_t, L.best_id);
+                pl++; pn--;
+                if (pn) pk = ldg_u32(s.leaf_prims + pl);
             }
         }
     }

@@ -74,10 +74,15 @@ struct DCamera {   // Camera ctor results, ray_cast/include/Camera.hpp:25-46
 };
 
 #define NRCU_BVH_NODE_F4 7   // float4s per BVH4 node: lox hix loy hiy loz hiz (4 children each) + 4 child refs
-#define NRCU_LEAF_MAX 4      // primitives per leaf the builder aims for
+#ifndef NRCU_LEAF_MAX
+#define NRCU_LEAF_MAX 4
+#endif
+// ^     // primitives per leaf the builder aims for
 // child ref encoding: >= 0 inner node index; < 0 leaf: ~ref = (first << 4) | (count - 1), count <= 16;
 // empty slots carry an inverted box (lo = +inf, hi = -inf) and are never entered.
 #define NRCU_REF_EMPTY 0x7fffffff
+#define NRCU_MAX_BIG 32       // capacity of the wide-primitive list
+#define NRCU_BIG_AREA_FRACTION 0.02f   // a primitive is "wide" when its box has >= this fraction of the scene box's surface area
 
 struct DScene {
     int mode;
@@ -90,7 +95,16 @@ struct DScene {
     // wide BVH
     const f4* nodes;
     const uint32_t* leaf_prims;   // (prim id << 2) | kind, grouped by leaf
+    const f4* leaf_geom;          // prim_geom gathered into leaf order (3 per leaf slot): no dependent load at the leaves
+    const f4* leaf_box;           // prim_box gathered into leaf order (2 per leaf slot), read by the AccPathTracer leaf gate
     int root_ref;                 // child-ref encoding; NRCU_REF_EMPTY for an empty scene
+    // "wide" primitives (boxes covering a sizeable part of the scene: walls, floors) are kept out of the BVH and
+    // tested by every ray in a warp-uniform loop (k_big) before the traversal starts; see nrcu_bvh.cuh
+    const f4* big_geom;           // 3 per wide primitive
+    const f4* big_box;            // 2 per wide primitive (leaf gate)
+    const uint32_t* big_meta;     // (prim id << 2) | kind, ascending id
+    uint32_t n_big;
+    vec3 bvh_lo, bvh_hi;          // padded bounds of everything inside the BVH (lo > hi when it is empty)
     // shading
     const DMaterial* materials;
     uint32_t n_materials;

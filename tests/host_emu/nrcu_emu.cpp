@@ -25,7 +25,9 @@ struct EmuScene {
     HostPrep hp;
     uint32_t spp;
     std::vector<float> mesh_pos;
-    std::vector<f4> geom, shade, box, nodes, env;
+    std::vector<f4> geom, shade, box, nodes, env, leaf_geom, leaf_box, big_geom, big_box;
+    std::vector<uint32_t> big_meta;
+    int n_big = 0;
     std::vector<uint32_t> meta, leaf_prims;
     std::vector<float> export16;
     int n_binary_nodes = 0, n_wide = 0, levels = 0, max_leaf = 0;
@@ -50,11 +52,25 @@ static void emu_build_bvh(EmuScene& es) {
     b.nleaf_first = nleaf_first.data(); b.nleaf_fill = nleaf_fill.data(); b.nwide = nwide.data();
     b.bins = bins.data(); b.bin_nodes = bin_nodes; b.counters = counters.data(); b.nbin_slot = nbin_slot.data();
     b.leaf_prims = es.leaf_prims.data(); b.wide_nodes = wide.data();
+    es.leaf_geom.assign(3 * (size_t)std::max(1u, n), mk4(0, 0, 0, 0)); es.leaf_box.assign(2 * (size_t)std::max(1u, n), mk4(0, 0, 0, 0));
+    b.prim_geom = es.geom.data(); b.leaf_geom = es.leaf_geom.data(); b.leaf_box = es.leaf_box.data();
+    es.big_geom.assign(3 * NRCU_MAX_BIG, mk4(0, 0, 0, 0)); es.big_box.assign(2 * NRCU_MAX_BIG, mk4(0, 0, 0, 0)); es.big_meta.assign(NRCU_MAX_BIG, 0);
+    b.big_geom = es.big_geom.data(); b.big_box = es.big_box.data(); b.big_meta = es.big_meta.data(); b.big_count = &es.n_big;
     b.inflate = es.hp.max_abs_coord * (1.0f / 65536.0f);
     // same orchestration as build_bvh() in nrcu_api.cu
     counters[0] = 1;
     for (int i = 0; i < cap; i++) node_clear(b, i);
     for (uint32_t i = 0; i < n; i++) bvh_init_prim(b, (int)i);
+    bvh_select_big(b, 0);
+    node_clear(b, 0);
+    for (uint32_t i = 0; i < n; i++) bvh_init_prim_rest(b, (int)i);
+    DScene& ds = es.ds;
+    ds.big_geom = es.big_geom.data(); ds.big_box = es.big_box.data(); ds.big_meta = es.big_meta.data(); ds.n_big = (uint32_t)es.n_big;
+    ds.leaf_prims = es.leaf_prims.data(); ds.leaf_geom = es.leaf_geom.data(); ds.leaf_box = es.leaf_box.data();
+    ds.root_ref = NRCU_REF_EMPTY; ds.bvh_lo = mk3(NRCU_INF); ds.bvh_hi = mk3(-NRCU_INF);
+    const uint32_t n_rest = n - (uint32_t)es.n_big;
+    if (n_rest == 0) return;
+    bvh_padded_bounds(nbox.data(), b.inflate, ds.bvh_lo, ds.bvh_hi);
     int begin = 0, end = 1;
     for (int level = 0; level < 128; level++) {
         b.level_begin = begin; b.level_end = end;
@@ -71,6 +87,7 @@ static void emu_build_bvh(EmuScene& es) {
     for (int i = 0; i < n_nodes; i++) bvh_leaf_alloc(b, i);
     for (uint32_t i = 0; i < n; i++) bvh_leaf_fill(b, (int)i);
     for (int i = 0; i < n_nodes; i++) bvh_leaf_sort(b, i);
+    for (uint32_t i = 0; i < n_rest; i++) bvh_leaf_gather(b, (int)i);
     for (int i = 0; i < n_nodes; i++) bvh_wide_index(b, i);
     for (int i = 0; i < n_nodes; i++) bvh_wide_emit(b, i);
     es.n_binary_nodes = n_nodes; es.n_wide = counters[2];
@@ -78,6 +95,7 @@ static void emu_build_bvh(EmuScene& es) {
     es.nodes.assign(wide.begin(), wide.begin() + (size_t)std::max(1, es.n_wide) * NRCU_BVH_NODE_F4);
     es.ds.nodes = es.nodes.data();
     es.ds.leaf_prims = es.leaf_prims.data();
+    es.ds.leaf_geom = es.leaf_geom.data(); es.ds.leaf_box = es.leaf_box.data();
     es.ds.root_ref = nstate[0] == BNODE_LEAF ? ~((nleaf_first[0] << 4) | (ncount[0] - 1)) : nwide[0];
 }
 
@@ -145,7 +163,7 @@ void emu_camera(EmuScene* es, float* cam18, float* lens_radius) {
 // out[0..5]: binary nodes, wide nodes, build levels, max leaf size, leaf prim slots used, root ref
 void emu_bvh_stats(EmuScene* es, int32_t* out) {
     out[0] = es->n_binary_nodes; out[1] = es->n_wide; out[2] = es->levels; out[3] = es->max_leaf;
-    out[4] = (int32_t)es->leaf_prims.size(); out[5] = es->ds.root_ref;
+    out[4] = (int32_t)es->leaf_prims.size(); out[5] = es->ds.root_ref; out[6] = es->n_big;
 }
 
 void emu_trace_batch(EmuScene* es, const float* rays, uint32_t n, int32_t* prim_id, float* t, int use_linear) {

@@ -79,7 +79,7 @@ class EmuScene:
     def bvh_stats(self):
         o = np.zeros(8, np.int32)
         lib().emu_bvh_stats(self._h, o.ctypes.data)
-        return dict(binary_nodes=int(o[0]), wide_nodes=int(o[1]), levels=int(o[2]), max_leaf=int(o[3]), leaf_slots=int(o[4]), root_ref=int(o[5]))
+        return dict(binary_nodes=int(o[0]), wide_nodes=int(o[1]), levels=int(o[2]), max_leaf=int(o[3]), leaf_slots=int(o[4]), root_ref=int(o[5]), n_big=int(o[6]))
 
     def trace_batch(self, rays, linear=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)

@@ -32,7 +32,8 @@ def test_bvh_build_invariants():
     # every primitive reachable: a ray aimed at each primitive's centroid from just in front of it hits something at t>0
     tiny = load_scene("env_map_spheres")
     st = pyemu.EmuScene(tiny, 2).bvh_stats()
-    assert st["wide_nodes"] == 0 and st["root_ref"] < 0          # two spheres fit one leaf: the root is a leaf reference
+    # two spheres, each a sizeable part of the scene box: both go to the wide list and the tree is empty
+    assert st["wide_nodes"] == 0 and st["n_big"] == 2 and st["root_ref"] == 0x7fffffff
 
 
 @pytest.mark.parametrize("name,mode,n", [("path_tracing_cornel", 1, 60000), ("path_tracing_cornel", 2, 60000), ("bunny5k_cornel", 2, 60000),

@@ -8,22 +8,27 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SETTINGS = [
-    {"NRCU_TRACE_VARIANT": "1"},
-    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "1"},
-    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "4"},
     {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "8"},
-    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "16"},
-    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "24"},
-    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "32"},
-    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_BLOCKS": "9"},
-    {"NRCU_TRACE_VARIANT": "2", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_BLOCKS": "16"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "8"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "1"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "4"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "16"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_WNODE": "1", "NRCU_TRACE_WPRIM": "2"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_WNODE": "2", "NRCU_TRACE_WPRIM": "1"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_WNODE": "2", "NRCU_TRACE_WPRIM": "3"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_WNODE": "3", "NRCU_TRACE_WPRIM": "2"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_BLOCKS": "9"},
+    {"NRCU_TRACE_VARIANT": "3", "NRCU_TRACE_REFILL": "8", "NRCU_TRACE_BLOCKS": "6"},
 ]
 
 
 def main():
     spp = sys.argv[1] if len(sys.argv) > 1 else "64"
     extra = sys.argv[2:]
-    for st in SETTINGS:
+    settings = SETTINGS
+    if os.environ.get("NRCU_TUNE_SETTINGS"):   # JSON list of env dicts
+        settings = json.loads(os.environ["NRCU_TUNE_SETTINGS"])
+    for st in settings:
         env = dict(os.environ, **st)
         r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "2", "--warmup", "1", "--spp", spp,
                             "--no-cpu-baseline", "--e2e-steps", "1"] + extra, capture_output=True, text=True, env=env)
