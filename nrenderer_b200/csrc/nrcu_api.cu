@@ -51,13 +51,13 @@ struct nrcu_ctx {
     uint32_t spp = 0;
     DScene ds{};
     // scene buffers
-    DevBuf prim_geom, prim_shade, prim_box, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_meta, materials, area_lights, env;
+    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, materials, area_lights, env;
     // scene-prep sources kept for nrcu_download_primitives
     DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
     PrimSources ps{};
     // wavefront state
-    DevBuf qa[2], qb[2], qc[2], hits, surv, L, counters, accum_own, rgba_dev;
+    DevBuf qa[2], qb[2], qc[2], hits[2], surv, L, counters, accum_own, rgba_dev;
     uint32_t queue_capacity = 0, wave_slots = 0;
     unsigned long long* d_ray_counter = nullptr;   // inside `counters`
     // stats
@@ -228,10 +228,11 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
     CTX_CUDA(ctx->prim_geom.ensure(sizeof(f4) * 3 * (size_t)std::max(n, 1u)));
     CTX_CUDA(ctx->prim_shade.ensure(sizeof(f4) * (size_t)std::max(n, 1u)));
     CTX_CUDA(ctx->prim_box.ensure(sizeof(f4) * 2 * (size_t)std::max(n, 1u)));
+    CTX_CUDA(ctx->prim_bound.ensure(sizeof(f4) * 2 * (size_t)std::max(n, 1u)));
     CTX_CUDA(ctx->prim_meta.ensure(sizeof(uint32_t) * (size_t)std::max(n, 1u)));
     if (n) {
         k_build_prims<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ps, n, mode == NRCU_MODE_RAYCAST, ctx->prim_geom.as<f4>(),
-                                                                 ctx->prim_shade.as<f4>(), ctx->prim_box.as<f4>(), ctx->prim_meta.as<uint32_t>(), nullptr);
+                                                                 ctx->prim_shade.as<f4>(), ctx->prim_box.as<f4>(), ctx->prim_bound.as<f4>(), ctx->prim_meta.as<uint32_t>(), nullptr);
         CTX_LAUNCH_CHECK("k_build_prims");
     }
     ds.prim_geom = ctx->prim_geom.as<f4>(); ds.prim_shade = ctx->prim_shade.as<f4>(); ds.prim_box = ctx->prim_box.as<f4>();
@@ -269,11 +270,11 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     CTX_CUDA(ctx->leaf_prims.ensure(sizeof(uint32_t) * (size_t)n));
     CTX_CUDA(ctx->leaf_geom.ensure(sizeof(f4) * 3 * (size_t)n)); CTX_CUDA(ctx->leaf_box.ensure(sizeof(f4) * 2 * (size_t)n));
     CTX_CUDA(ctx->big_geom.ensure(sizeof(f4) * 3 * NRCU_MAX_BIG)); CTX_CUDA(ctx->big_box.ensure(sizeof(f4) * 2 * NRCU_MAX_BIG));
-    CTX_CUDA(ctx->big_meta.ensure(sizeof(uint32_t) * NRCU_MAX_BIG));
+    CTX_CUDA(ctx->big_meta.ensure(sizeof(uint32_t) * NRCU_MAX_BIG)); CTX_CUDA(ctx->big_bound.ensure(sizeof(f4) * 2 * NRCU_MAX_BIG));
     CTX_CUDA(wide_tmp.ensure(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1u, n)));
 
     BvhBuild b{};
-    b.n_prims = n; b.prim_box = ctx->prim_box.as<f4>(); b.prim_meta = ctx->prim_meta.as<uint32_t>();
+    b.n_prims = n; b.prim_box = ctx->prim_box.as<f4>(); b.prim_bound = ctx->prim_bound.as<f4>(); b.prim_meta = ctx->prim_meta.as<uint32_t>();
     b.prim_node = prim_node.as<int>(); b.nbox = nbox.as<int>(); b.cbox = cbox.as<int>(); b.ncount = ncount.as<int>();
     b.nidmin = nidmin.as<int>(); b.nidmax = nidmax.as<int>(); b.nstate = nstate.as<int>(); b.nchild = nchild.as<int>();
     b.nsplit_axis = nsplit_axis.as<int>(); b.nsplit_pos = nsplit_pos.as<float>(); b.ndepth = ndepth.as<int>();
@@ -281,7 +282,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     b.bins = bins.as<int>(); b.bin_nodes = bin_nodes; b.counters = counters.as<int>(); b.nbin_slot = nbin_slot.as<int>();
     b.leaf_prims = ctx->leaf_prims.as<uint32_t>(); b.wide_nodes = wide_tmp.as<f4>();
     b.prim_geom = ctx->prim_geom.as<f4>(); b.leaf_geom = ctx->leaf_geom.as<f4>(); b.leaf_box = ctx->leaf_box.as<f4>();
-    b.big_geom = ctx->big_geom.as<f4>(); b.big_box = ctx->big_box.as<f4>(); b.big_meta = ctx->big_meta.as<uint32_t>(); b.big_count = big_count.as<int>();
+    b.big_geom = ctx->big_geom.as<f4>(); b.big_box = ctx->big_box.as<f4>(); b.big_bound = ctx->big_bound.as<f4>(); b.big_meta = ctx->big_meta.as<uint32_t>(); b.big_count = big_count.as<int>();
     b.inflate = max_abs_coord * (1.0f / 65536.0f);
     cudaStream_t st = ctx->stream;
     const int T = 128;
@@ -300,7 +301,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     CTX_CUDA(cudaStreamSynchronize(st));
     ctx->n_big = (uint32_t)n_big;
     DScene& ds = ctx->ds;
-    ds.big_geom = ctx->big_geom.as<f4>(); ds.big_box = ctx->big_box.as<f4>(); ds.big_meta = ctx->big_meta.as<uint32_t>(); ds.n_big = (uint32_t)n_big;
+    ds.big_geom = ctx->big_geom.as<f4>(); ds.big_box = ctx->big_box.as<f4>(); ds.big_bound = ctx->big_bound.as<f4>(); ds.big_meta = ctx->big_meta.as<uint32_t>(); ds.n_big = (uint32_t)n_big;
     ds.nodes = nullptr; ds.leaf_prims = ctx->leaf_prims.as<uint32_t>(); ds.leaf_geom = ctx->leaf_geom.as<f4>(); ds.leaf_box = ctx->leaf_box.as<f4>();
     ds.root_ref = NRCU_REF_EMPTY; ds.bvh_lo = mk3(NRCU_INF); ds.bvh_hi = mk3(-NRCU_INF);
     ctx->bvh_nodes = 0;
@@ -361,10 +362,10 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
     const uint32_t n = ctx->ds.n_prims;
     if (!n) return NRCU_OK;
     if (data16) {
-        DevBuf ex, g, s, bx, mt;   // scratch outputs so the live scene is not disturbed
+        DevBuf ex, g, s, bx, bd, mt;   // scratch outputs so the live scene is not disturbed
         CTX_CUDA(ex.ensure(sizeof(float) * 16 * (size_t)n)); CTX_CUDA(g.ensure(sizeof(f4) * 3 * (size_t)n));
-        CTX_CUDA(s.ensure(sizeof(f4) * (size_t)n)); CTX_CUDA(bx.ensure(sizeof(f4) * 2 * (size_t)n)); CTX_CUDA(mt.ensure(sizeof(uint32_t) * (size_t)n));
-        k_build_prims<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->ps, n, ctx->mode == NRCU_MODE_RAYCAST, g.as<f4>(), s.as<f4>(), bx.as<f4>(), mt.as<uint32_t>(), ex.as<float>());
+        CTX_CUDA(s.ensure(sizeof(f4) * (size_t)n)); CTX_CUDA(bx.ensure(sizeof(f4) * 2 * (size_t)n)); CTX_CUDA(bd.ensure(sizeof(f4) * 2 * (size_t)n)); CTX_CUDA(mt.ensure(sizeof(uint32_t) * (size_t)n));
+        k_build_prims<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->ps, n, ctx->mode == NRCU_MODE_RAYCAST, g.as<f4>(), s.as<f4>(), bx.as<f4>(), bd.as<f4>(), mt.as<uint32_t>(), ex.as<float>());
         CTX_LAUNCH_CHECK("k_build_prims");
         CTX_CUDA(cudaMemcpyAsync(data16, ex.p, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -389,7 +390,7 @@ static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_
         CTX_CUDA(ctx->qb[k].ensure(sizeof(f4) * (size_t)capacity));
         CTX_CUDA(ctx->qc[k].ensure(sizeof(f4) * (size_t)capacity));
     }
-    CTX_CUDA(ctx->hits.ensure(sizeof(float2) * (size_t)capacity));
+    for (int k = 0; k < 2; k++) CTX_CUDA(ctx->hits[k].ensure(sizeof(float2) * (size_t)capacity));
     CTX_CUDA(ctx->surv.ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(ctx->L.ensure(sizeof(f4) * (size_t)slots));
     CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 3 * (size_t)depth + 12)));
@@ -413,22 +414,30 @@ static int sm_count(int device) {
 static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
 static uint32_t env_u32(const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : dflt; }
+static bool fuse_stage1() { static uint32_t v = env_u32("NRCU_FUSE_STAGE1", 0); return v != 0; }
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
 
-// Closest hit for the first *n_ptr entries of queue `q` into hits[]: stage 1 (wide primitives, every ray) then
-// stage 2 (BVH traversal of the survivors).  `work` points at three zeroed words: survivor count, fetch cursor, spare.
+// Stage 2 of the closest hit: BVH traversal of the *n_surv rays listed in `surv`, refining hits[] in place.
+template <bool GATE>
+static void launch_stage2(nrcu_ctx* ctx, const DScene& ds, PathQueue q, float2* hits, const uint32_t* surv, const uint32_t* n_surv,
+                          uint32_t* fetch, unsigned long long* rays) {
+    const unsigned grid = (unsigned)sm_count(ctx->device) * trace_blocks_per_sm();
+    if (trace_variant() == 3) k_trace3<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill(), trace_w_node(), trace_w_prim());
+    else k_trace2<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
+}
+
+// Closest hit for the first *n_ptr entries of queue `q` into hits[] (the stand-alone form used by
+// nrcu_trace_batch; the renderer fuses stage 1 into the kernels that generate the rays): stage 1 (wide
+// primitives, every ray) then stage 2 (BVH traversal of the survivors).
 template <bool GATE>
 static void launch_closest_hit(nrcu_ctx* ctx, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* surv,
                                uint32_t* n_surv, uint32_t* fetch, unsigned long long* rays, int* launches) {
-    const unsigned sms = (unsigned)sm_count(ctx->device);
-    k_big<GATE><<<sms * 8, 256, 0, ctx->stream>>>(ds, q, n_ptr, hits, surv, n_surv, rays);
+    k_big<GATE><<<(unsigned)sm_count(ctx->device) * 8, 256, 0, ctx->stream>>>(ds, q, n_ptr, hits, surv, n_surv, rays);
     (*launches)++;
     if (ds.root_ref == NRCU_REF_EMPTY) return;
-    const unsigned grid = sms * trace_blocks_per_sm();
-    if (trace_variant() == 3) k_trace3<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill(), trace_w_node(), trace_w_prim());
-    else k_trace2<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
+    launch_stage2<GATE>(ctx, ds, q, hits, surv, n_surv, fetch, rays);
     (*launches)++;
 }
 
@@ -476,18 +485,34 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     for (uint32_t w0 = s0; w0 < s1; w0 += k) {
         const uint32_t kw = std::min(k, s1 - w0), n_slots = kw * npix;
         CTX_CUDA(cudaMemsetAsync(cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
-        k_raygen<<<grid_for(n_slots, 256), 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn);
+        const bool gate = ctx->mode == NRCU_MODE_ACC, fuse = fuse_stage1();
+        float2* hb[2] = {ctx->hits[0].as<float2>(), ctx->hits[1].as<float2>()};
+        uint32_t* surv = ctx->surv.as<uint32_t>();
+        const unsigned gen_grid = std::min<unsigned>(grid_for(n_slots, 256), (unsigned)sms * 8);
+        if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
+        if (gate) k_raygen<true><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn, hb[0], surv, d_nsurv, d_rays);
+        else k_raygen<false><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn, hb[0], surv, d_nsurv, d_rays);
         CTX_LAUNCH_CHECK("k_raygen");
+        if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 1}); ev_i += 2; }
         for (uint32_t d = 0; d < ds.depth; d++) {
             PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
+            float2* hi = hb[d & 1]; float2* ho = hb[(d + 1) & 1];
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
-            int nl = 0;
-            if (ctx->mode == NRCU_MODE_ACC) launch_closest_hit<true>(ctx, ds, qi, d_qn + d, ctx->hits.as<float2>(), ctx->surv.as<uint32_t>(), d_nsurv + d, d_fetch + d, d_rays, &nl);
-            else launch_closest_hit<false>(ctx, ds, qi, d_qn + d, ctx->hits.as<float2>(), ctx->surv.as<uint32_t>(), d_nsurv + d, d_fetch + d, d_rays, &nl);
-            ctx->launches += nl - 1;
-            CTX_LAUNCH_CHECK("k_big/k_trace");
+            if (d > 0 && !fuse) {   // stage 1 of this bounce (bounce 0's ran inside k_raygen)
+                if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
+                else k_big<false><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
+                CTX_LAUNCH_CHECK("k_big");
+            }
+            if (ds.root_ref != NRCU_REF_EMPTY) {
+                if (gate) launch_stage2<true>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays);
+                else launch_stage2<false>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays);
+                CTX_LAUNCH_CHECK("k_trace");
+            }
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
-            k_shade<<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, ctx->hits.as<float2>(), qo, d_qn + d + 1, capacity, ctx->L.as<f4>());
+#define NRCU_SHADE(G, F) k_shade<G, F><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, capacity, ctx->L.as<f4>(), ho, surv, d_nsurv + d + 1, d_rays)
+            if (gate) { if (fuse) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
+            else { if (fuse) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
+#undef NRCU_SHADE
             CTX_LAUNCH_CHECK("k_shade");
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
             k_clamp_count<<<1, 1, 0, st>>>(d_qn + d + 1, capacity, cnt + CNT_HIGH_WATER);

@@ -55,7 +55,8 @@ enum { BNODE_OPEN = 0, BNODE_LEAF = 1, BNODE_INNER = 2 };
 
 struct BvhBuild {
     uint32_t n_prims;
-    const f4* prim_box;        // 2 per primitive
+    const f4* prim_box;        // 2 per primitive: the reference's leaf box (gate)
+    const f4* prim_bound;      // 2 per primitive: true bounds (tree construction)
     const uint32_t* prim_meta; // kind | material << 2
     int* prim_node;            // [n_prims] binary node of each primitive
     // binary nodes, capacity 2*n_prims + 2
@@ -82,7 +83,7 @@ struct BvhBuild {
     f4* leaf_geom;             // [n_prims * 3] prim_geom in leaf order
     f4* leaf_box;              // [n_prims * 2] prim_box in leaf order
     // wide-primitive list (outputs of bvh_select_big)
-    f4* big_geom; f4* big_box; uint32_t* big_meta;   // capacity NRCU_MAX_BIG
+    f4* big_geom; f4* big_box; f4* big_bound; uint32_t* big_meta;   // capacity NRCU_MAX_BIG; big_bound = padded true bounds
     int* big_count;            // [1]
     f4* wide_nodes;            // [wide capacity * 7]
     float inflate;             // absolute padding of wide-node boxes
@@ -101,7 +102,7 @@ NR_HD void node_clear(const BvhBuild& b, int n) {
 }
 
 NR_HD void node_add_prim(const BvhBuild& b, int n, int i) {
-    f4 lo = b.prim_box[2 * i], hi = b.prim_box[2 * i + 1];
+    f4 lo = b.prim_bound[2 * i], hi = b.prim_bound[2 * i + 1];
     vec3 c = box_centroid(lo, hi);
     atomic_min_i(&b.nbox[n * 6 + 0], fkey(lo.x)); atomic_min_i(&b.nbox[n * 6 + 1], fkey(lo.y)); atomic_min_i(&b.nbox[n * 6 + 2], fkey(lo.z));
     atomic_max_i(&b.nbox[n * 6 + 3], fkey(hi.x)); atomic_max_i(&b.nbox[n * 6 + 4], fkey(hi.y)); atomic_max_i(&b.nbox[n * 6 + 5], fkey(hi.z));
@@ -137,7 +138,7 @@ NR_HD void bvh_select_big(const BvhBuild& b, int) {
     if (root_area > 0.f && root_area < NRCU_INF) {
         const float thr = NRCU_BIG_AREA_FRACTION * root_area;
         for (int i = 0; i < (int)b.n_prims; i++) {
-            float ar = box_half_area(b.prim_box[2 * i], b.prim_box[2 * i + 1]);
+            float ar = box_half_area(b.prim_bound[2 * i], b.prim_bound[2 * i + 1]);
             if (!(ar >= thr)) continue;
             // keep the list sorted by (area desc, id asc); drop the smallest when full
             int pos = cnt;
@@ -149,12 +150,23 @@ NR_HD void bvh_select_big(const BvhBuild& b, int) {
             if (cnt < NRCU_MAX_BIG) cnt++;
         }
     }
-    // ascending id order (insertion sort, <= 32 entries)
-    for (int i = 1; i < cnt; i++) { int v = ids[i], j = i - 1; while (j >= 0 && ids[j] > v) { ids[j + 1] = ids[j]; j--; } ids[j + 1] = v; }
+    // order: planes, then triangles, then spheres (so that the lanes of a warp run the same test most of the
+    // time), ascending id inside each class; ties between equal-t hits are settled by id, not by list order
+    for (int i = 1; i < cnt; i++) {
+        int v = ids[i], j = i - 1;
+        #define NRCU_KCLASS(id_) ((b.prim_meta[id_] & 3u) == KIND_PLANE ? 0 : ((b.prim_meta[id_] & 3u) == KIND_SPHERE ? 2 : 1))
+        while (j >= 0 && (NRCU_KCLASS(ids[j]) > NRCU_KCLASS(v) || (NRCU_KCLASS(ids[j]) == NRCU_KCLASS(v) && ids[j] > v))) { ids[j + 1] = ids[j]; j--; }
+        #undef NRCU_KCLASS
+        ids[j + 1] = v;
+    }
     for (int k = 0; k < cnt; k++) {
         int id = ids[k];
         for (int q = 0; q < 3; q++) b.big_geom[3 * k + q] = b.prim_geom[3 * (size_t)id + q];
         for (int q = 0; q < 2; q++) b.big_box[2 * k + q] = b.prim_box[2 * (size_t)id + q];
+        f4 lo = b.prim_bound[2 * (size_t)id], hi = b.prim_bound[2 * (size_t)id + 1];
+        float px = b.inflate + 1e-6f * fmaxf(fabsf(lo.x), fabsf(hi.x)), py = b.inflate + 1e-6f * fmaxf(fabsf(lo.y), fabsf(hi.y)),
+              pz = b.inflate + 1e-6f * fmaxf(fabsf(lo.z), fabsf(hi.z));
+        b.big_bound[2 * k] = mk4(lo.x - px, lo.y - py, lo.z - pz, 0.f); b.big_bound[2 * k + 1] = mk4(hi.x + px, hi.y + py, hi.z + pz, 0.f);
         b.big_meta[k] = ((uint32_t)id << 2) | (b.prim_meta[id] & 3u);
         b.prim_node[id] = NRCU_PRIM_EXCLUDED;
     }
@@ -191,7 +203,7 @@ NR_HD void bvh_bin(const BvhBuild& b, int i) {
     if (n < 0 || n < b.level_begin || b.nstate[n] != BNODE_OPEN) return;
     int slot = b.nbin_slot[n];
     if (slot < 0 || slot >= b.bin_nodes) return;
-    f4 lo = b.prim_box[2 * i], hi = b.prim_box[2 * i + 1];
+    f4 lo = b.prim_bound[2 * i], hi = b.prim_bound[2 * i + 1];
     vec3 c = box_centroid(lo, hi);
     int* bn = b.bins + (size_t)slot * 3 * NRCU_NBINS * NRCU_BIN_WORDS;
     for (int a = 0; a < 3; a++) {
@@ -266,7 +278,7 @@ NR_HD void bvh_partition(const BvhBuild& b, int i) {
     int a = b.nsplit_axis[n];
     if (a == 3) side = (i <= f2i(b.nsplit_pos[n])) ? 0 : 1;
     else {
-        f4 lo = b.prim_box[2 * i], hi = b.prim_box[2 * i + 1];
+        f4 lo = b.prim_bound[2 * i], hi = b.prim_bound[2 * i + 1];
         vec3 c = box_centroid(lo, hi);
         float clo = fkey_inv(b.cbox[n * 6 + a]), chi = fkey_inv(b.cbox[n * 6 + 3 + a]);
         side = ((float)bin_of(comp(c, a), clo, chi) < b.nsplit_pos[n]) ? 0 : 1;

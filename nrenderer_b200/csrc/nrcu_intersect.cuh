@@ -65,8 +65,12 @@ NR_HD bool x_sphere(const Ray& ray, f4 g0, float tmin, float tmax, float& t_out)
 
 // xPlane / xAreaLight: n is the normal the variant uses (normalised for RayCast, as stored for the
 // path tracers, cross(u,v) for lights), folded into the record at upload time.
+// `cull_t` (NRCU_INF = off): the caller cannot use a hit with t > cull_t.  Two rejections are taken before
+// the division; both are exact, i.e. they only drop candidates the reference drops too (or that cannot win):
+//   * num and nd of opposite sign  =>  t = num/nd <= -0 < tMin (tMin > 0 in every variant)
+//   * |num| > cull_t*|nd|*(1+1e-5)  =>  the rounded quotient is strictly greater than cull_t
 template <bool RC>
-NR_HD bool x_quad(const Ray& ray, f4 g0, f4 g1, f4 g2, float tmin, float tmax, float& t_out) {
+NR_HD bool x_quad(const Ray& ray, f4 g0, f4 g1, f4 g2, float tmin, float tmax, float cull_t, float& t_out) {
     vec3 n = mk3(g0.x, g0.y, g0.z), p = mk3(g0.w, g1.x, g1.y);
     float nd = dot(ray.d, n);
     if (nd < 0.0000001f && nd > -0.00000001f) return false;
@@ -76,6 +80,8 @@ NR_HD bool x_quad(const Ray& ray, f4 g0, f4 g1, f4 g2, float tmin, float tmax, f
     // without the division (a zero / denormal numerator - a ray leaving the very plane it is tested
     // against - would otherwise take the slow path of the IEEE division on the device).
     if (fabsf(num) < 1e-30f) return false;
+    if ((num < 0.f) != (nd < 0.f)) return false;
+    if (fabsf(num) > cull_t * fabsf(nd) * 1.00001f) return false;
     float t = num / nd;
     if (!t_in_range<RC>(t, tmin, tmax)) return false;
     vec3 q = ray_at(ray, t) - p;
@@ -105,7 +111,7 @@ NR_HD bool x_prim(const DScene& s, const Ray& ray, uint32_t id, uint32_t kind, f
     f4 g0 = ldg4(g);
     if (kind == KIND_SPHERE) return x_sphere<RC>(ray, g0, tmin, tmax, t_out);
     f4 g1 = ldg4(g + 1), g2 = ldg4(g + 2);
-    if (kind == KIND_PLANE) return x_quad<RC>(ray, g0, g1, g2, tmin, tmax, t_out);
+    if (kind == KIND_PLANE) return x_quad<RC>(ray, g0, g1, g2, tmin, tmax, tmax, t_out);
     return x_triangle<RC>(ray, g0, g1, g2, tmin, tmax, t_out);
 }
 
@@ -208,7 +214,7 @@ NR_HD void prim_test(const Ray& ray, vec3 ginv, f4 g0, f4 g1, f4 g2, const f4* b
     const uint32_t id = pk >> 2, kind = pk & 3u;
     float t;
     bool hit;
-    if (kind == KIND_PLANE) hit = x_quad<false>(ray, g0, g1, g2, tmin, NRCU_INF, t);
+    if (kind == KIND_PLANE) hit = x_quad<false>(ray, g0, g1, g2, tmin, NRCU_INF, best_t, t);
     else if (kind == KIND_SPHERE) hit = x_sphere<false>(ray, g0, tmin, NRCU_INF, t);
     else hit = x_triangle<false>(ray, g0, g1, g2, tmin, NRCU_INF, t);
     if (hit && (t < best_t || (t == best_t && (int)id < best_id))) {
@@ -237,11 +243,48 @@ NR_HD void leaf_step(const DScene& s, const Ray& ray, vec3 ginv, int leaf_ref, f
     for (uint32_t j = 0; j < count; j++) prim_step<GATE>(s, ray, ginv, first + j, ldg_u32(s.leaf_prims + first + j), best_t, best_id);
 }
 
-// The wide primitives (DScene::big_*), tested in list order by every ray before the traversal.
+NR_HD int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+// The wide primitives (DScene::big_*), tested by every ray before the traversal (best_t = inf, best_id = -1 on entry).
+//   pass 1  every lane walks the same list: conservative slab test of each primitive's padded bounds -> candidate
+//           bit mask (warp-uniform loop, shared-memory broadcasts, no divergence);
+//   pass 2  each lane runs the exact reference test on its own candidates only (typically 2-3 of them).
+// The leaf gate is applied optimistically: the ungated closest hit is found first and only the winner's box is
+// tested; if it passes, it is also the closest of the gate-passing primitives (same t order, same lowest-id tie
+// rule).  Only when the winner fails its gate (zero-thickness box or a grazing hit) are the candidates walked
+// again with the gate applied per candidate.
 template <bool GATE>
-NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const uint32_t* meta, const Ray& ray, vec3 ginv, float& best_t, int& best_id) {
-    for (uint32_t k = 0; k < s.n_big; k++)
-        prim_test<GATE>(ray, ginv, geom[3 * k], geom[3 * k + 1], geom[3 * k + 2], box + 2 * k, meta[k], best_t, best_id);
+NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const f4* bound, const uint32_t* meta,
+                         const Ray& ray, const RayPrep& rp, vec3 ginv, float& best_t, int& best_id) {
+    uint32_t mask = 0;
+    for (uint32_t k = 0; k < s.n_big; k++) {
+        f4 lo = bound[2 * k], hi = bound[2 * k + 1];
+        float ax = fmaf(lo.x, rp.inv.x, -rp.oinv.x), bx = fmaf(hi.x, rp.inv.x, -rp.oinv.x);
+        float ay = fmaf(lo.y, rp.inv.y, -rp.oinv.y), by = fmaf(hi.y, rp.inv.y, -rp.oinv.y);
+        float az = fmaf(lo.z, rp.inv.z, -rp.oinv.z), bz = fmaf(hi.z, rp.inv.z, -rp.oinv.z);
+        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        if (tn <= tf) mask |= 1u << k;
+    }
+    uint32_t kb = 0;
+    for (uint32_t m = mask; m; m &= m - 1u) {
+        uint32_t k = (uint32_t)ctz32(m);
+        int before = best_id;
+        prim_test<false>(ray, ginv, geom[3 * k], geom[3 * k + 1], geom[3 * k + 2], box, meta[k], best_t, best_id);
+        if (best_id != before) kb = k;
+    }
+    if (GATE && best_id >= 0 && !bounds_intersectp_inv(box[2 * kb], box[2 * kb + 1], ray, ginv.x, ginv.y, ginv.z)) {
+        best_t = NRCU_INF; best_id = -1;
+        for (uint32_t m = mask; m; m &= m - 1u) {
+            uint32_t k = (uint32_t)ctz32(m);
+            prim_test<true>(ray, ginv, geom[3 * k], geom[3 * k + 1], geom[3 * k + 2], box + 2 * k, meta[k], best_t, best_id);
+        }
+    }
 }
 // Can anything inside the BVH still beat best_t?  Conservative slab test against the padded BVH bounds.
 NR_HD bool bvh_reachable(const DScene& s, const RayPrep& rp, float best_t) {
@@ -261,7 +304,7 @@ NR_HD void closest_hit_bvh(const DScene& s, const Ray& ray, Stack& stack, float&
     best_t = NRCU_INF; best_id = -1;
     RayPrep rp = prep_ray(ray);
     vec3 ginv = gate_inverse(ray);
-    big_list_step<GATE>(s, s.big_geom, s.big_box, s.big_meta, ray, ginv, best_t, best_id);
+    big_list_step<GATE>(s, s.big_geom, s.big_box, s.big_bound, s.big_meta, ray, rp, ginv, best_t, best_id);
     if (!bvh_reachable(s, rp, best_t)) return;
     int cur = s.root_ref;
     for (;;) {

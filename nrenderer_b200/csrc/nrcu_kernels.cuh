@@ -16,9 +16,9 @@ __global__ void k_mesh_transform(float* pos, uint32_t first_vertex, uint32_t n_v
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_vertices) mesh_transform_vertex(pos, first_vertex + i);
 }
-__global__ void k_build_prims(PrimSources ps, uint32_t n, int raycast, f4* geom, f4* shade, f4* box, uint32_t* meta, float* export16) {
+__global__ void k_build_prims(PrimSources ps, uint32_t n, int raycast, f4* geom, f4* shade, f4* box, f4* bound, uint32_t* meta, float* export16) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) build_prim(ps, i, raycast, geom, shade, box, meta, export16);
+    if (i < n) build_prim(ps, i, raycast, geom, shade, box, bound, meta, export16);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -65,18 +65,67 @@ __global__ void k_raycast(DScene s, f4* rgba, unsigned long long* ray_counter) {
 // slot = sample_in_wave * n_pixels + pixel identifies the path; its radiance lands in L[slot].
 struct PathQueue { f4* a; f4* b; f4* c; };
 
-__global__ void k_raygen(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_slots, PathQueue q, f4* L, uint32_t* n_queue) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_slots) return;
-    if (slot == 0) *n_queue = s.depth == 0 ? 0u : n_slots;   // every slot starts one path: the bounce-0 queue is dense
-    uint32_t npix = s.width * s.height;
-    uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
-    if (s.depth == 0) { L[slot] = mk4(s.ambient.x, s.ambient.y, s.ambient.z, 0.f); return; }   // trace(): currDepth == depth
-    L[slot] = mk4(0.f, 0.f, 0.f, 0.f);
-    Ray r = pt_camera_ray(s, seed, pixel, sample);
-    q.a[slot] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
-    q.b[slot] = mk4(r.d.y, r.d.z, 1.f, 1.f);
-    q.c[slot] = mk4(1.f, i2f((int)slot), i2f(0), 0.f);
+// The wide-primitive list staged in shared memory (read as warp-wide broadcasts).
+struct BigList {
+    f4 g[NRCU_MAX_BIG * 3]; f4 b[NRCU_MAX_BIG * 2]; f4 bd[NRCU_MAX_BIG * 2]; uint32_t m[NRCU_MAX_BIG];
+    __device__ __forceinline__ void load(const DScene& s) {
+        for (uint32_t k = threadIdx.x; k < s.n_big * 3; k += blockDim.x) g[k] = s.big_geom[k];
+        for (uint32_t k = threadIdx.x; k < s.n_big * 2; k += blockDim.x) { b[k] = s.big_box[k]; bd[k] = s.big_bound[k]; }
+        for (uint32_t k = threadIdx.x; k < s.n_big; k += blockDim.x) m[k] = s.big_meta[k];
+        __syncthreads();
+    }
+};
+// Closest hit, stage 1, for a ray that is still in registers: every lane walks the same short list of wide
+// primitives (no traversal divergence), stores the provisional hit of queue entry `pos` and reports whether
+// anything inside the BVH could still be closer (conservative test against the BVH bounds).
+template <bool GATE>
+__device__ __forceinline__ bool stage1(const DScene& s, const BigList& bl, const Ray& r, uint32_t pos, float2* hits) {
+    RayPrep rp = prep_ray(r);
+    float best_t = NRCU_INF; int best_id = -1;
+    big_list_step<GATE>(s, bl.g, bl.b, bl.bd, bl.m, r, rp, gate_inverse(r), best_t, best_id);
+    hits[pos] = make_float2(best_t, __int_as_float(best_id));
+    return bvh_reachable(s, rp, best_t);
+}
+// Append the flagged lanes' queue positions to the survivor list with one atomic per warp.
+__device__ __forceinline__ void append_survivors(bool more, uint32_t pos, uint32_t* surv, uint32_t* n_surv) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = __ballot_sync(0xffffffffu, more);
+    if (m == 0) return;
+    uint32_t start = 0;
+    if (lane == 0) start = atomicAdd(n_surv, (uint32_t)__popc(m));
+    start = __shfl_sync(0xffffffffu, start, 0);
+    if (more) surv[start + __popc(m & ((1u << lane) - 1u))] = pos;
+}
+
+// Camera rays of one wave (slot = sample_in_wave * n_pixels + pixel) + stage 1 of their closest hit.
+template <bool GATE>
+__global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_slots, PathQueue q, f4* L, uint32_t* n_queue,
+                                               float2* hits, uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+    __shared__ BigList bl;
+    bl.load(s);
+    const uint32_t npix = s.width * s.height;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *n_queue = s.depth == 0 ? 0u : n_slots;   // every slot starts one path: the bounce-0 queue is dense
+        if (s.depth != 0) atomicAdd(ray_counter, (unsigned long long)n_slots);
+    }
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_slots; base += stride) {   // warp-uniform trip count
+        const uint32_t slot = base + threadIdx.x;
+        bool more = false;
+        if (slot < n_slots) {
+            uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
+            if (s.depth == 0) L[slot] = mk4(s.ambient.x, s.ambient.y, s.ambient.z, 0.f);   // trace(): currDepth == depth
+            else {
+                L[slot] = mk4(0.f, 0.f, 0.f, 0.f);
+                Ray r = pt_camera_ray(s, seed, pixel, sample);
+                q.a[slot] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
+                q.b[slot] = mk4(r.d.y, r.d.z, 1.f, 1.f);
+                q.c[slot] = mk4(1.f, i2f((int)slot), i2f(0), 0.f);
+                more = stage1<GATE>(s, bl, r, slot, hits);
+            }
+        }
+        append_survivors(more, slot, surv, n_surv);
+    }
 }
 
 #define NRCU_TRACE_THREADS 128
@@ -92,13 +141,8 @@ __global__ void k_raygen(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_s
 template <bool GATE>
 __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
                                             uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
-    __shared__ f4 sg[NRCU_MAX_BIG * 3];
-    __shared__ f4 sb[NRCU_MAX_BIG * 2];
-    __shared__ uint32_t sm[NRCU_MAX_BIG];
-    for (uint32_t k = threadIdx.x; k < s.n_big * 3; k += blockDim.x) sg[k] = s.big_geom[k];
-    for (uint32_t k = threadIdx.x; k < s.n_big * 2; k += blockDim.x) sb[k] = s.big_box[k];
-    for (uint32_t k = threadIdx.x; k < s.n_big; k += blockDim.x) sm[k] = s.big_meta[k];
-    __syncthreads();
+    __shared__ BigList bl;
+    bl.load(s);
     const uint32_t n = *n_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -109,20 +153,10 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
         if (i < n) {
             f4 a = q.a[i], b = q.b[i];
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
-            RayPrep rp = prep_ray(r);
-            float best_t = NRCU_INF; int best_id = -1;
-            big_list_step<GATE>(s, sg, sb, sm, r, gate_inverse(r), best_t, best_id);
-            hits[i] = make_float2(best_t, __int_as_float(best_id));
-            more = bvh_reachable(s, rp, best_t);
+            more = stage1<GATE>(s, bl, r, i, hits);
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, more);
-        uint32_t start = 0;
-        if (lane == 0) {
-            if (m) start = atomicAdd(n_surv, (uint32_t)__popc(m));
-            atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
-        }
-        start = __shfl_sync(0xffffffffu, start, 0);
-        if (more) surv[start + __popc(m & ((1u << lane) - 1u))] = i;
+        if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        append_survivors(more, i, surv, n_surv);
     }
 }
 
@@ -334,11 +368,18 @@ __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hit
     hits[i] = make_float2(t, __int_as_float(id));
 }
 
-// Shading + next-ray generation for bounce `d`; surviving paths are compacted into `qo` with one
-// atomic per warp (ballot + popc prefix).
+// Shading + next-ray generation for bounce `d`; surviving paths are compacted into `qo` with one atomic per
+// warp (ballot + popc prefix).  FUSE: stage 1 of the NEXT bounce's closest hit runs here, while the new ray is
+// still in registers (it writes hits_out[pos] and appends the rays that must enter the BVH to the survivor list).
+// Measured on B200 the fused form is slower (profiles/r1_*): it pushes the kernel from 64 to 73 registers and the
+// shading kernel is latency-bound, so by default stage 1 of bounces >= 1 runs as its own kernel (k_big).
+template <bool GATE, bool FUSE>
 __global__ void __launch_bounds__(256) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
                                               PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
-                                              PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L) {
+                                              PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L,
+                                              float2* hits_out, uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+    __shared__ BigList bl;
+    if (FUSE) bl.load(s);
     const uint32_t n = *n_in_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -366,25 +407,28 @@ __global__ void __launch_bounds__(256) k_shade(DScene s, uint64_t seed, uint32_t
         // warp-aggregated allocation in the output queue
         uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
         uint32_t total = __popc(m1) + __popc(m2);
+        if (total == 0) continue;   // warp-uniform
         uint32_t start = 0;
-        if (lane == 0 && total) start = atomicAdd(n_out_ptr, total);
+        if (lane == 0) { start = atomicAdd(n_out_ptr, total); if (FUSE) atomicAdd(ray_counter, (unsigned long long)total); }
         start = __shfl_sync(0xffffffffu, start, 0);
         uint32_t lt = (1u << lane) - 1u;
-        if (n_out >= 1) {
-            uint32_t pos = start + __popc(m1 & lt);
-            if (pos < out_capacity) {
-                qo.a[pos] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
-                qo.b[pos] = mk4(ps.next.d.y, ps.next.d.z, ps.thr.x, ps.thr.y);
-                qo.c[pos] = mk4(ps.thr.z, i2f((int)slot), i2f((int)branch), 0.f);
-            }
+        bool more1 = false, more2 = false;
+        uint32_t pos1 = start + __popc(m1 & lt), pos2 = start + __popc(m1) + __popc(m2 & lt);
+        if (n_out >= 1 && pos1 < out_capacity) {
+            qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
+            qo.b[pos1] = mk4(ps.next.d.y, ps.next.d.z, ps.thr.x, ps.thr.y);
+            qo.c[pos1] = mk4(ps.thr.z, i2f((int)slot), i2f((int)branch), 0.f);
+            if (FUSE) more1 = stage1<GATE>(s, bl, ps.next, pos1, hits_out);
         }
-        if (n_out == 2) {
-            uint32_t pos = start + __popc(m1) + __popc(m2 & lt);
-            if (pos < out_capacity) {
-                qo.a[pos] = mk4(ps.next2.o.x, ps.next2.o.y, ps.next2.o.z, ps.next2.d.x);
-                qo.b[pos] = mk4(ps.next2.d.y, ps.next2.d.z, ps.thr2.x, ps.thr2.y);
-                qo.c[pos] = mk4(ps.thr2.z, i2f((int)slot), i2f((int)(branch | (1u << (d & 31u)))), 0.f);
+        if (FUSE) append_survivors(more1, pos1, surv, n_surv);
+        if (m2) {   // warp-uniform: glass branch mode only
+            if (n_out == 2 && pos2 < out_capacity) {
+                qo.a[pos2] = mk4(ps.next2.o.x, ps.next2.o.y, ps.next2.o.z, ps.next2.d.x);
+                qo.b[pos2] = mk4(ps.next2.d.y, ps.next2.d.z, ps.thr2.x, ps.thr2.y);
+                qo.c[pos2] = mk4(ps.thr2.z, i2f((int)slot), i2f((int)(branch | (1u << (d & 31u)))), 0.f);
+                if (FUSE) more2 = stage1<GATE>(s, bl, ps.next2, pos2, hits_out);
             }
+            if (FUSE) append_survivors(more2, pos2, surv, n_surv);
         }
     }
 }

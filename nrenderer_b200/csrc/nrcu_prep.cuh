@@ -32,10 +32,14 @@ struct PrimSources {
 // Flattening (SimplePathTracer.cpp:57-78, BVH.hpp:34-60) + Bounds3 constructors (Bounds3.hpp:35-103):
 // one thread per output primitive writes its intersection record, shading record, leaf box and meta word
 // (and, for nrcu_download_primitives, the 16-float world-space description when export16 != null).
-NR_HD void build_prim(const PrimSources& ps, uint32_t i, int raycast, f4* geom, f4* shade, f4* box, uint32_t* meta, float* export16) {
+// `box` is the reference's Bounds3 of the primitive (what its leaf gate tests); `bound` is a box that really
+// contains the primitive (the reference's plane box can leave corners outside, Bounds3.hpp:52-78) and is
+// what the BVH and the wide-primitive pre-test are built from.
+NR_HD void build_prim(const PrimSources& ps, uint32_t i, int raycast, f4* geom, f4* shade, f4* box, f4* bound, uint32_t* meta, float* export16) {
     uint32_t a = ps.src_a[i], kind = a & 3u, e = a >> 2;
     int material;
-    vec3 lo, hi;
+    vec3 lo, hi, blo, bhi;
+    bool own_bound = false;
     if (kind == KIND_SPHERE) {
         vec3 c = ld3(ps.sphere_position + 3 * e); float r = ps.sphere_radius[e];
         material = ps.sphere_material[e];
@@ -55,6 +59,8 @@ NR_HD void build_prim(const PrimSources& ps, uint32_t i, int raycast, f4* geom, 
         vec3 p1 = p, p2 = p + u, p3 = p + v, p4 = p + u + v, en = 0.01f * n0;
         p1 = p1 - en; p2 = p2 - en; p3 = p3 + en; p4 = p4 + en;
         lo = vmin(p1, vmin(p2, vmin(p3, p4))); hi = vmax(p1, vmax(p2, vmax(p3, p4)));
+        vec3 c2 = p + u, c3 = p + v, c4 = p + u + v;
+        blo = vmin(lo, vmin(p, vmin(c2, vmin(c3, c4)))); bhi = vmax(hi, vmax(p, vmax(c2, vmax(c3, c4)))); own_bound = true;
         if (export16) { float* o = export16 + 16 * (size_t)i; for (int k = 0; k < 16; k++) o[k] = 0.f; st3(o, nn); st3(o + 3, p); st3(o + 6, u); st3(o + 9, v); }
     } else {
         vec3 v1, v2, v3, nrm;
@@ -78,6 +84,8 @@ NR_HD void build_prim(const PrimSources& ps, uint32_t i, int raycast, f4* geom, 
         if (export16) { float* o = export16 + 16 * (size_t)i; for (int k = 0; k < 16; k++) o[k] = 0.f; st3(o, v1); st3(o + 3, v2); st3(o + 6, v3); st3(o + 9, nrm); }
     }
     box[2 * i] = mk4(lo.x, lo.y, lo.z, 0.f); box[2 * i + 1] = mk4(hi.x, hi.y, hi.z, 0.f);
+    if (!own_bound) { blo = lo; bhi = hi; }
+    bound[2 * i] = mk4(blo.x, blo.y, blo.z, 0.f); bound[2 * i + 1] = mk4(bhi.x, bhi.y, bhi.z, 0.f);
     meta[i] = kind | ((uint32_t)material << 2);
 }
 

@@ -82,7 +82,10 @@ struct DCamera {   // Camera ctor results, ray_cast/include/Camera.hpp:25-46
 // empty slots carry an inverted box (lo = +inf, hi = -inf) and are never entered.
 #define NRCU_REF_EMPTY 0x7fffffff
 #define NRCU_MAX_BIG 32       // capacity of the wide-primitive list
-#define NRCU_BIG_AREA_FRACTION 0.02f   // a primitive is "wide" when its box has >= this fraction of the scene box's surface area
+#ifndef NRCU_BIG_AREA_FRACTION
+#define NRCU_BIG_AREA_FRACTION 0.02f
+#endif
+//   // a primitive is "wide" when its box has >= this fraction of the scene box's surface area
 
 struct DScene {
     int mode;
@@ -102,7 +105,8 @@ struct DScene {
     // tested by every ray in a warp-uniform loop (k_big) before the traversal starts; see nrcu_bvh.cuh
     const f4* big_geom;           // 3 per wide primitive
     const f4* big_box;            // 2 per wide primitive (leaf gate)
-    const uint32_t* big_meta;     // (prim id << 2) | kind, ascending id
+    const f4* big_bound;          // 2 per wide primitive: padded true bounds (conservative pre-test)
+    const uint32_t* big_meta;     // (prim id << 2) | kind; planes first, then triangles, then spheres
     uint32_t n_big;
     vec3 bvh_lo, bvh_hi;          // padded bounds of everything inside the BVH (lo > hi when it is empty)
     // shading

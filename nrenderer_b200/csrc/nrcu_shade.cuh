@@ -118,7 +118,7 @@ NR_HD float closest_light(const DScene& s, const Ray& r, vec3& radiance) {
     for (uint32_t i = 0; i < s.n_area_lights; i++) {
         const f4* L = s.area_lights + 4 * (size_t)i;
         float t;
-        if (x_quad<false>(r, ldg4(L), ldg4(L + 1), ldg4(L + 2), (float)0.000001, closest, t) && closest > t) {
+        if (x_quad<false>(r, ldg4(L), ldg4(L + 1), ldg4(L + 2), (float)0.000001, closest, closest, t) && closest > t) {
             closest = t;
             f4 rad = ldg4(L + 3);
             radiance = mk3(rad.x, rad.y, rad.z);

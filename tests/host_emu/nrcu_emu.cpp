@@ -25,7 +25,7 @@ struct EmuScene {
     HostPrep hp;
     uint32_t spp;
     std::vector<float> mesh_pos;
-    std::vector<f4> geom, shade, box, nodes, env, leaf_geom, leaf_box, big_geom, big_box;
+    std::vector<f4> geom, shade, box, nodes, env, leaf_geom, leaf_box, big_geom, big_box, big_bound, bound;
     std::vector<uint32_t> big_meta;
     int n_big = 0;
     std::vector<uint32_t> meta, leaf_prims;
@@ -45,7 +45,7 @@ static void emu_build_bvh(EmuScene& es) {
     es.leaf_prims.assign(n, 0);
     std::vector<f4> wide((size_t)std::max(1u, n) * NRCU_BVH_NODE_F4);
     BvhBuild b{};
-    b.n_prims = n; b.prim_box = es.box.data(); b.prim_meta = es.meta.data();
+    b.n_prims = n; b.prim_box = es.box.data(); b.prim_bound = es.bound.data(); b.prim_meta = es.meta.data();
     b.prim_node = prim_node.data(); b.nbox = nbox.data(); b.cbox = cbox.data(); b.ncount = ncount.data();
     b.nidmin = nidmin.data(); b.nidmax = nidmax.data(); b.nstate = nstate.data(); b.nchild = nchild.data();
     b.nsplit_axis = nsplit_axis.data(); b.nsplit_pos = nsplit_pos.data(); b.ndepth = ndepth.data();
@@ -54,8 +54,8 @@ static void emu_build_bvh(EmuScene& es) {
     b.leaf_prims = es.leaf_prims.data(); b.wide_nodes = wide.data();
     es.leaf_geom.assign(3 * (size_t)std::max(1u, n), mk4(0, 0, 0, 0)); es.leaf_box.assign(2 * (size_t)std::max(1u, n), mk4(0, 0, 0, 0));
     b.prim_geom = es.geom.data(); b.leaf_geom = es.leaf_geom.data(); b.leaf_box = es.leaf_box.data();
-    es.big_geom.assign(3 * NRCU_MAX_BIG, mk4(0, 0, 0, 0)); es.big_box.assign(2 * NRCU_MAX_BIG, mk4(0, 0, 0, 0)); es.big_meta.assign(NRCU_MAX_BIG, 0);
-    b.big_geom = es.big_geom.data(); b.big_box = es.big_box.data(); b.big_meta = es.big_meta.data(); b.big_count = &es.n_big;
+    es.big_geom.assign(3 * NRCU_MAX_BIG, mk4(0, 0, 0, 0)); es.big_box.assign(2 * NRCU_MAX_BIG, mk4(0, 0, 0, 0)); es.big_bound.assign(2 * NRCU_MAX_BIG, mk4(0, 0, 0, 0)); es.big_meta.assign(NRCU_MAX_BIG, 0);
+    b.big_geom = es.big_geom.data(); b.big_box = es.big_box.data(); b.big_bound = es.big_bound.data(); b.big_meta = es.big_meta.data(); b.big_count = &es.n_big;
     b.inflate = es.hp.max_abs_coord * (1.0f / 65536.0f);
     // same orchestration as build_bvh() in nrcu_api.cu
     counters[0] = 1;
@@ -65,7 +65,7 @@ static void emu_build_bvh(EmuScene& es) {
     node_clear(b, 0);
     for (uint32_t i = 0; i < n; i++) bvh_init_prim_rest(b, (int)i);
     DScene& ds = es.ds;
-    ds.big_geom = es.big_geom.data(); ds.big_box = es.big_box.data(); ds.big_meta = es.big_meta.data(); ds.n_big = (uint32_t)es.n_big;
+    ds.big_geom = es.big_geom.data(); ds.big_box = es.big_box.data(); ds.big_bound = es.big_bound.data(); ds.big_meta = es.big_meta.data(); ds.n_big = (uint32_t)es.n_big;
     ds.leaf_prims = es.leaf_prims.data(); ds.leaf_geom = es.leaf_geom.data(); ds.leaf_box = es.leaf_box.data();
     ds.root_ref = NRCU_REF_EMPTY; ds.bvh_lo = mk3(NRCU_INF); ds.bvh_hi = mk3(-NRCU_INF);
     const uint32_t n_rest = n - (uint32_t)es.n_big;
@@ -123,8 +123,8 @@ EmuScene* emu_create(const nrcu_scene* sc, int mode) {
     ps.mesh_vertex_offset = sc->n_meshes ? sc->mesh_vertex_offset : &zero; ps.mesh_index_offset = sc->n_meshes ? sc->mesh_index_offset : &zero;
     ps.mesh_positions = es->mesh_pos.data(); ps.mesh_indices = sc->mesh_indices; ps.mesh_material = sc->mesh_material;
     es->geom.assign(3 * (size_t)std::max(n, 1u), mk4(0, 0, 0, 0)); es->shade.assign(std::max(n, 1u), mk4(0, 0, 0, 0));
-    es->box.assign(2 * (size_t)std::max(n, 1u), mk4(0, 0, 0, 0)); es->meta.assign(std::max(n, 1u), 0); es->export16.assign(16 * (size_t)std::max(n, 1u), 0.f);
-    for (uint32_t i = 0; i < n; i++) build_prim(ps, i, mode == NRCU_MODE_RAYCAST, es->geom.data(), es->shade.data(), es->box.data(), es->meta.data(), es->export16.data());
+    es->box.assign(2 * (size_t)std::max(n, 1u), mk4(0, 0, 0, 0)); es->bound.assign(2 * (size_t)std::max(n, 1u), mk4(0, 0, 0, 0)); es->meta.assign(std::max(n, 1u), 0); es->export16.assign(16 * (size_t)std::max(n, 1u), 0.f);
+    for (uint32_t i = 0; i < n; i++) build_prim(ps, i, mode == NRCU_MODE_RAYCAST, es->geom.data(), es->shade.data(), es->box.data(), es->bound.data(), es->meta.data(), es->export16.data());
     DScene& ds = es->ds;
     ds.prim_geom = es->geom.data(); ds.prim_shade = es->shade.data(); ds.prim_box = es->box.data(); ds.prim_meta = es->meta.data();
     ds.materials = hp.materials.data(); ds.area_lights = hp.lights.data();

@@ -1,5 +1,4 @@
 set -x
 mkdir -p gpurun_out
-export NRCU_TRACE_REFILL=16
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_trace3 -c 3 -f -o gpurun_out/prof_v3 python bench.py --steps 1 --warmup 1 --spp 8 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_v3.log 2>&1
-tail -3 gpurun_out/ncu_v3.log
+timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_v4.csv python bench.py --steps 1 --warmup 1 --spp 4 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_v4.log 2>&1
+tail -2 gpurun_out/ncu_v4.log

@@ -11,7 +11,7 @@ static void traverse_count(const DScene& s, const Ray& ray, float& best_t, int& 
     best_t = NRCU_INF; best_id = -1; nodes = leaves = prims = 0;
     RayPrep rp = prep_ray(ray);
     vec3 ginv = gate_inverse(ray);
-    big_list_step<GATE>(s, s.big_geom, s.big_box, s.big_meta, ray, ginv, best_t, best_id);
+    big_list_step<GATE>(s, s.big_geom, s.big_box, s.big_bound, s.big_meta, ray, rp, ginv, best_t, best_id);
     if (!bvh_reachable(s, rp, best_t)) return;
     int cur = s.root_ref;
     LocalStack stack;
