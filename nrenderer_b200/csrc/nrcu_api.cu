@@ -474,7 +474,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 3 * (size_t)ds.depth + 12);
     cudaStream_t st = ctx->stream;
     const int sms = sm_count(ctx->device);
-    const unsigned shade_grid = (unsigned)sms * 4;
+    const unsigned shade_grid = (unsigned)sms * NRCU_SHADE_MINB;
     const bool timing = stats != nullptr;
     size_t ev_i = 0;
     struct Span { size_t a, b; int kind; };

@@ -147,16 +147,25 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // software pipeline as in k_shade: the next ray is requested before waiting for the survivor-list atomic
+    f4 a = mk4(0, 0, 0, 0), b = a;
+    { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
         const uint32_t i = base + lane;
         bool more = false;
         if (i < n) {
-            f4 a = q.a[i], b = q.b[i];
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             more = stage1<GATE>(s, bl, r, i, hits);
         }
         if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
-        append_survivors(more, i, surv, n_surv);
+        const uint32_t m = __ballot_sync(0xffffffffu, more);
+        uint32_t start = 0;
+        if (lane == 0 && m) start = atomicAdd(n_surv, (uint32_t)__popc(m));
+        { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; } }
+        if (m) {
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (more) surv[start + __popc(m & ((1u << lane) - 1u))] = i;
+        }
     }
 }
 
@@ -373,8 +382,11 @@ __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hit
 // still in registers (it writes hits_out[pos] and appends the rays that must enter the BVH to the survivor list).
 // Measured on B200 the fused form is slower (profiles/r1_*): it pushes the kernel from 64 to 73 registers and the
 // shading kernel is latency-bound, so by default stage 1 of bounces >= 1 runs as its own kernel (k_big).
+#ifndef NRCU_SHADE_MINB
+#define NRCU_SHADE_MINB 4
+#endif
 template <bool GATE, bool FUSE>
-__global__ void __launch_bounds__(256) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
+__global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
                                               PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
                                               PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L,
                                               float2* hits_out, uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
@@ -385,14 +397,21 @@ __global__ void __launch_bounds__(256) k_shade(DScene s, uint64_t seed, uint32_t
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t npix = s.width * s.height;
+    // Software pipeline: the queue entry of the NEXT iteration is requested right after this iteration's
+    // output-slot atomic has been issued, so the atomic's round trip and the loads' latency overlap (ncu on the
+    // unpipelined loop: 38 % of the stall samples sat on the shuffle that waits for the atomic, 16 % on the first
+    // use of the loaded entry).
+    f4 a = mk4(0, 0, 0, 0), b = a, c = a; float2 h = make_float2(0.f, 0.f);
+    {
+        const uint32_t i0 = warp_global * 32u + lane;
+        if (i0 < n) { a = qi.a[i0]; b = qi.b[i0]; c = qi.c[i0]; h = hits[i0]; }
+    }
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
         uint32_t i = base + lane;
         int n_out = 0;
         PathStep ps;
         uint32_t slot = 0, branch = 0;
         if (i < n) {
-            f4 a = qi.a[i], b = qi.b[i], c = qi.c[i];
-            float2 h = hits[i];
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             vec3 thr = mk3(b.z, b.w, c.x);
             slot = (uint32_t)f2i(c.y); branch = (uint32_t)f2i(c.z);
@@ -407,9 +426,13 @@ __global__ void __launch_bounds__(256) k_shade(DScene s, uint64_t seed, uint32_t
         // warp-aggregated allocation in the output queue
         uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
         uint32_t total = __popc(m1) + __popc(m2);
-        if (total == 0) continue;   // warp-uniform
         uint32_t start = 0;
-        if (lane == 0) { start = atomicAdd(n_out_ptr, total); if (FUSE) atomicAdd(ray_counter, (unsigned long long)total); }
+        if (lane == 0 && total) { start = atomicAdd(n_out_ptr, total); if (FUSE) atomicAdd(ray_counter, (unsigned long long)total); }
+        {   // prefetch the next iteration's entry while the atomic is in flight
+            const uint32_t inext = i + warps_total * 32u;
+            if (inext < n) { a = qi.a[inext]; b = qi.b[inext]; c = qi.c[inext]; h = hits[inext]; }
+        }
+        if (total == 0) continue;   // warp-uniform
         start = __shfl_sync(0xffffffffu, start, 0);
         uint32_t lt = (1u << lane) - 1u;
         bool more1 = false, more2 = false;
