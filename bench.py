@@ -8,13 +8,15 @@ Workload (BASELINE.json configs[2], the configuration the north-star target is q
 AccPathTracer semantics on the Stanford bunny (5k triangles) inside the Cornell box, 1920x1080,
 1024 spp, depth 20, aspect 16/9 — SURVEY.md §8(d) cfg3.  A "step" renders that whole frame.
 With N GPUs the 1024 samples of every pixel are split into N sample slices (strong scaling), the
-partial linear frames are combined with one NCCL reduce, rank 0 resolves (÷spp, sqrt) the frame.
+partial linear frames are combined with one NCCL reduce, rank 0 resolves (÷spp, sqrt) the frame
+(nrenderer_b200/multigpu.py).
 
 One JSON line on rank 0:
   value      Mpath-samples/s, whole job, scene resident in HBM, device-timed (CUDA events, max over ranks)
   e2e        the same metric through the reference-facing call sequence with HOST buffers: upload of
              the Scene arrays (H2D), render, D2H of the RGBA frame that Screen::set would receive
-  roofline   the traversal kernel (k_trace): algorithmic bytes/ray x rays / CUDA-event time of its launches
+  roofline   the closest-hit kernels (k_raygen incl. fused stage 1, k_big, k_trace2): algorithmic bytes/ray x rays /
+             CUDA-event time of their launches inside the timed region
   cpu_baseline  the reference's own AccPathTracer (oracle/_ref, unmodified sources) on the host cores,
              on a bounded sample (same frame, few spp)
 """
@@ -53,6 +55,15 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_summary():
+    """Numbers derived from the committed ncu captures (profiles/r1_summary.json); not measured live."""
+    p = os.path.join(REPO, "profiles", "r1_summary.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -168,7 +179,6 @@ def cuda_arm(args):
     dev = torch.device(f"cuda:{local}")
     fs, mode, comp, bytes_per_ray = load_workload(args.workload, args.spp)
     w, h, spp = fs.width, fs.height, fs.samples_per_pixel
-    s0, s1 = rank * spp // world, (rank + 1) * spp // world
 
     ctx = Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)   # our kernels, NCCL and the timing events share one stream
@@ -183,15 +193,16 @@ def cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from nrenderer_b200 import multigpu
+
+    def resolve(acc, out):
+        ctx.resolve(acc.data_ptr(), out.data_ptr())
+
     def step(want_stats):
         flush.fill_(1)
-        accum.zero_()
-        st = ctx.render_accumulate(accum.data_ptr(), s0=s0, s1=s1, seed=args.seed, want_stats=want_stats)
-        if world > 1:
-            dist.reduce(accum, dst=0)
-        if rank == 0:
-            ctx.resolve(accum.data_ptr(), rgba.data_ptr())
-        return st
+        return multigpu.render_frame(
+            lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=want_stats),
+            resolve, accum, rgba, spp, rank, world)
 
     for _ in range(args.warmup):
         step(False)
@@ -205,7 +216,7 @@ def cuda_arm(args):
     for _ in range(args.steps):
         st = step(True)
         for k in agg:
-            agg[k] += st[k]
+            agg[k] += st[k] if st else 0
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -226,12 +237,10 @@ def cuda_arm(args):
 
     def e2e_step():
         ctx.upload(fs, mode)                                    # H2D of the scene + device-side flattening + BVH build
-        accum.zero_()
-        ctx.render_accumulate(accum.data_ptr(), s0=s0, s1=s1, seed=args.seed, want_stats=False)
-        if world > 1:
-            dist.reduce(accum, dst=0)
+        multigpu.render_frame(
+            lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=False),
+            resolve, accum, rgba, spp, rank, world)
         if rank == 0:
-            ctx.resolve(accum.data_ptr(), rgba.data_ptr())
             host_rgba.copy_(rgba, non_blocking=True)            # D2H of what Screen::set receives
         torch.cuda.synchronize()
 
@@ -259,12 +268,17 @@ def cuda_arm(args):
                        "l2": "256 MB flush buffer written between steps; per-wave ray/path state (~1 GB) exceeds the 126 MB L2",
                        "glass_mode": "stochastic", "seed": args.seed},
             "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / max(paths, 1),
-            "kernel_ms": {"trace": ms_trace / args.steps, "shade": ms_shade / args.steps},
+            "kernel_ms": {"closest_hit": ms_trace / args.steps, "shade": ms_shade / args.steps},
             "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h if True else 0, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                         "traffic": None, "kernel": "k_trace", "algorithmic_bytes_per_ray": bytes_per_ray, "peak_source": peak_src,
-                         "note": "scene is L1/L2 resident: the binding limit is issue slots / warp efficiency (see profiles/)"},
+                         "traffic": profile_summary().get("closest_hit_dram_bytes_per_step_equiv"),
+                         "kernel": "closest hit = k_raygen (camera rays + fused stage 1) + k_big + k_trace2", "algorithmic_bytes_per_ray": bytes_per_ray,
+                         "peak_source": peak_src, "share_of_step": ms_trace / ms if ms else None,
+                         "note": "algorithmic bytes are those of the REFERENCE's traversal (SURVEY 8d); the scene is L1/L2 resident, so the "
+                                 "fraction can exceed 1 and the binding limit is issue slots x warp efficiency: see 'issue' (from the committed "
+                                 "ncu launch list, profiles/) and DESIGN.md section 5",
+                         "issue": profile_summary().get("issue")},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

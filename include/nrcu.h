@@ -192,8 +192,8 @@ typedef struct nrcu_stats {
     uint64_t rays;             /* closest-hit queries + shadow rays actually traced (device counter) */
     uint64_t kernel_launches;  /* launches of this library's kernels during the call */
     float ms_total;            /* CUDA-event time of the whole call on the context's stream */
-    float ms_trace;            /* time inside the traversal kernels */
-    float ms_shade;            /* time inside the shading / ray generation kernels */
+    float ms_trace;            /* time inside the closest-hit kernels: k_raygen (camera rays + fused stage 1), k_big, k_trace* */
+    float ms_shade;            /* time inside the shading kernels */
     float ms_setup;            /* scene preparation + BVH build at upload time */
     uint32_t bvh_nodes;        /* wide nodes */
     uint32_t n_primitives;     /* primitives after mesh flattening */

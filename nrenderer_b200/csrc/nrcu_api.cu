@@ -493,7 +493,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         if (gate) k_raygen<true><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn, hb[0], surv, d_nsurv, d_rays);
         else k_raygen<false><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn, hb[0], surv, d_nsurv, d_rays);
         CTX_LAUNCH_CHECK("k_raygen");
-        if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 1}); ev_i += 2; }
+        if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); ev_i += 2; }   // booked as closest-hit time: stage 1 of bounce 0 is most of this kernel
         for (uint32_t d = 0; d < ds.depth; d++) {
             PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
             float2* hi = hb[d & 1]; float2* ho = hb[(d + 1) & 1];

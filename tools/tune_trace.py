@@ -34,7 +34,7 @@ def main():
                             "--no-cpu-baseline", "--e2e-steps", "1"] + extra, capture_output=True, text=True, env=env)
         try:
             d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-            print(f"{st}: {d['value']:.1f} Mpath/s  {d['mrays_per_s']:.1f} Mrays/s  trace {d['kernel_ms']['trace']:.2f} ms  shade {d['kernel_ms']['shade']:.2f} ms  step {d['ms_per_step']:.2f} ms", flush=True)
+            print(f"{st}: {d['value']:.1f} Mpath/s  {d['mrays_per_s']:.1f} Mrays/s  closest-hit {d['kernel_ms']['closest_hit']:.2f} ms  shade {d['kernel_ms']['shade']:.2f} ms  step {d['ms_per_step']:.2f} ms", flush=True)
         except Exception:
             print(st, "FAILED", r.stdout[-500:], r.stderr[-1500:], flush=True)
 
