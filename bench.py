@@ -246,11 +246,15 @@ def cuda_arm(args):
 
     e2e_step()
     barrier()
+    sampler2 = ClockSampler(local) if rank == 0 else None
+    if sampler2:
+        sampler2.start()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_clocks = sampler2.stop() if sampler2 else None
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -269,7 +273,7 @@ def cuda_arm(args):
                        "glass_mode": "stochastic", "seed": args.seed},
             "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / max(paths, 1),
             "kernel_ms": {"closest_hit": ms_trace / args.steps, "shade": ms_shade / args.steps},
-            "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h if True else 0, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "clocks": e2e_clocks},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": profile_summary().get("closest_hit_dram_bytes_per_step_equiv"),

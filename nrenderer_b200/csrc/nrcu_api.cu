@@ -415,6 +415,7 @@ static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
 static uint32_t env_u32(const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : dflt; }
 static bool fuse_stage1() { static uint32_t v = env_u32("NRCU_FUSE_STAGE1", 0); return v != 0; }
+static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 32) << 20; return v; }
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
@@ -425,7 +426,8 @@ static void launch_stage2(nrcu_ctx* ctx, const DScene& ds, PathQueue q, float2* 
                           uint32_t* fetch, unsigned long long* rays) {
     const unsigned grid = (unsigned)sm_count(ctx->device) * trace_blocks_per_sm();
     if (trace_variant() == 3) k_trace3<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill(), trace_w_node(), trace_w_prim());
-    else k_trace2<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
+    else if (trace_variant() == 4) k_trace2<GATE, true><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
+    else k_trace2<GATE, false><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
 }
 
 // Closest hit for the first *n_ptr entries of queue `q` into hits[] (the stand-alone form used by
@@ -456,9 +458,11 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     if (s1 < s0) { ctx->error = "sample_end < sample_begin"; return NRCU_ERR_INVALID; }
     const uint64_t seed = params ? params->seed : 0;
     const int glass_branch = params && params->glass_mode == NRCU_GLASS_BRANCH;
-    // wave size: k samples of every pixel, about 8M paths in flight
+    // wave size: k samples of every pixel, about NRCU_WAVE_SLOTS (default 32 Mi) paths in flight.  Bigger waves
+    // amortise the per-launch latency floor of the deep bounces (few rays, ~50 us per persistent launch) over
+    // more paths; 32 Mi slots cost ~4 GB of the 180 GB HBM.
     uint32_t k = params ? params->samples_per_wave : 0;
-    if (k == 0) k = std::max<uint32_t>(1, (8u << 20) / npix);
+    if (k == 0) k = std::max<uint32_t>(1, wave_slots_target() / npix);
     k = std::min<uint32_t>(k, std::max<uint32_t>(1, s1 - s0));
     if ((uint64_t)k * npix > 0x7fffffffull) k = std::max<uint32_t>(1, (uint32_t)(0x7fffffffull / npix));
     const uint32_t slots = k * npix;
@@ -515,8 +519,10 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
 #undef NRCU_SHADE
             CTX_LAUNCH_CHECK("k_shade");
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
-            k_clamp_count<<<1, 1, 0, st>>>(d_qn + d + 1, capacity, cnt + CNT_HIGH_WATER);
-            CTX_LAUNCH_CHECK("k_clamp_count");
+            if (glass_branch) {   // only the branching mode can outgrow the queue
+                k_clamp_count<<<1, 1, 0, st>>>(d_qn + d + 1, capacity, cnt + CNT_HIGH_WATER);
+                CTX_LAUNCH_CHECK("k_clamp_count");
+            }
         }
         k_accumulate<<<grid_for(npix, 256), 256, 0, st>>>(ctx->L.as<f4>(), d_accum, npix, kw);
         CTX_LAUNCH_CHECK("k_accumulate");
@@ -537,7 +543,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         stats->rays = rays; stats->paths = (uint64_t)npix * (s1 - s0);
         stats->kernel_launches = ctx->launches - launches0;
         stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
-        stats->max_queue = h_cnt[CNT_HIGH_WATER];
+        stats->max_queue = glass_branch ? h_cnt[CNT_HIGH_WATER] : std::min<uint32_t>(slots, npix * (s1 - s0));   // without branching the bounce-0 queue is the largest
     }
     return NRCU_OK;
 }

@@ -252,7 +252,7 @@ __device__ __forceinline__ bool fetch_ray(const DScene& s, const PathQueue& q, c
 // v2: persistent threads, "while-while" traversal and lane refill.  Every lane keeps one ray's traversal state
 // in registers; when at least `refill` lanes of the warp are idle (or all of them) the warp claims that many new
 // rays.  Leaf work is postponed until every active lane has reached a leaf (Aila & Laine's while-while).
-template <bool GATE>
+template <bool GATE, bool IFIF>
 __global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace2(DScene s, PathQueue q, const uint32_t* n_ptr, const uint32_t* surv, float2* hits,
                                                                uint32_t* fetch, unsigned long long* ray_counter, uint32_t refill) {
     __shared__ uint2 stack_mem[NRCU_T3_STACK * NRCU_TRACE_THREADS];
@@ -282,8 +282,9 @@ __global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace2(DScene s, PathQue
             }
         }
         if (active) {
-            while (L.cur >= 0) L.cur = node_step3(s, L.rp, L.cur, L.best_t, st, L.sp);
-            if (L.cur != NRCU_REF_DONE) {
+            if (IFIF) { if (L.cur >= 0) L.cur = node_step3(s, L.rp, L.cur, L.best_t, st, L.sp); }   // "if-if": one step of either kind per iteration
+            else while (L.cur >= 0) L.cur = node_step3(s, L.rp, L.cur, L.best_t, st, L.sp);
+            if (L.cur < 0 && L.cur != NRCU_REF_DONE) {
                 leaf_step<GATE>(s, L.r, L.ginv, L.cur, L.best_t, L.best_id);
                 L.cur = pop3(st, L.sp, L.best_t);
             }
@@ -418,9 +419,13 @@ __global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScen
             uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
             ps = path_vertex(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch);
             if (ps.action == PATH_TERMINATE) {
-                if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
-                if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
-                if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
+                if (glass_branch) {   // several branches of one path share the slot
+                    if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
+                    if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
+                    if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
+                } else if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
+                    L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);   // one path per slot, it ends once: plain store into the zeroed slot
+                }
             } else n_out = ps.action == PATH_SPLIT ? 2 : 1;
         }
         // warp-aggregated allocation in the output queue
