@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,18 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// NRCU_TRACE_UPLOAD=1: print the wall time of the phases of nrcu_upload_scene to stderr (diagnostics)
+struct PhaseTimer {
+    bool on; std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(std::getenv("NRCU_TRACE_UPLOAD") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[nrcu upload] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
     ~DevBuf() { release(); }
@@ -38,6 +51,10 @@ struct DevBuf {
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// sub-allocation of the BVH build arena
+struct Carve { char* base; size_t off; void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; } };
+struct Sub { void* p = nullptr; template <typename T> T* as() const { return reinterpret_cast<T*>(p); } };
 
 }  // namespace
 
@@ -57,7 +74,7 @@ struct nrcu_ctx {
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
     PrimSources ps{};
     // wavefront state
-    DevBuf qa[2], qb[2], qc[2], hits[2], surv, L, counters, accum_own, rgba_dev;
+    DevBuf qa[2], qb[2], qc[2], hits[2], surv, L, counters, accum_own, rgba_dev, build_scratch;
     uint32_t queue_capacity = 0, wave_slots = 0;
     unsigned long long* d_ray_counter = nullptr;   // inside `counters`
     // stats
@@ -175,8 +192,10 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
     if (!sc || mode < NRCU_MODE_RAYCAST || mode > NRCU_MODE_ACC) { ctx->error = "nrcu_upload_scene: bad arguments"; return NRCU_ERR_INVALID; }
     CTX_CUDA(cudaSetDevice(ctx->device));
     ctx->have_scene = false;
+    PhaseTimer pt;
     HostPrep hp;
     std::string why = host_prepare(sc, mode, hp);
+    pt.mark("host_prepare");
     if (!why.empty()) { ctx->error = "nrcu_upload_scene: " + why; return NRCU_ERR_INVALID; }
     cudaEvent_t e0, e1;
     CTX_CUDA(cudaEventCreate(&e0)); CTX_CUDA(cudaEventCreate(&e1));
@@ -242,12 +261,14 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
     ctx->spp = sc->samples_per_pixel;
     ctx->mode = mode;
     CTX_CUDA(cudaStreamSynchronize(ctx->stream));   // the pageable staging vectors in `hp` die with this scope
+    pt.mark("h2d + flatten kernels");
 
     // ---- BVH ----------------------------------------------------------------------------------------
     ctx->bvh_nodes = 0;
     if (mode != NRCU_MODE_RAYCAST && n > 0) {
         if ((rc = build_bvh(ctx, n, hp.max_abs_coord)) != NRCU_OK) return rc;
     }
+    pt.mark("build_bvh (incl. frees)");
     CTX_CUDA(cudaEventRecord(e1, ctx->stream));
     CTX_CUDA(cudaEventSynchronize(e1));
     CTX_CUDA(cudaEventElapsedTime(&ctx->ms_setup, e0, e1));
@@ -259,20 +280,28 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
 static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     const int cap = 2 * (int)n + 2;
     const int bin_nodes = std::max(64, (int)(0.4 * n) + 8);
-    DevBuf prim_node, nbox, cbox, ncount, nidmin, nidmax, nstate, nchild, nsplit_axis, nsplit_pos, ndepth, nleaf_first, nleaf_fill,
+    // Build scratch comes from ONE arena that lives in the context and only ever grows: cudaMalloc/cudaFree per
+    // upload cost 5 ms in the good case and hundreds of ms when gigabytes of wave buffers are mapped (measured).
+    Sub prim_node, nbox, cbox, ncount, nidmin, nidmax, nstate, nchild, nsplit_axis, nsplit_pos, ndepth, nleaf_first, nleaf_fill,
         nwide, bins, counters, nbin_slot, wide_tmp, big_count;
-    CTX_CUDA(prim_node.ensure(sizeof(int) * (size_t)n));
-    CTX_CUDA(nbox.ensure(sizeof(int) * 6 * (size_t)cap)); CTX_CUDA(cbox.ensure(sizeof(int) * 6 * (size_t)cap));
-    DevBuf* per_node[] = {&ncount, &nidmin, &nidmax, &nstate, &nchild, &nsplit_axis, &nsplit_pos, &ndepth, &nleaf_first, &nleaf_fill, &nwide, &nbin_slot};
-    for (DevBuf* b : per_node) CTX_CUDA(b->ensure(sizeof(int) * (size_t)cap));
-    CTX_CUDA(bins.ensure(sizeof(int) * (size_t)bin_nodes * 3 * NRCU_NBINS * NRCU_BIN_WORDS));
-    CTX_CUDA(counters.ensure(sizeof(int) * 8)); CTX_CUDA(big_count.ensure(sizeof(int)));
+    Sub* per_node[] = {&ncount, &nidmin, &nidmax, &nstate, &nchild, &nsplit_axis, &nsplit_pos, &ndepth, &nleaf_first, &nleaf_fill, &nwide, &nbin_slot};
+    for (int pass = 0; pass < 2; pass++) {   // pass 0 sizes the arena, pass 1 hands out the pointers
+        Carve cv{pass ? ctx->build_scratch.as<char>() : nullptr, 0};
+        prim_node.p = cv.take(sizeof(int) * (size_t)n);
+        nbox.p = cv.take(sizeof(int) * 6 * (size_t)cap); cbox.p = cv.take(sizeof(int) * 6 * (size_t)cap);
+        for (Sub* b : per_node) b->p = cv.take(sizeof(int) * (size_t)cap);
+        bins.p = cv.take(sizeof(int) * (size_t)bin_nodes * 3 * NRCU_NBINS * NRCU_BIN_WORDS);
+        counters.p = cv.take(sizeof(int) * 8); big_count.p = cv.take(sizeof(int));
+        wide_tmp.p = cv.take(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1u, n));
+        if (pass == 0) CTX_CUDA(ctx->build_scratch.ensure(cv.off));
+    }
     CTX_CUDA(ctx->leaf_prims.ensure(sizeof(uint32_t) * (size_t)n));
     CTX_CUDA(ctx->leaf_geom.ensure(sizeof(f4) * 3 * (size_t)n)); CTX_CUDA(ctx->leaf_box.ensure(sizeof(f4) * 2 * (size_t)n));
     CTX_CUDA(ctx->big_geom.ensure(sizeof(f4) * 3 * NRCU_MAX_BIG)); CTX_CUDA(ctx->big_box.ensure(sizeof(f4) * 2 * NRCU_MAX_BIG));
     CTX_CUDA(ctx->big_meta.ensure(sizeof(uint32_t) * NRCU_MAX_BIG)); CTX_CUDA(ctx->big_bound.ensure(sizeof(f4) * 2 * NRCU_MAX_BIG));
-    CTX_CUDA(wide_tmp.ensure(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1u, n)));
 
+    PhaseTimer pt;
+    pt.mark("  bvh: allocations");
     BvhBuild b{};
     b.n_prims = n; b.prim_box = ctx->prim_box.as<f4>(); b.prim_bound = ctx->prim_bound.as<f4>(); b.prim_meta = ctx->prim_meta.as<uint32_t>();
     b.prim_node = prim_node.as<int>(); b.nbox = nbox.as<int>(); b.cbox = cbox.as<int>(); b.ncount = ncount.as<int>();
@@ -299,6 +328,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     CTX_CUDA(cudaMemcpyAsync(&n_big, big_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CTX_CUDA(cudaMemcpyAsync(root_box, nbox.p, sizeof(root_box), cudaMemcpyDeviceToHost, st));
     CTX_CUDA(cudaStreamSynchronize(st));
+    pt.mark("  bvh: init + wide list");
     ctx->n_big = (uint32_t)n_big;
     DScene& ds = ctx->ds;
     ds.big_geom = ctx->big_geom.as<f4>(); ds.big_box = ctx->big_box.as<f4>(); ds.big_bound = ctx->big_bound.as<f4>(); ds.big_meta = ctx->big_meta.as<uint32_t>(); ds.n_big = (uint32_t)n_big;
@@ -322,6 +352,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
         k_bvh_partition<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_partition");
         begin = end; end = h_counters[0];
     }
+    pt.mark("  bvh: level loop");
     const int n_nodes = h_counters[0];
     k_bvh_leaf_alloc<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_leaf_alloc");
     k_bvh_leaf_fill<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_leaf_fill");
@@ -341,6 +372,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     CTX_CUDA(ctx->nodes.ensure(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1, n_wide)));
     if (n_wide) CTX_CUDA(cudaMemcpyAsync(ctx->nodes.p, wide_tmp.p, sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)n_wide, cudaMemcpyDeviceToDevice, st));
     CTX_CUDA(cudaStreamSynchronize(st));
+    pt.mark("  bvh: leaves + wide emit");
     ds.nodes = ctx->nodes.as<f4>();
     ds.root_ref = root_state == BNODE_LEAF ? ~((root_first << 4) | (root_cnt - 1)) : root_wide;
     ctx->bvh_nodes = (uint32_t)n_wide;
@@ -416,6 +448,7 @@ static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e =
 static uint32_t env_u32(const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : dflt; }
 static bool fuse_stage1() { static uint32_t v = env_u32("NRCU_FUSE_STAGE1", 0); return v != 0; }
 static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 32) << 20; return v; }
+static bool shade_deferred() { static uint32_t v = env_u32("NRCU_SHADE_DEFERRED", 0); return v != 0; }
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
@@ -514,7 +547,11 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
             }
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
 #define NRCU_SHADE(G, F) k_shade<G, F><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, capacity, ctx->L.as<f4>(), ho, surv, d_nsurv + d + 1, d_rays)
-            if (gate) { if (fuse) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
+            if (!fuse && !glass_branch && shade_deferred()) {
+                if (gate) k_shade_deferred<true><<<shade_grid, 256, 0, st>>>(ds, seed, d, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, ctx->L.as<f4>());
+                else k_shade_deferred<false><<<shade_grid, 256, 0, st>>>(ds, seed, d, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, ctx->L.as<f4>());
+            }
+            else if (gate) { if (fuse) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
             else { if (fuse) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
 #undef NRCU_SHADE
             CTX_LAUNCH_CHECK("k_shade");

@@ -461,6 +461,73 @@ __global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScen
     }
 }
 
+// k_shade for the common case (no glass branching, stage 1 not fused): same arithmetic, but the output-slot
+// atomic of iteration i is consumed in iteration i+1.  The continuation ray of iteration i waits in shared
+// memory (13 words per thread, [word][thread]) while the next queue entry is shaded, so the round trip of the
+// atomic (the largest stall of the plain kernel: 38 % of its samples) is hidden behind a whole iteration of work.
+template <bool GATE>
+__global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_deferred(DScene s, uint64_t seed, uint32_t d, uint32_t sample0,
+                                                                        PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
+                                                                        PathQueue qo, uint32_t* n_out_ptr, f4* L) {
+    __shared__ float park[11 * 256];
+    float* pk = park + threadIdx.x;
+    const uint32_t n = *n_in_ptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t npix = s.width * s.height;
+    f4 a = mk4(0, 0, 0, 0), b = a, c = a; float2 h = make_float2(0.f, 0.f);
+    { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = qi.a[i0]; b = qi.b[i0]; c = qi.c[i0]; h = hits[i0]; } }
+    uint32_t pend_start = 0, pend_rank = 0; bool pend_mine = false, pend_any = false;   // iteration i-1's allocation
+    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
+        const uint32_t i = base + lane;
+        bool out = false;
+        PathStep ps;
+        uint32_t slot = 0;
+        if (i < n) {
+            Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
+            vec3 thr = mk3(b.z, b.w, c.x);
+            slot = (uint32_t)f2i(c.y);
+            uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
+            ps = path_vertex(s, seed, pixel, sample, d, 0u, r, thr, h.x, __float_as_int(h.y), 0);
+            if (ps.action == PATH_TERMINATE) {
+                if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f)
+                    L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);   // one path per slot, it ends once
+            } else out = true;
+        }
+        { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = qi.a[inext]; b = qi.b[inext]; c = qi.c[inext]; h = hits[inext]; } }
+        // flush iteration i-1: its atomic was issued a whole iteration ago
+        if (pend_any) {
+            const uint32_t start = __shfl_sync(0xffffffffu, pend_start, 0);
+            if (pend_mine) {
+                const uint32_t pos = start + pend_rank;
+                qo.a[pos] = mk4(pk[0 * 256], pk[1 * 256], pk[2 * 256], pk[3 * 256]);
+                qo.b[pos] = mk4(pk[4 * 256], pk[5 * 256], pk[6 * 256], pk[7 * 256]);
+                qo.c[pos] = mk4(pk[8 * 256], pk[9 * 256], i2f(0), 0.f);
+            }
+        }
+        // park iteration i and issue its atomic
+        const uint32_t m = __ballot_sync(0xffffffffu, out);
+        pend_any = m != 0; pend_mine = out; pend_rank = __popc(m & lt);
+        if (out) {
+            pk[0 * 256] = ps.next.o.x; pk[1 * 256] = ps.next.o.y; pk[2 * 256] = ps.next.o.z; pk[3 * 256] = ps.next.d.x;
+            pk[4 * 256] = ps.next.d.y; pk[5 * 256] = ps.next.d.z; pk[6 * 256] = ps.thr.x; pk[7 * 256] = ps.thr.y;
+            pk[8 * 256] = ps.thr.z; pk[9 * 256] = i2f((int)slot);
+        }
+        if (lane == 0 && m) pend_start = atomicAdd(n_out_ptr, (uint32_t)__popc(m));
+    }
+    if (pend_any) {
+        const uint32_t start = __shfl_sync(0xffffffffu, pend_start, 0);
+        if (pend_mine) {
+            const uint32_t pos = start + pend_rank;
+            qo.a[pos] = mk4(pk[0 * 256], pk[1 * 256], pk[2 * 256], pk[3 * 256]);
+            qo.b[pos] = mk4(pk[4 * 256], pk[5 * 256], pk[6 * 256], pk[7 * 256]);
+            qo.c[pos] = mk4(pk[8 * 256], pk[9 * 256], i2f(0), 0.f);
+        }
+    }
+}
+
 // The shade kernel may have tried to allocate past the queue capacity (glass branch mode only).
 __global__ void k_clamp_count(uint32_t* n_ptr, uint32_t capacity, uint32_t* high_water) {
     uint32_t n = *n_ptr;

@@ -3,19 +3,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import load_workload, DEFAULT_WORKLOAD
 from nrenderer_b200 import Context
-fs, mode, comp, bpr = load_workload(DEFAULT_WORKLOAD, 128)
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+fs, mode, comp, bpr = load_workload(DEFAULT_WORKLOAD, spp)
 ctx = Context(0); ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 w, h = fs.width, fs.height
+ctx.upload(fs, mode)
 accum = torch.zeros(h, w, 4, device="cuda"); rgba = torch.empty(h, w, 4, device="cuda"); host = torch.empty(h, w, 4, pin_memory=True)
-def t(f, n=3):
-    f(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(n): f()
-    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
-print("upload ms", t(lambda: ctx.upload(fs, mode)))
-print("render stats=True ms", t(lambda: (accum.zero_(), ctx.render_accumulate(accum.data_ptr(), s0=0, s1=128, want_stats=True))))
-print("render stats=False ms", t(lambda: (accum.zero_(), ctx.render_accumulate(accum.data_ptr(), s0=0, s1=128, want_stats=False))))
-print("resolve+d2h ms", t(lambda: (ctx.resolve(accum.data_ptr(), rgba.data_ptr()), host.copy_(rgba, non_blocking=True))))
-def e2e():
-    ctx.upload(fs, mode); accum.zero_(); ctx.render_accumulate(accum.data_ptr(), s0=0, s1=128, want_stats=False)
-    ctx.resolve(accum.data_ptr(), rgba.data_ptr()); host.copy_(rgba, non_blocking=True); torch.cuda.synchronize()
-print("e2e ms", t(e2e))
+def sync(): torch.cuda.synchronize()
+def timed(label, f):
+    sync(); t0 = time.perf_counter(); r = f(); sync(); print(f"{label}: {(time.perf_counter()-t0)*1e3:.1f} ms", flush=True); return r
+for it in range(2):
+    timed("render stats=True ", lambda: (accum.zero_(), ctx.render_accumulate(accum.data_ptr(), s0=0, s1=spp, want_stats=True)))
+for it in range(3):
+    timed("upload            ", lambda: ctx.upload(fs, mode))
+    timed("render stats=False", lambda: (accum.zero_(), ctx.render_accumulate(accum.data_ptr(), s0=0, s1=spp, want_stats=False)))
+    timed("resolve+d2h       ", lambda: (ctx.resolve(accum.data_ptr(), rgba.data_ptr()), host.copy_(rgba, non_blocking=True)))
+for it in range(2):
+    timed("render stats=False (no upload)", lambda: (accum.zero_(), ctx.render_accumulate(accum.data_ptr(), s0=0, s1=spp, want_stats=False)))
+for it in range(2):
+    timed("render stats=True ", lambda: (accum.zero_(), ctx.render_accumulate(accum.data_ptr(), s0=0, s1=spp, want_stats=True)))
