@@ -39,9 +39,11 @@ struct PhaseTimer {
 
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
+    size_t skew = 0;   // as<T>() starts this many bytes into the allocation (see ensure_wave)
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
     cudaError_t ensure(size_t n) {
+        n += skew;
         if (n <= bytes && p) return cudaSuccess;
         release();
         if (n == 0) n = 16;
@@ -49,8 +51,11 @@ struct DevBuf {
         if (e == cudaSuccess) bytes = n; else p = nullptr;
         return e;
     }
-    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + skew); }
 };
+
+static uint32_t env_u32(const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : dflt; }
+static uint32_t wave_skew_kb() { static uint32_t v = env_u32("NRCU_WAVE_SKEW_KB", 68); return v; }
 
 // sub-allocation of the BVH build arena
 struct Carve { char* base; size_t off; void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; } };
@@ -417,6 +422,13 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
 enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
 
 static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth) {
+    // The wave buffers are power-of-two sized (32 Mi x 16 B = 512 MiB) and the kernels stream through ten of
+    // them at the same index; each buffer starts at its own skew inside its allocation so that the streams do
+    // not share an HBM channel/bank phase (k_shade has been measured anywhere between 39 and 54 ms per 128 spp on
+    // different boxes with identical code; the skew did not change that, it is kept as a cheap precaution).
+    const size_t S = (size_t)wave_skew_kb() << 10;
+    DevBuf* bufs[] = {&ctx->qa[0], &ctx->qb[0], &ctx->qc[0], &ctx->qa[1], &ctx->qb[1], &ctx->qc[1], &ctx->hits[0], &ctx->hits[1], &ctx->surv, &ctx->L};
+    for (size_t j = 0; j < sizeof(bufs) / sizeof(bufs[0]); j++) bufs[j]->skew = (j + 1) * S;
     for (int k = 0; k < 2; k++) {
         CTX_CUDA(ctx->qa[k].ensure(sizeof(f4) * (size_t)capacity));
         CTX_CUDA(ctx->qb[k].ensure(sizeof(f4) * (size_t)capacity));
@@ -445,10 +457,11 @@ static int sm_count(int device) {
 // first, batch-of-32 kernel kept for A/B measurements).
 static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
-static uint32_t env_u32(const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : dflt; }
 static bool fuse_stage1() { static uint32_t v = env_u32("NRCU_FUSE_STAGE1", 0); return v != 0; }
 static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 32) << 20; return v; }
 static bool shade_deferred() { static uint32_t v = env_u32("NRCU_SHADE_DEFERRED", 0); return v != 0; }
+static bool big_balanced() { static uint32_t v = env_u32("NRCU_BIG_BALANCED", 0); return v != 0; }
+static uint32_t big_blocks() { static uint32_t v = env_u32("NRCU_BIG_BLOCKS", 6); return v ? v : 1; }
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
@@ -536,7 +549,11 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
             float2* hi = hb[d & 1]; float2* ho = hb[(d + 1) & 1];
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
             if (d > 0 && !fuse) {   // stage 1 of this bounce (bounce 0's ran inside k_raygen)
-                if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
+                if (big_balanced()) {
+                    if (gate) k_big2<true><<<(unsigned)sms * big_blocks(), 32 * NRCU_BIG2_WARPS, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
+                    else k_big2<false><<<(unsigned)sms * big_blocks(), 32 * NRCU_BIG2_WARPS, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
+                }
+                else if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
                 else k_big<false><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
                 CTX_LAUNCH_CHECK("k_big");
             }

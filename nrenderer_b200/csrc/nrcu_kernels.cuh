@@ -169,6 +169,93 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
     }
 }
 
+// k_big with WARP-BALANCED exact tests.  In k_big the exact tests of a warp take as many rounds as its busiest
+// lane has candidates (about 5 on incoherent rays, at 2-8 active lanes: ncu, profiles/r1_*), although the warp
+// holds only ~2 candidates per ray.  Here the (ray, candidate) pairs of the 32 rays are written to a per-warp list in
+// shared memory (exclusive scan of the per-lane counts) and dealt out 32 at a time, so every round runs 32 exact
+// tests; results go back to the owning ray through a 64-bit shared-memory atomicMin on (t bits, id, list index) -
+// t > 0, so unsigned order is (t, id) order, exactly the tie rule of the per-ray loop.  The optimistic leaf gate and
+// its per-candidate fallback stay with the owner.
+#define NRCU_BIG2_WARPS 8
+template <bool GATE>
+__global__ void __launch_bounds__(32 * NRCU_BIG2_WARPS) k_big2(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
+                                                               uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+    __shared__ BigList bl;
+    __shared__ unsigned short pairs[NRCU_BIG2_WARPS][32 * NRCU_MAX_BIG];
+    __shared__ float rays[NRCU_BIG2_WARPS][6][32];
+    __shared__ unsigned long long best[NRCU_BIG2_WARPS][32];
+    bl.load(s);
+    const uint32_t n = *n_ptr;
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned short* my_pairs = pairs[wib];
+    f4 a = mk4(0, 0, 0, 0), b = a;
+    { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
+    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
+        const uint32_t i = base + lane;
+        Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
+        RayPrep rp = prep_ray(r);
+        // pass 1: candidate mask (warp-uniform loop over the list, broadcast reads)
+        uint32_t mask = 0;
+        if (i < n) {
+            for (uint32_t k = 0; k < s.n_big; k++) {
+                f4 lo = bl.bd[2 * k], hi = bl.bd[2 * k + 1];
+                float ax = fmaf(lo.x, rp.inv.x, -rp.oinv.x), bx = fmaf(hi.x, rp.inv.x, -rp.oinv.x);
+                float ay = fmaf(lo.y, rp.inv.y, -rp.oinv.y), by = fmaf(hi.y, rp.inv.y, -rp.oinv.y);
+                float az = fmaf(lo.z, rp.inv.z, -rp.oinv.z), bz = fmaf(hi.z, rp.inv.z, -rp.oinv.z);
+                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+                if (tn <= tf) mask |= 1u << k;
+            }
+        }
+        { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; } }   // prefetch
+        // deal the (ray, candidate) pairs out over the warp
+        const uint32_t cnt = __popc(mask);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (uint32_t)off) incl += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        rays[wib][0][lane] = r.o.x; rays[wib][1][lane] = r.o.y; rays[wib][2][lane] = r.o.z;
+        rays[wib][3][lane] = r.d.x; rays[wib][4][lane] = r.d.y; rays[wib][5][lane] = r.d.z;
+        best[wib][lane] = ~0ull;
+        { uint32_t pos = incl - cnt; for (uint32_t m = mask; m; m &= m - 1u) my_pairs[pos++] = (unsigned short)((lane << 5) | (uint32_t)(__ffs((int)m) - 1)); }
+        __syncwarp();
+        for (uint32_t j = lane; j < total; j += 32u) {
+            const uint32_t p = my_pairs[j], ol = p >> 5, k = p & 31u;
+            Ray pr; pr.o = mk3(rays[wib][0][ol], rays[wib][1][ol], rays[wib][2][ol]); pr.d = mk3(rays[wib][3][ol], rays[wib][4][ol], rays[wib][5][ol]);
+            float bt = NRCU_INF; int bi = -1;
+            prim_test<false>(pr, mk3(0.f), bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b, bl.m[k], bt, bi);
+            if (bi >= 0) atomicMin(&best[wib][ol], ((unsigned long long)__float_as_uint(bt) << 32) | (unsigned long long)(((uint32_t)bi << 5) | k));
+        }
+        __syncwarp();
+        bool more = false;
+        if (i < n) {
+            const unsigned long long key = best[wib][lane];
+            float best_t = NRCU_INF; int best_id = -1;
+            if (key != ~0ull) {
+                best_t = __uint_as_float((uint32_t)(key >> 32)); best_id = (int)((uint32_t)key >> 5);
+                if (GATE) {
+                    const uint32_t kb = (uint32_t)key & 31u;
+                    const vec3 ginv = gate_inverse(r);
+                    if (!bounds_intersectp_inv(bl.b[2 * kb], bl.b[2 * kb + 1], r, ginv.x, ginv.y, ginv.z)) {   // rare: gate per candidate
+                        best_t = NRCU_INF; best_id = -1;
+                        for (uint32_t m = mask; m; m &= m - 1u) {
+                            const uint32_t k = (uint32_t)(__ffs((int)m) - 1);
+                            prim_test<true>(r, ginv, bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b + 2 * k, bl.m[k], best_t, best_id);
+                        }
+                    }
+                }
+            }
+            hits[i] = make_float2(best_t, __int_as_float(best_id));
+            more = bvh_reachable(s, rp, best_t);
+        }
+        __syncwarp();   // the shared lists are rewritten by the next iteration
+        if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        append_survivors(more, i, surv, n_surv);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Closest hit, stage 2: BVH4 traversal of the surviving rays
 // ---------------------------------------------------------------------------------------------

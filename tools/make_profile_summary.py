@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Turn the ncu captures of a round into the committed summaries under profiles/.
+
+  python tools/make_profile_summary.py <round> <launch_list.csv> <hot_kernels_raw.csv>
+
+launch_list.csv      `ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,... --clock-control none --csv`
+                     of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (first N launches)
+hot_kernels_raw.csv  `ncu -i <rep> --page raw --csv` of an `ncu --set full` capture of k_big / k_trace2 / k_shade
+
+Writes profiles/<round>_launches_bench.csv (per-launch lines, compacted), profiles/<round>_hot_kernels_raw.csv (selected
+metrics), profiles/<round>_summary.json (read by bench.py for the `traffic` / `issue` fields) and profiles/<round>_summary.md.
+"""
+import collections
+import csv
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMS, SCHEDULERS = 148, 4
+KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__t_bytes.sum", "l1tex__t_bytes.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+
+
+def short(name):
+    return name.split("(")[0].replace("void ", "").replace("nrcu::", "").strip()
+
+
+def read_launch_list(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    iK, iM, iV, iID, iU = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID"), hdr.index("Metric Unit")
+    L = collections.OrderedDict()
+    for r in rows[1:]:
+        v = float(r[iV].replace(",", ""))
+        if r[iM] == "gpu__time_duration.sum":
+            v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[iU], 1e-3)   # -> us
+        if r[iM].startswith("dram__bytes"):
+            v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iU], 1.0)
+        L.setdefault(r[iID], {"kernel": short(r[iK])})[r[iM]] = v
+    return list(L.values())
+
+
+def main():
+    rnd, launch_csv, raw_csv = sys.argv[1:4]
+    out_dir = os.path.join(REPO, "profiles")
+    launches = read_launch_list(launch_csv)
+    with open(os.path.join(out_dir, f"{rnd}_launches_bench.csv"), "w") as f:
+        f.write("launch,kernel,time_us,warp_inst,threads_per_inst,issue_active_pct,dram_read_bytes,dram_write_bytes\n")
+        for i, d in enumerate(launches):
+            f.write(f"{i},{d['kernel']},{d.get('gpu__time_duration.sum', 0):.2f},{d.get('smsp__inst_executed.sum', 0):.0f},"
+                    f"{d.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0):.2f},{d.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.1f},"
+                    f"{d.get('dram__bytes_read.sum', 0):.0f},{d.get('dram__bytes_write.sum', 0):.0f}\n")
+    ours = [d for d in launches if d["kernel"].startswith("k_")]
+    render = [d for d in ours if not d["kernel"].startswith(("k_bvh", "k_build", "k_mesh"))]
+    T = sum(d["gpu__time_duration.sum"] for d in render)
+    agg = collections.OrderedDict()
+    for d in render:
+        a = agg.setdefault(d["kernel"], dict(launches=0, time_us=0.0, warp_inst=0.0, lane_inst=0.0, dram=0.0, issue_w=0.0))
+        t = d["gpu__time_duration.sum"]
+        a["launches"] += 1; a["time_us"] += t; a["warp_inst"] += d.get("smsp__inst_executed.sum", 0)
+        a["lane_inst"] += d.get("smsp__inst_executed.sum", 0) * d.get("smsp__thread_inst_executed_per_inst_executed.ratio", 0)
+        a["dram"] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+        a["issue_w"] += d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0) * t
+    kernels = {}
+    for k, a in agg.items():
+        kernels[k] = dict(launches=a["launches"], time_us=round(a["time_us"], 1), share=round(a["time_us"] / T, 4),
+                          warp_inst=a["warp_inst"], threads_per_inst=round(a["lane_inst"] / max(a["warp_inst"], 1), 2),
+                          issue_active_pct=round(a["issue_w"] / max(a["time_us"], 1e-9), 1),
+                          dram_bytes_per_launch=round(a["dram"] / a["launches"]), dram_gbs=round(a["dram"] / (a["time_us"] * 1e-6) * 1e-9, 1))
+    ch = [k for k in kernels if k.startswith(("k_raygen", "k_big", "k_trace"))]
+    ch_time = sum(kernels[k]["time_us"] for k in ch)
+    ch_inst = sum(kernels[k]["warp_inst"] for k in ch)
+    ch_dram = sum(kernels[k]["dram_bytes_per_launch"] * kernels[k]["launches"] for k in ch)
+    # raw metrics of the full captures
+    hot = []
+    rows = list(csv.reader(open(raw_csv)))
+    hdr, units = rows[0], rows[1]
+    with open(os.path.join(out_dir, f"{rnd}_hot_kernels_raw.csv"), "w") as f:
+        cols = ["Kernel Name"] + [k for k in KEEP if k in hdr]
+        w = csv.writer(f); w.writerow(cols); w.writerow([""] + [units[hdr.index(k)] for k in cols[1:]])
+        for r in rows[2:]:
+            w.writerow([short(r[hdr.index("Kernel Name")])] + [r[hdr.index(k)] for k in cols[1:]])
+            hot.append({"kernel": short(r[hdr.index("Kernel Name")]), **{k: r[hdr.index(k)] for k in cols[1:]}})
+    summary = {
+        "round": rnd,
+        "source": {"launch_list": os.path.basename(launch_csv), "captured_launches": len(launches), "full_capture": os.path.basename(raw_csv)},
+        "render_kernel_time_us": round(T, 1),
+        "kernels": kernels,
+        "closest_hit": {"kernels": ch, "share_of_render_kernels": round(ch_time / T, 4)},
+        # closest-hit DRAM traffic per captured unit of work, and the issue-slot utilisation of the closest-hit kernels:
+        # warp instructions issued / (elapsed cycles x 148 SMs x 4 schedulers), clock from the capture (1.965 GHz locked by ncu --clock-control none = application clocks)
+        "closest_hit_dram_bytes_per_step_equiv": None,
+        "issue": {"closest_hit_warp_inst_per_us": round(ch_inst / ch_time, 1),
+                  "peak_warp_inst_per_us_at_1965MHz": SMS * SCHEDULERS * 1965.0,
+                  "frac_of_issue_peak": round(ch_inst / ch_time / (SMS * SCHEDULERS * 1965.0), 4),
+                  "threads_per_inst": {k: kernels[k]["threads_per_inst"] for k in ch},
+                  "note": "from the committed ncu launch list (cold-cache, serialised launches); shares, not absolute times, carry over to the bench"},
+        "closest_hit_dram_bytes_per_launch": {k: kernels[k]["dram_bytes_per_launch"] for k in ch},
+        "hot_kernels_full_capture": hot,
+    }
+    summary["closest_hit_dram_bytes_per_step_equiv"] = round(ch_dram / max(sum(kernels[k]["launches"] for k in ch if k.startswith("k_raygen")), 1))   # per wave
+    json.dump(summary, open(os.path.join(out_dir, f"{rnd}_summary.json"), "w"), indent=1)
+    with open(os.path.join(out_dir, f"{rnd}_summary.md"), "w") as f:
+        f.write(f"# {rnd} profile summary (ncu, B200, `bench.py --steps 2 --warmup 1`, first {len(launches)} launches)\n\n")
+        f.write("| kernel | launches | time (us) | share | warp-inst | lanes/inst | issue-active % | DRAM B/launch | DRAM GB/s |\n|---|---|---|---|---|---|---|---|---|\n")
+        for k, a in sorted(kernels.items(), key=lambda kv: -kv[1]["time_us"]):
+            f.write(f"| `{k}` | {a['launches']} | {a['time_us']:.0f} | {a['share']*100:.1f} % | {a['warp_inst']/1e6:.0f} M | {a['threads_per_inst']} | {a['issue_active_pct']} | {a['dram_bytes_per_launch']/1e6:.1f} M | {a['dram_gbs']} |\n")
+        f.write(f"\nClosest-hit kernels ({', '.join(ch)}): {ch_time/T*100:.1f} % of the render-kernel time, "
+                f"{ch_inst/ch_time/(SMS*SCHEDULERS*1965.0)*100:.1f} % of the issue-slot peak (148 SMs x 4 x 1.965 GHz), "
+                f"DRAM traffic per wave {summary['closest_hit_dram_bytes_per_step_equiv']/1e9:.2f} GB.\n")
+        f.write("\nFull captures (`ncu --set full`, one launch each at bounce 1):\n\n| kernel | time us | regs | lanes/inst | issue % | warps active % | L1 hit % | L2 hit % | DRAM R MB | DRAM W MB | long-scoreboard stall |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for h in hot:
+            g = lambda k: h.get(k, "")
+            f.write(f"| `{h['kernel']}` | {g('gpu__time_duration.sum')} | {g('launch__registers_per_thread')} | {g('smsp__thread_inst_executed_per_inst_executed.ratio')} | "
+                    f"{float(g('smsp__issue_active.avg.pct_of_peak_sustained_active') or 0):.1f} | {float(g('sm__warps_active.avg.pct_of_peak_sustained_active') or 0):.1f} | "
+                    f"{float(g('l1tex__t_sector_hit_rate.pct') or 0):.1f} | {float(g('lts__t_sector_hit_rate.pct') or 0):.1f} | {g('dram__bytes_read.sum')} | {g('dram__bytes_write.sum')} | "
+                    f"{float(g('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio') or 0):.2f} |\n")
+    print(open(os.path.join(out_dir, f"{rnd}_summary.md")).read())
+
+
+if __name__ == "__main__":
+    main()
