@@ -20,6 +20,9 @@
  *                       <- the same render loop split at the "sum over samples" / "÷spp, sqrt gamma"
  *                          boundary (AccPathTracer.cpp:22-34) so that sample slices rendered on
  *                          several GPUs can be reduced in linear space before the gamma.
+ *   nrcu_render_multi   <- the reference's row-striped std::thread pool (AccPathTracer.cpp:63-70: 16 threads,
+ *                          `for i = off; i < h; i += step`) at box scale: one host thread per GPU, sample slices
+ *                          instead of row stripes, partial frames combined in linear space before the gamma
  *   nrcu_trace_batch    <- closestHitObject (SimplePathTracer.cpp:104-129 brute force;
  *                          AccPathTracer.cpp:87-99 -> BVHTree::Intersect BVH.hpp:93-164)
  *
@@ -234,6 +237,14 @@ int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out
  * the caller owns (e.g. a torch tensor) and may reduce across GPUs. Asynchronous on the
  * context's stream unless stats != NULL. */
 int nrcu_render_accumulate(nrcu_ctx* ctx, const nrcu_render_params* params, float* d_accum, nrcu_stats* stats);
+
+/* Whole frame on SEVERAL devices of one box (sample slices): ctxs[g] (one context per device, the
+ * same scene uploaded to each in the same mode) renders samples [g*spp/n, (g+1)*spp/n) of every pixel on its own
+ * host thread; ctxs[0] then sums the partial LINEAR frames straight out of its peers' HBM over NVLink (peer access;
+ * staged copies when peer access is unavailable) inside the kernel that resolves (/ n, sqrt gamma), and the frame
+ * is copied to HOST memory `rgba_out`.  With n_ctx == 1 this is nrcu_render.  stats (may be NULL): sums over the
+ * devices; ms_* = maximum over the devices. */
+int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params* params, float* rgba_out, nrcu_stats* stats);
 
 /* d_rgba[p] = (sqrt(d_accum[p].rgb / d_accum[p].a), 1); both DEVICE pointers; may alias. */
 int nrcu_resolve(nrcu_ctx* ctx, const float* d_accum, float* d_rgba);

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG, "libnrcuda.so")
 ABI_SYMBOLS = [
     "nrcu_abi_version", "nrcu_device_count", "nrcu_create", "nrcu_destroy", "nrcu_last_error", "nrcu_upload_scene",
     "nrcu_primitive_count", "nrcu_download_primitives", "nrcu_render", "nrcu_render_accumulate", "nrcu_resolve",
-    "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
+    "nrcu_render_multi", "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
 ]
 
 
@@ -65,6 +65,7 @@ def load_library() -> C.CDLL:
     L.nrcu_download_primitives.argtypes = [vp, vp, vp, vp]
     L.nrcu_render.argtypes = [vp, vp, vp, vp]
     L.nrcu_render_accumulate.argtypes = [vp, vp, vp, vp]
+    L.nrcu_render_multi.argtypes = [vp, i32, vp, vp, vp]
     L.nrcu_resolve.argtypes = [vp, vp, vp]
     L.nrcu_trace_batch.argtypes = [vp, vp, u32, vp, vp]
     L.nrcu_set_stream.argtypes = [vp, vp]
@@ -167,3 +168,14 @@ class Context:
         pid, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
         self._check(self._lib.nrcu_trace_batch(self._h, rays.ctypes.data, n, pid.ctypes.data, t.ctypes.data), "nrcu_trace_batch")
         return pid, t
+
+
+def render_multi(contexts, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None):
+    """One frame on several devices of the box (nrcu_render_multi): contexts[g] must hold the same scene."""
+    c0 = contexts[0]
+    if out is None:
+        out = np.empty((c0.height, c0.width, 4), np.float32)
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    p, st = Context._params(seed, 0, 0, glass_mode, samples_per_wave), NrcuStats()
+    c0._check(c0._lib.nrcu_render_multi(arr, len(contexts), C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render_multi")
+    return out, st.as_dict()

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nrcu.h"
@@ -663,6 +664,81 @@ int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out
     if (stats) stats->kernel_launches++;
     CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
     CTX_CUDA(cudaStreamSynchronize(st));
+    return NRCU_OK;
+}
+
+int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params* params, float* rgba_out, nrcu_stats* stats) {
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return NRCU_ERR_INVALID;
+    nrcu_ctx* ctx = ctxs[0];   // root: errors are reported here
+    if (n_ctx == 1 || ctx->mode == NRCU_MODE_RAYCAST) return nrcu_render(ctx, params, rgba_out, stats);
+    if (n_ctx > NRCU_MAX_DEVICES) { ctx->error = "nrcu_render_multi: too many contexts"; return NRCU_ERR_INVALID; }
+    if (!rgba_out) { ctx->error = "rgba_out is null"; return NRCU_ERR_INVALID; }
+    for (int g = 0; g < n_ctx; g++) {
+        nrcu_ctx* c = ctxs[g];
+        if (!c || !c->have_scene) { ctx->error = "nrcu_render_multi: a context has no scene"; return NRCU_ERR_STATE; }
+        if (c->mode != ctx->mode || c->spp != ctx->spp || c->ds.width != ctx->ds.width || c->ds.height != ctx->ds.height || c->ds.n_prims != ctx->ds.n_prims) {
+            ctx->error = "nrcu_render_multi: the contexts hold different scenes"; return NRCU_ERR_INVALID;
+        }
+        for (int h = 0; h < g; h++) if (ctxs[h]->device == c->device) { ctx->error = "nrcu_render_multi: two contexts on one device"; return NRCU_ERR_INVALID; }
+    }
+    const uint32_t npix = ctx->ds.width * ctx->ds.height, spp = ctx->spp;
+    std::vector<int> rc(n_ctx, NRCU_OK);
+    std::vector<nrcu_stats> st(n_ctx);
+    std::vector<std::thread> pool;
+    auto wall0 = std::chrono::steady_clock::now();
+    for (int g = 0; g < n_ctx; g++) {
+        pool.emplace_back([&, g]() {
+            nrcu_ctx* c = ctxs[g];
+            std::memset(&st[g], 0, sizeof(nrcu_stats));
+            if (cudaSetDevice(c->device) != cudaSuccess) { c->error = "cudaSetDevice failed"; rc[g] = NRCU_ERR_CUDA; return; }
+            if (c->accum_own.ensure(sizeof(f4) * (size_t)npix) != cudaSuccess ||
+                cudaMemsetAsync(c->accum_own.p, 0, sizeof(f4) * (size_t)npix, c->stream) != cudaSuccess) { c->error = "accum allocation failed"; rc[g] = NRCU_ERR_CUDA; return; }
+            nrcu_render_params p{};
+            if (params) p = *params;
+            p.sample_begin = (uint32_t)((uint64_t)g * spp / n_ctx); p.sample_end = (uint32_t)((uint64_t)(g + 1) * spp / n_ctx);
+            if (p.sample_end > p.sample_begin) rc[g] = render_pt(c, &p, c->accum_own.as<f4>(), &st[g]);
+            if (rc[g] == NRCU_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) { c->error = "synchronize failed"; rc[g] = NRCU_ERR_CUDA; }
+        });
+    }
+    for (auto& t : pool) t.join();
+    for (int g = 0; g < n_ctx; g++) if (rc[g] != NRCU_OK) { if (g) ctx->error = "device " + std::to_string(ctxs[g]->device) + ": " + ctxs[g]->error; return rc[g]; }
+    // ---- reduce + resolve on the root, reading the peers' partial frames in place ------------------------------
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s0 = ctx->stream;
+    CTX_CUDA(ctx->rgba_dev.ensure(sizeof(f4) * (size_t)npix));
+    PartialFrames pf{}; pf.n = n_ctx; pf.part[0] = ctx->accum_own.as<f4>();
+    std::vector<DevBuf> staged(n_ctx);
+    for (int g = 1; g < n_ctx; g++) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[g]->device);
+        if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[g]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            can = e == cudaSuccess;
+            if (!can) cudaGetLastError();
+        }
+        if (can) pf.part[g] = ctxs[g]->accum_own.as<f4>();
+        else {   // no peer mapping: stage the partial frame through a copy
+            CTX_CUDA(staged[g].ensure(sizeof(f4) * (size_t)npix));
+            CTX_CUDA(cudaMemcpyPeerAsync(staged[g].p, ctx->device, ctxs[g]->accum_own.p, ctxs[g]->device, sizeof(f4) * (size_t)npix, s0));
+            pf.part[g] = staged[g].as<f4>();
+        }
+    }
+    k_resolve_multi<<<grid_for(npix, 256), 256, 0, s0>>>(pf, nullptr, ctx->rgba_dev.as<f4>(), npix);
+    CTX_LAUNCH_CHECK("k_resolve_multi");
+    CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, s0));
+    CTX_CUDA(cudaStreamSynchronize(s0));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        for (int g = 0; g < n_ctx; g++) {
+            stats->paths += st[g].paths; stats->rays += st[g].rays; stats->kernel_launches += st[g].kernel_launches;
+            stats->ms_trace = std::max(stats->ms_trace, st[g].ms_trace); stats->ms_shade = std::max(stats->ms_shade, st[g].ms_shade);
+            stats->max_queue = std::max(stats->max_queue, st[g].max_queue);
+        }
+        stats->kernel_launches += 1;
+        stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+        stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ctx->ds.n_prims;
+    }
     return NRCU_OK;
 }
 

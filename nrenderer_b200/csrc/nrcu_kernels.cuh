@@ -644,6 +644,19 @@ __global__ void k_resolve(const f4* accum, f4* rgba, uint32_t npix) {
     rgba[p] = mk4(sqrtf(a.x / a.w), sqrtf(a.y / a.w), sqrtf(a.z / a.w), 1.f);
 }
 
+// Multi-device resolve: sum the partial linear frames (pointers into this device's and its peers' memory - peer
+// loads travel over NVLink) and apply the reference's epilogue in the same pass.
+#define NRCU_MAX_DEVICES 16
+struct PartialFrames { const f4* part[NRCU_MAX_DEVICES]; int n; };
+__global__ void k_resolve_multi(PartialFrames pf, f4* accum_out, f4* rgba, uint32_t npix) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    f4 a = pf.part[0][p];
+    for (int g = 1; g < pf.n; g++) { f4 v = pf.part[g][p]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    if (accum_out) accum_out[p] = a;
+    rgba[p] = mk4(sqrtf(a.x / a.w), sqrtf(a.y / a.w), sqrtf(a.z / a.w), 1.f);
+}
+
 __global__ void k_pack_rays(const float* rays6, uint32_t n, PathQueue q) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

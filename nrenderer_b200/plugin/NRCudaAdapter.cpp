@@ -11,6 +11,7 @@
 // place); the frame is published through getServer().screen.set exactly like ray_cast/src/Adapter.cpp:15-19.
 // It is compiled by g++ against the reference's headers and talks to the kernels only through the
 // C ABI in include/nrcu.h.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <mutex>
@@ -35,8 +36,9 @@ namespace NRCuda
     // (the GUI runs render() on a fresh detached thread per click, ComponentManager.hpp:41-64).
     struct SharedContext {
         std::mutex mtx;
-        nrcu_ctx* ctx = nullptr;
-        ~SharedContext() { if (ctx) nrcu_destroy(ctx); }
+        nrcu_ctx* ctx = nullptr;               // device NRCU_DEVICE (default 0)
+        std::vector<nrcu_ctx*> extra;          // further devices when NRCU_DEVICES > 1 (sample slices, nrcu_render_multi)
+        ~SharedContext() { for (auto* c : extra) nrcu_destroy(c); if (ctx) nrcu_destroy(ctx); }
     };
     static SharedContext& shared() { static SharedContext s; return s; }
 
@@ -74,12 +76,33 @@ namespace NRCuda
                     publishBlack(w, h);
                     return;
                 }
+                // NRCU_DEVICES=N (or "all"): split the samples of the frame over N GPUs of this box
+                std::vector<nrcu_ctx*> devs{sh.ctx};
+                if (const char* e = std::getenv("NRCU_DEVICES")) {
+                    int want = std::string(e) == "all" ? nrcu_device_count() : std::atoi(e);
+                    want = std::min(want, nrcu_device_count());
+                    for (int d = 0, have = 1; d < nrcu_device_count() && have < want; d++) {
+                        bool used = false;   // the primary context may sit on any device
+                        if (const char* pd = std::getenv("NRCU_DEVICE")) used = std::atoi(pd) == d; else used = d == 0;
+                        if (used) continue;
+                        size_t slot = (size_t)have - 1;
+                        if (sh.extra.size() <= slot) {
+                            nrcu_ctx* c = nullptr;
+                            if (nrcu_create(d, &c) != NRCU_OK) { logger.warning(std::string("NRCuda: device skipped: ") + nrcu_last_error(nullptr)); continue; }
+                            sh.extra.push_back(c);
+                        }
+                        if (nrcu_upload_scene(sh.extra[slot], &view, NRCU_PLUGIN_MODE) != NRCU_OK) {
+                            logger.warning(std::string("NRCuda: device skipped: ") + nrcu_last_error(sh.extra[slot])); continue;
+                        }
+                        devs.push_back(sh.extra[slot]); have++;
+                    }
+                }
                 nrcu_render_params params{};
                 if (const char* e = std::getenv("NRCU_SEED")) params.seed = std::strtoull(e, nullptr, 10);
                 if (const char* e = std::getenv("NRCU_GLASS_BRANCH")) params.glass_mode = std::atoi(e) ? NRCU_GLASS_BRANCH : NRCU_GLASS_STOCHASTIC;
                 nrcu_stats st{};
                 RGBA* pixels = new RGBA[(size_t)w * h];   // plugin owns the buffer, Screen::set copies it (RayCastRenderer.cpp:7-10)
-                int rc = nrcu_render(sh.ctx, &params, reinterpret_cast<float*>(pixels), &st);
+                int rc = nrcu_render_multi(devs.data(), (int)devs.size(), &params, reinterpret_cast<float*>(pixels), &st);
                 if (rc != NRCU_OK) {
                     logger.error(std::string("NRCuda: ") + nrcu_last_error(sh.ctx));
                     delete[] pixels;
@@ -91,8 +114,8 @@ namespace NRCuda
                 double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
                 char buf[320];
                 std::snprintf(buf, sizeof(buf),
-                              "Done... %.3f s (GPU %.1f ms, setup %.2f ms): %.2f Mpath-samples/s, %.1f Mrays/s, %u primitives, %u BVH4 nodes",
-                              wall, st.ms_total, st.ms_setup, st.paths / wall * 1e-6, st.rays / (st.ms_total * 1e-3) * 1e-6,
+                              "Done... %.3f s on %d GPU(s) (GPU %.1f ms, setup %.2f ms): %.2f Mpath-samples/s, %.1f Mrays/s, %u primitives, %u BVH4 nodes",
+                              wall, (int)devs.size(), st.ms_total, st.ms_setup, st.paths / wall * 1e-6, st.rays / (st.ms_total * 1e-3) * 1e-6,
                               st.n_primitives, st.bvh_nodes);
                 logger.log(buf);
             } catch (const std::exception& ex) {

@@ -274,3 +274,42 @@ def test_empty_scene_renders_black(ctx):
     ctx.upload(fs, 0)
     img, _ = ctx.render()
     assert (img[..., :3] == 0).all()
+
+
+@pytest.mark.gpu
+def test_multi_device_frame_equals_single_device_frame(ctx):
+    """nrcu_render_multi: sample slices on two GPUs, peer-memory reduce + resolve == the one-GPU frame (fp32 summation order only)."""
+    import nrenderer_b200 as nr
+    if nr.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fs = load_scene("bunny200_cornel", width=96, height=64, samples_per_pixel=12, depth=8)
+    ctx.upload(fs, nr.MODE_ACC)
+    one, st1 = ctx.render(seed=5)
+    other = nr.Context(1)
+    try:
+        other.upload(fs, nr.MODE_ACC)
+        two, st2 = nr.render_multi([ctx, other], seed=5)
+    finally:
+        other.close()
+    assert st2["paths"] == st1["paths"] and st2["rays"] == st1["rays"]      # the union of the slices is the same set of paths
+    np.testing.assert_allclose(two, one, rtol=3e-6, atol=1e-6)
+    assert np.all(two[..., 3] == 1.0)
+
+
+@pytest.mark.gpu
+def test_multi_device_rejects_mismatched_contexts(ctx):
+    import nrenderer_b200 as nr
+    if nr.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fs = load_scene("bunny200_cornel", width=32, height=32, samples_per_pixel=2, depth=4)
+    ctx.upload(fs, nr.MODE_ACC)
+    other = nr.Context(1)
+    try:
+        with pytest.raises(nr.NrcuError):
+            nr.render_multi([ctx, other])          # no scene on the second device
+        fs2 = load_scene("bunny200_cornel", width=16, height=16, samples_per_pixel=2, depth=4)
+        other.upload(fs2, nr.MODE_ACC)
+        with pytest.raises(nr.NrcuError):
+            nr.render_multi([ctx, other])          # different resolution
+    finally:
+        other.close()
