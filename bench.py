@@ -235,8 +235,13 @@ def cuda_arm(args):
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h2d, d2h = scene_bytes(fs), w * h * 16
 
+    host_np = host_rgba.numpy()
+
     def e2e_step():
         ctx.upload(fs, mode)                                    # H2D of the scene + device-side flattening + BVH build
+        if world == 1:                                          # exactly the plugin adapter's call sequence (NRCudaAdapter.cpp):
+            ctx.render(seed=args.seed, out=host_np)             # nrcu_upload_scene + nrcu_render into HOST memory (pinned)
+            return
         multigpu.render_frame(
             lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=False),
             resolve, accum, rgba, spp, rank, world)
@@ -260,6 +265,8 @@ def cuda_arm(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = (w * h * spp * e2e_steps) / te.item() * 1e-6
 
+    waves = -(-spp // max(1, (32 << 20) // (w * h))) if world == 1 else None
+    closest_hit_launches = args.steps * waves * (1 + (fs.depth - 1) + fs.depth) if waves else 0
     if rank == 0:
         peak, peak_src = peaks()
         achieved = rays * bytes_per_ray / (ms_trace * 1e-3) * 1e-9 if ms_trace > 0 else None
@@ -276,7 +283,8 @@ def cuda_arm(args):
             "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "clocks": e2e_clocks},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                         "traffic": profile_summary().get("closest_hit_dram_bytes_per_step_equiv"),
+                         "traffic": profile_summary().get("closest_hit", {}).get("dram_bytes_per_launch"),
+                         "algorithmic_bytes_per_launch": (rays * bytes_per_ray / max(closest_hit_launches, 1)) if closest_hit_launches else None,
                          "kernel": "closest hit = k_raygen (camera rays + fused stage 1) + k_big + k_trace2", "algorithmic_bytes_per_ray": bytes_per_ray,
                          "peak_source": peak_src, "share_of_step": ms_trace / ms if ms else None,
                          "note": "algorithmic bytes are those of the REFERENCE's traversal (SURVEY 8d); the scene is L1/L2 resident, so the "

@@ -107,6 +107,8 @@ def main():
         "closest_hit_dram_bytes_per_launch": {k: kernels[k]["dram_bytes_per_launch"] for k in ch},
         "hot_kernels_full_capture": hot,
     }
+    summary["closest_hit"]["dram_bytes_per_launch"] = round(ch_dram / max(sum(kernels[k]["launches"] for k in ch), 1))
+    summary["closest_hit"]["launches_per_wave"] = round(sum(kernels[k]["launches"] for k in ch) / max(sum(kernels[k]["launches"] for k in ch if k.startswith("k_raygen")), 1), 2)
     summary["closest_hit_dram_bytes_per_step_equiv"] = round(ch_dram / max(sum(kernels[k]["launches"] for k in ch if k.startswith("k_raygen")), 1))   # per wave
     json.dump(summary, open(os.path.join(out_dir, f"{rnd}_summary.json"), "w"), indent=1)
     with open(os.path.join(out_dir, f"{rnd}_summary.md"), "w") as f:
@@ -118,11 +120,18 @@ def main():
                 f"{ch_inst/ch_time/(SMS*SCHEDULERS*1965.0)*100:.1f} % of the issue-slot peak (148 SMs x 4 x 1.965 GHz), "
                 f"DRAM traffic per wave {summary['closest_hit_dram_bytes_per_step_equiv']/1e9:.2f} GB.\n")
         f.write("\nFull captures (`ncu --set full`, one launch each at bounce 1):\n\n| kernel | time us | regs | lanes/inst | issue % | warps active % | L1 hit % | L2 hit % | DRAM R MB | DRAM W MB | long-scoreboard stall |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+        U = {k: units[hdr.index(k)] for k in KEEP if k in hdr}
+        def mb(h, k):
+            v = float(h.get(k, 0) or 0)
+            return v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(U.get(k, "byte"), 1e-6)
+        def us(h, k):
+            v = float(h.get(k, 0) or 0)
+            return v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(U.get(k, "us"), 1.0)
         for h in hot:
             g = lambda k: h.get(k, "")
-            f.write(f"| `{h['kernel']}` | {g('gpu__time_duration.sum')} | {g('launch__registers_per_thread')} | {g('smsp__thread_inst_executed_per_inst_executed.ratio')} | "
+            f.write(f"| `{h['kernel']}` | {us(h, 'gpu__time_duration.sum'):.1f} | {g('launch__registers_per_thread')} | {g('smsp__thread_inst_executed_per_inst_executed.ratio')} | "
                     f"{float(g('smsp__issue_active.avg.pct_of_peak_sustained_active') or 0):.1f} | {float(g('sm__warps_active.avg.pct_of_peak_sustained_active') or 0):.1f} | "
-                    f"{float(g('l1tex__t_sector_hit_rate.pct') or 0):.1f} | {float(g('lts__t_sector_hit_rate.pct') or 0):.1f} | {g('dram__bytes_read.sum')} | {g('dram__bytes_write.sum')} | "
+                    f"{float(g('l1tex__t_sector_hit_rate.pct') or 0):.1f} | {float(g('lts__t_sector_hit_rate.pct') or 0):.1f} | {mb(h, 'dram__bytes_read.sum'):.1f} | {mb(h, 'dram__bytes_write.sum'):.1f} | "
                     f"{float(g('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio') or 0):.2f} |\n")
     print(open(os.path.join(out_dir, f"{rnd}_summary.md")).read())
 
