@@ -231,6 +231,39 @@ def test_sample_slices_add_up_and_waves_do_not_matter(ctx):
     assert abs(st2["rays"] - orays) <= 2e-3 * orays                               # 16:9 view: many primary rays miss the box
 
 
+# BASELINE.json configs 2-5 at their FULL resolution (few spp): the whole frame is rendered on the GPU, a random
+# subset of pixels is checked against the oracle with the same RNG, and the frame-level invariants are checked everywhere.
+FULL_SIZE_CASES = [
+    ("cfg2", "path_tracing_cornel", 1, 1024, 1024, 1.0, None),
+    ("cfg3", "bunny5k_cornel", 2, 1920, 1080, 16 / 9, None),
+    ("cfg4-i", "pt_glass", 2, 1920, 1080, 16 / 9, None),
+    ("cfg4-ii", "pt_glass", 2, 1920, 1080, 16 / 9, glassify),
+    ("cfg4-iii", "pt_glass_conductors", 2, 1920, 1080, 16 / 9, microfacet),
+    ("cfg5", "env_map_spheres", 2, 3840, 2160, 16 / 9, env_texture),
+]
+
+
+@pytest.mark.parametrize("cfg,name,mode,w,h,aspect,edit", FULL_SIZE_CASES)
+def test_baseline_configs_at_full_resolution(ctx, cfg, name, mode, w, h, aspect, edit):
+    spp, depth = 4, 20
+    fs = load_scene(name, width=w, height=h, samples_per_pixel=spp, depth=depth, cam_aspect=aspect)
+    if edit:
+        edit(fs)
+    ctx.upload(fs, mode)
+    acc, st = accum_device(ctx, seed=21)
+    again, _ = accum_device(ctx, seed=21)
+    assert np.array_equal(acc.view(np.uint32), again.view(np.uint32))            # deterministic at full size
+    assert st["paths"] == w * h * spp and np.all(acc[..., 3] == spp)
+    assert np.isfinite(acc[..., :3]).all() and (acc[..., :3] >= 0).all()
+    px = np.random.default_rng(4).choice(w * h, 1500, replace=False).astype(np.uint32)
+    oacc, _ = oracle(fs, mode).render_pt_accum(seed=21, pixels=px)
+    a, b = acc.reshape(-1, 4)[px, :3], oacc[:, :3]
+    rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+    close = (rel < 1e-3).all(-1)
+    print(f"{cfg}: {w}x{h}, {close.mean() * 100:.2f}% of {len(px)} sampled pixels within 1e-3 of the oracle, rays/path {st['rays'] / st['paths']:.3f}")
+    assert close.mean() >= 0.99
+
+
 def test_full_frame_resolve_and_host_copy(ctx):
     fs = load_scene("path_tracing_cornel", width=256, height=256, samples_per_pixel=64, depth=4)
     ctx.upload(fs, 1)
