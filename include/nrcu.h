@@ -238,6 +238,15 @@ int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out
  * context's stream unless stats != NULL. */
 int nrcu_render_accumulate(nrcu_ctx* ctx, const nrcu_render_params* params, float* d_accum, nrcu_stats* stats);
 
+/* Progressive form of nrcu_render (the GUI re-uploads the frame whenever Screen::isUpdated(),
+ * app/src/ui/views/ScreenView.cpp:168-173, so a component may publish intermediate frames): after every
+ * `samples_per_update` samples (0 = one wave) the frame resolved from the samples so far is copied to `rgba_out`
+ * and `on_update(user, rgba_out, samples_done, samples_total)` is called on the calling thread; a non-zero return
+ * stops the render early (the frame then holds samples_done samples).  The last update is the final frame. */
+typedef int (*nrcu_update_fn)(void* user, const float* rgba, uint32_t samples_done, uint32_t samples_total);
+int nrcu_render_progressive(nrcu_ctx* ctx, const nrcu_render_params* params, uint32_t samples_per_update,
+                            float* rgba_out, nrcu_update_fn on_update, void* user, nrcu_stats* stats);
+
 /* Whole frame on SEVERAL devices of one box (sample slices): ctxs[g] (one context per device, the
  * same scene uploaded to each in the same mode) renders samples [g*spp/n, (g+1)*spp/n) of every pixel on its own
  * host thread; ctxs[0] then sums the partial LINEAR frames straight out of its peers' HBM over NVLink (peer access;

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG, "libnrcuda.so")
 ABI_SYMBOLS = [
     "nrcu_abi_version", "nrcu_device_count", "nrcu_create", "nrcu_destroy", "nrcu_last_error", "nrcu_upload_scene",
     "nrcu_primitive_count", "nrcu_download_primitives", "nrcu_render", "nrcu_render_accumulate", "nrcu_resolve",
-    "nrcu_render_multi", "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
+    "nrcu_render_multi", "nrcu_render_progressive", "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
 ]
 
 
@@ -41,6 +41,7 @@ class NrcuStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+UPDATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 _LIB = None
 
 
@@ -66,6 +67,7 @@ def load_library() -> C.CDLL:
     L.nrcu_render.argtypes = [vp, vp, vp, vp]
     L.nrcu_render_accumulate.argtypes = [vp, vp, vp, vp]
     L.nrcu_render_multi.argtypes = [vp, i32, vp, vp, vp]
+    L.nrcu_render_progressive.argtypes = [vp, vp, u32, vp, UPDATE_FN, vp, vp]
     L.nrcu_resolve.argtypes = [vp, vp, vp]
     L.nrcu_trace_batch.argtypes = [vp, vp, u32, vp, vp]
     L.nrcu_set_stream.argtypes = [vp, vp]
@@ -150,6 +152,16 @@ class Context:
         assert out.dtype == np.float32 and out.size == self.width * self.height * 4 and out.flags.c_contiguous
         p, st = self._params(seed, 0, 0, glass_mode, samples_per_wave), NrcuStats()
         self._check(self._lib.nrcu_render(self._h, C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render")
+        return out, st.as_dict()
+
+    def render_progressive(self, on_update, samples_per_update=0, seed=0, glass_mode=0, out: np.ndarray | None = None):
+        """nrcu_render_progressive: on_update(frame[h,w,4], samples_done, samples_total) -> truthy to stop early."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        p, st = self._params(seed, 0, 0, glass_mode, 0), NrcuStats()
+        cb = UPDATE_FN(lambda user, rgba, done, total: int(bool(on_update(out, done, total))))
+        self._check(self._lib.nrcu_render_progressive(self._h, C.addressof(p), samples_per_update, out.ctypes.data, cb, None, C.addressof(st)),
+                    "nrcu_render_progressive")
         return out, st.as_dict()
 
     def render_accumulate(self, d_accum_ptr: int, s0=0, s1=0, seed=0, glass_mode=0, samples_per_wave=0, want_stats=True):

@@ -667,6 +667,45 @@ int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out
     return NRCU_OK;
 }
 
+int nrcu_render_progressive(nrcu_ctx* ctx, const nrcu_render_params* params, uint32_t samples_per_update,
+                            float* rgba_out, nrcu_update_fn on_update, void* user, nrcu_stats* stats) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) { ctx->error = "nrcu_render_progressive: no scene uploaded"; return NRCU_ERR_STATE; }
+    if (!rgba_out) { ctx->error = "rgba_out is null"; return NRCU_ERR_INVALID; }
+    if (ctx->mode == NRCU_MODE_RAYCAST || ctx->spp == 0) {   // one deterministic pass: a single update
+        int rc = nrcu_render(ctx, params, rgba_out, stats);
+        if (rc == NRCU_OK && on_update) on_update(user, rgba_out, 1, 1);
+        return rc;
+    }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t npix = ctx->ds.width * ctx->ds.height, spp = ctx->spp;
+    cudaStream_t st = ctx->stream;
+    CTX_CUDA(ctx->rgba_dev.ensure(sizeof(f4) * (size_t)npix));
+    CTX_CUDA(ctx->accum_own.ensure(sizeof(f4) * (size_t)npix));
+    CTX_CUDA(cudaMemsetAsync(ctx->accum_own.p, 0, sizeof(f4) * (size_t)npix, st));
+    uint32_t step = samples_per_update ? samples_per_update : std::max<uint32_t>(1, wave_slots_target() / npix);
+    nrcu_stats total{}; std::memset(&total, 0, sizeof(total));
+    for (uint32_t s0 = 0; s0 < spp; s0 += step) {
+        nrcu_render_params p{};
+        if (params) p = *params;
+        p.sample_begin = s0; p.sample_end = std::min(spp, s0 + step);
+        nrcu_stats part{};
+        int rc = render_pt(ctx, &p, ctx->accum_own.as<f4>(), &part);
+        if (rc != NRCU_OK) return rc;
+        k_resolve<<<grid_for(npix, 256), 256, 0, st>>>(ctx->accum_own.as<f4>(), ctx->rgba_dev.as<f4>(), npix);
+        CTX_LAUNCH_CHECK("k_resolve");
+        CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+        CTX_CUDA(cudaStreamSynchronize(st));
+        total.paths += part.paths; total.rays += part.rays; total.kernel_launches += part.kernel_launches + 1;
+        total.ms_total += part.ms_total; total.ms_trace += part.ms_trace; total.ms_shade += part.ms_shade;
+        total.max_queue = std::max(total.max_queue, part.max_queue);
+        total.ms_setup = part.ms_setup; total.bvh_nodes = part.bvh_nodes; total.n_primitives = part.n_primitives;
+        if (on_update && on_update(user, rgba_out, p.sample_end, spp) != 0) break;
+    }
+    if (stats) *stats = total;
+    return NRCU_OK;
+}
+
 int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params* params, float* rgba_out, nrcu_stats* stats) {
     if (!ctxs || n_ctx < 1 || !ctxs[0]) return NRCU_ERR_INVALID;
     nrcu_ctx* ctx = ctxs[0];   // root: errors are reported here

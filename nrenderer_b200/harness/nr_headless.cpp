@@ -50,7 +50,7 @@ static void usage() {
         "         [--mesh-material K] [--texture IMG] [--env-map TEXIDX]\n"
         "         [--w W --h H --depth D --spp S --aspect A --ambient R G B]\n"
         "         [--dump-flat OUT.nrsc]\n"
-        "         [--plugin LIB.so]... [--component NAME --out FRAME.f32] [--repeat N] [--list]\n");
+        "         [--plugin LIB.so]... [--component NAME --out FRAME.f32|.ppm|.pfm] [--repeat N] [--list]\n");
 }
 
 int main(int argc, char** argv) {
@@ -168,8 +168,33 @@ int main(int argc, char** argv) {
     auto& screen = getServer().screen;
     unsigned sw = screen.getWidth(), sh = screen.getHeight();
     if (!out.empty()) {
+        // The reference has no image export at all.  By extension:
+        //   .ppm  8-bit RGB of the published frame (already sqrt-gamma'd and clamped by Screen::set), row 0 = top
+        //   .pfm  RGB fp32, little endian, rows bottom-to-top as the format requires
+        //   else  raw RGBA fp32 exactly as getServer().screen holds it (what the parity tests read)
+        const RGBA* px = screen.getPixels();
+        auto ends_with = [&](const char* ext) { std::string e(ext); return out.size() >= e.size() && out.compare(out.size() - e.size(), e.size(), e) == 0; };
         std::ofstream o(out, std::ios::binary);
-        o.write((const char*)screen.getPixels(), sizeof(float) * 4 * (size_t)sw * sh);
+        if (ends_with(".ppm")) {
+            o << "P6\n" << sw << " " << sh << "\n255\n";
+            std::vector<unsigned char> row(3 * (size_t)sw);
+            for (unsigned y = 0; y < sh; y++) {
+                for (unsigned x = 0; x < sw; x++) for (int c = 0; c < 3; c++) {
+                    float v = px[(size_t)y * sw + x][c]; v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+                    row[3 * x + c] = (unsigned char)(v * 255.f + 0.5f);
+                }
+                o.write((const char*)row.data(), row.size());
+            }
+        } else if (ends_with(".pfm")) {
+            o << "PF\n" << sw << " " << sh << "\n-1.0\n";
+            std::vector<float> row(3 * (size_t)sw);
+            for (unsigned y = sh; y-- > 0;) {
+                for (unsigned x = 0; x < sw; x++) for (int c = 0; c < 3; c++) row[3 * x + c] = px[(size_t)y * sw + x][c];
+                o.write((const char*)row.data(), row.size() * sizeof(float));
+            }
+        } else {
+            o.write((const char*)px, sizeof(float) * 4 * (size_t)sw * sh);
+        }
     }
     std::string last_log;
     {

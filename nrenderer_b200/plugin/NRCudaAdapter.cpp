@@ -102,7 +102,18 @@ namespace NRCuda
                 if (const char* e = std::getenv("NRCU_GLASS_BRANCH")) params.glass_mode = std::atoi(e) ? NRCU_GLASS_BRANCH : NRCU_GLASS_STOCHASTIC;
                 nrcu_stats st{};
                 RGBA* pixels = new RGBA[(size_t)w * h];   // plugin owns the buffer, Screen::set copies it (RayCastRenderer.cpp:7-10)
-                int rc = nrcu_render_multi(devs.data(), (int)devs.size(), &params, reinterpret_cast<float*>(pixels), &st);
+                int rc;
+                const char* prog = std::getenv("NRCU_PROGRESSIVE");
+                if (prog && std::atoi(prog) > 0 && devs.size() == 1) {
+                    // publish intermediate frames: the GUI re-uploads whenever Screen::isUpdated() (ScreenView.cpp:168-173)
+                    struct Pub { unsigned w, h; } pub{w, h};
+                    rc = nrcu_render_progressive(sh.ctx, &params, (uint32_t)std::atoi(prog), reinterpret_cast<float*>(pixels),
+                                                 [](void* u, const float* rgba, uint32_t, uint32_t) -> int {
+                                                     auto* p = static_cast<Pub*>(u);
+                                                     getServer().screen.set(reinterpret_cast<RGBA*>(const_cast<float*>(rgba)), (int)p->w, (int)p->h);
+                                                     return 0;
+                                                 }, &pub, &st);
+                } else rc = nrcu_render_multi(devs.data(), (int)devs.size(), &params, reinterpret_cast<float*>(pixels), &st);
                 if (rc != NRCU_OK) {
                     logger.error(std::string("NRCuda: ") + nrcu_last_error(sh.ctx));
                     delete[] pixels;

@@ -58,3 +58,22 @@ def test_cuda_plugins_register_through_the_reference_factory():
     env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
     names = set(subprocess.run(cmd, capture_output=True, text=True, check=True, env=env).stdout.split())
     assert {"CudaRayCast", "CudaSimplePathTracer", "CudaAccPathTracer", "RayCast", "SimplePathTracer", "AccPathTracer"} <= names
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
+def test_harness_image_writers(tmp_path):
+    """--out by extension: raw RGBA fp32, .pfm (bottom-up RGB fp32) and .ppm (8-bit) hold the same published frame."""
+    env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
+    base = [os.path.join(po.REF_DIR, "nr_headless"), "--flat", os.path.join(GOLDEN, "ray_cast_cornel.nrsc"), "--w", "40", "--h", "30",
+            "--plugin", os.path.join(po.REF_DIR, po.REF_PLUGINS["RayCast"]), "--component", "RayCast", "--out"]
+    raw, pfm, ppm = tmp_path / "f.f32", tmp_path / "f.pfm", tmp_path / "f.ppm"
+    for o in (raw, pfm, ppm):
+        subprocess.run(base + [str(o)], check=True, env=env, capture_output=True)
+    img = np.fromfile(raw, np.float32).reshape(30, 40, 4)
+    head, data = pfm.read_bytes().split(b"-1.0\n", 1)
+    assert head == b"PF\n40 30\n"
+    assert np.array_equal(np.frombuffer(data, np.float32).reshape(30, 40, 3)[::-1], img[..., :3])
+    head, data = ppm.read_bytes().split(b"255\n", 1)
+    assert head == b"P6\n40 30\n"
+    want = (np.clip(img[..., :3], 0, 1) * 255 + 0.5).astype(np.uint8)
+    assert np.array_equal(np.frombuffer(data, np.uint8).reshape(30, 40, 3), want)

@@ -346,3 +346,21 @@ def test_multi_device_rejects_mismatched_contexts(ctx):
             nr.render_multi([ctx, other])          # different resolution
     finally:
         other.close()
+
+
+@pytest.mark.gpu
+def test_progressive_updates_converge_to_the_one_shot_frame(ctx):
+    fs = load_scene("path_tracing_cornel", width=64, height=48, samples_per_pixel=24, depth=6)
+    ctx.upload(fs, 2)
+    final, _ = ctx.render(seed=2)
+    seen = []
+    out, st = ctx.render_progressive(lambda frame, done, total: seen.append((done, total, frame.copy())) or False, samples_per_update=10, seed=2)
+    assert [d for d, _, _ in seen] == [10, 20, 24] and all(t == 24 for _, t, _ in seen)
+    np.testing.assert_allclose(out, final, rtol=2e-6, atol=1e-7)          # same samples; fp32 sum grouped per update
+    np.testing.assert_allclose(seen[-1][2], out, rtol=0, atol=0)
+    assert st["paths"] == 64 * 48 * 24
+    # the first update is the frame of the first 10 samples, and a truthy return stops the render
+    part = []
+    ctx.render_progressive(lambda frame, done, total: part.append((done, frame.copy())) or True, samples_per_update=10, seed=2)
+    assert len(part) == 1 and part[0][0] == 10
+    np.testing.assert_allclose(part[0][1], seen[0][2], rtol=0, atol=0)
