@@ -80,7 +80,7 @@ struct nrcu_ctx {
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
     PrimSources ps{};
     // wavefront state
-    DevBuf qa[2], qb[2], qc[2], hits[2], surv, L, counters, accum_own, rgba_dev, build_scratch;
+    DevBuf qa[2], qb[2], qc[2], qd[2], hits[2], surv, L, counters, accum_own, rgba_dev, build_scratch;
     uint32_t queue_capacity = 0, wave_slots = 0;
     unsigned long long* d_ray_counter = nullptr;   // inside `counters`
     // stats
@@ -422,7 +422,7 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
 // ---------------------------------------------------------------------------------------------
 enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
 
-static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth) {
+static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth, bool branch_bits) {
     // The wave buffers are power-of-two sized (32 Mi x 16 B = 512 MiB) and the kernels stream through ten of
     // them at the same index; each buffer starts at its own skew inside its allocation so that the streams do
     // not share an HBM channel/bank phase (k_shade has been measured anywhere between 39 and 54 ms per 128 spp on
@@ -432,10 +432,11 @@ static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_
     for (size_t j = 0; j < sizeof(bufs) / sizeof(bufs[0]); j++) bufs[j]->skew = (j + 1) * S;
     for (int k = 0; k < 2; k++) {
         CTX_CUDA(ctx->qa[k].ensure(sizeof(f4) * (size_t)capacity));
-        CTX_CUDA(ctx->qb[k].ensure(sizeof(f4) * (size_t)capacity));
+        CTX_CUDA(ctx->qb[k].ensure(sizeof(float2) * (size_t)capacity));
         CTX_CUDA(ctx->qc[k].ensure(sizeof(f4) * (size_t)capacity));
     }
     for (int k = 0; k < 2; k++) CTX_CUDA(ctx->hits[k].ensure(sizeof(float2) * (size_t)capacity));
+    if (branch_bits) for (int k = 0; k < 2; k++) CTX_CUDA(ctx->qd[k].ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(ctx->surv.ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(ctx->L.ensure(sizeof(f4) * (size_t)slots));
     CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 3 * (size_t)depth + 12)));
@@ -460,9 +461,6 @@ static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
 static bool fuse_stage1() { static uint32_t v = env_u32("NRCU_FUSE_STAGE1", 0); return v != 0; }
 static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 32) << 20; return v; }
-static bool shade_deferred() { static uint32_t v = env_u32("NRCU_SHADE_DEFERRED", 0); return v != 0; }
-static bool big_balanced() { static uint32_t v = env_u32("NRCU_BIG_BALANCED", 0); return v != 0; }
-static uint32_t big_blocks() { static uint32_t v = env_u32("NRCU_BIG_BLOCKS", 6); return v ? v : 1; }
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
@@ -515,8 +513,9 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     const uint32_t slots = k * npix;
     const uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
     int rc;
-    if ((rc = ensure_wave(ctx, slots, capacity, ds.depth)) != NRCU_OK) return rc;
-    PathQueue q[2] = {{ctx->qa[0].as<f4>(), ctx->qb[0].as<f4>(), ctx->qc[0].as<f4>()}, {ctx->qa[1].as<f4>(), ctx->qb[1].as<f4>(), ctx->qc[1].as<f4>()}};
+    if ((rc = ensure_wave(ctx, slots, capacity, ds.depth, glass_branch != 0)) != NRCU_OK) return rc;
+    PathQueue q[2] = {{ctx->qa[0].as<f4>(), ctx->qb[0].as<float2>(), ctx->qc[0].as<f4>(), glass_branch ? ctx->qd[0].as<uint32_t>() : nullptr},
+                      {ctx->qa[1].as<f4>(), ctx->qb[1].as<float2>(), ctx->qc[1].as<f4>(), glass_branch ? ctx->qd[1].as<uint32_t>() : nullptr}};
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     unsigned long long* d_rays = reinterpret_cast<unsigned long long*>(cnt + CNT_RAYS);
     uint32_t* d_qn = cnt + CNT_QUEUE0;                 // queue size entering bounce d
@@ -550,11 +549,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
             float2* hi = hb[d & 1]; float2* ho = hb[(d + 1) & 1];
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
             if (d > 0 && !fuse) {   // stage 1 of this bounce (bounce 0's ran inside k_raygen)
-                if (big_balanced()) {
-                    if (gate) k_big2<true><<<(unsigned)sms * big_blocks(), 32 * NRCU_BIG2_WARPS, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
-                    else k_big2<false><<<(unsigned)sms * big_blocks(), 32 * NRCU_BIG2_WARPS, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
-                }
-                else if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
+                if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
                 else k_big<false><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
                 CTX_LAUNCH_CHECK("k_big");
             }
@@ -565,11 +560,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
             }
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
 #define NRCU_SHADE(G, F) k_shade<G, F><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, capacity, ctx->L.as<f4>(), ho, surv, d_nsurv + d + 1, d_rays)
-            if (!fuse && !glass_branch && shade_deferred()) {
-                if (gate) k_shade_deferred<true><<<shade_grid, 256, 0, st>>>(ds, seed, d, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, ctx->L.as<f4>());
-                else k_shade_deferred<false><<<shade_grid, 256, 0, st>>>(ds, seed, d, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, ctx->L.as<f4>());
-            }
-            else if (gate) { if (fuse) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
+            if (gate) { if (fuse) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
             else { if (fuse) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
 #undef NRCU_SHADE
             CTX_LAUNCH_CHECK("k_shade");
@@ -789,12 +780,12 @@ int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim
     CTX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DevBuf d_rays, qa, qb, hits, surv, cnt;
-    CTX_CUDA(d_rays.ensure(sizeof(float) * 6 * (size_t)n)); CTX_CUDA(qa.ensure(sizeof(f4) * (size_t)n)); CTX_CUDA(qb.ensure(sizeof(f4) * (size_t)n));
+    CTX_CUDA(d_rays.ensure(sizeof(float) * 6 * (size_t)n)); CTX_CUDA(qa.ensure(sizeof(f4) * (size_t)n)); CTX_CUDA(qb.ensure(sizeof(float2) * (size_t)n));
     CTX_CUDA(hits.ensure(sizeof(float2) * (size_t)n)); CTX_CUDA(surv.ensure(sizeof(uint32_t) * (size_t)n)); CTX_CUDA(cnt.ensure(32));
     CTX_CUDA(cudaMemcpyAsync(d_rays.p, rays, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, st));
     uint32_t h_cnt[8] = {0, 0, n, 0, 0, 0, 0, 0};   // [0..1] ray counter, [2] n, [3] fetch cursor, [4] survivors
     CTX_CUDA(cudaMemcpyAsync(cnt.p, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
-    PathQueue q{qa.as<f4>(), qb.as<f4>(), nullptr};
+    PathQueue q{qa.as<f4>(), qb.as<float2>(), nullptr, nullptr};
     k_pack_rays<<<grid_for(n, 256), 256, 0, st>>>(d_rays.as<float>(), n, q);
     CTX_LAUNCH_CHECK("k_pack_rays");
     uint32_t* c = cnt.as<uint32_t>();

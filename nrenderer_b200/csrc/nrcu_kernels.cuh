@@ -61,9 +61,11 @@ __global__ void k_raycast(DScene s, f4* rgba, unsigned long long* ray_counter) {
 // ---------------------------------------------------------------------------------------------
 // Wavefront path tracer
 // ---------------------------------------------------------------------------------------------
-// A queue entry is three float4:  a = (o.xyz, d.x)  b = (d.y, d.z, thr.x, thr.y)  c = (thr.z, slot, branch, -)
+// A queue entry is 40 bytes in three arrays:  a = float4 (o.xyz, d.x)   b = float2 (d.y, d.z)   c = float4 (thr.xyz, slot)
+// (+ d = uint32 glass-branch bits, only allocated and touched in the branching glass mode).  The closest-hit kernels
+// read a and b (24 B/ray), the shading kernel reads and writes all of it.
 // slot = sample_in_wave * n_pixels + pixel identifies the path; its radiance lands in L[slot].
-struct PathQueue { f4* a; f4* b; f4* c; };
+struct PathQueue { f4* a; float2* b; f4* c; uint32_t* d; };
 
 // The wide-primitive list staged in shared memory (read as warp-wide broadcasts).
 struct BigList {
@@ -119,8 +121,9 @@ __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_
                 L[slot] = mk4(0.f, 0.f, 0.f, 0.f);
                 Ray r = pt_camera_ray(s, seed, pixel, sample);
                 q.a[slot] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
-                q.b[slot] = mk4(r.d.y, r.d.z, 1.f, 1.f);
-                q.c[slot] = mk4(1.f, i2f((int)slot), i2f(0), 0.f);
+                q.b[slot] = make_float2(r.d.y, r.d.z);
+                q.c[slot] = mk4(1.f, 1.f, 1.f, i2f((int)slot));
+                if (q.d) q.d[slot] = 0u;
                 more = stage1<GATE>(s, bl, r, slot, hits);
             }
         }
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     // software pipeline as in k_shade: the next ray is requested before waiting for the survivor-list atomic
-    f4 a = mk4(0, 0, 0, 0), b = a;
+    f4 a = mk4(0, 0, 0, 0); float2 b = make_float2(0.f, 0.f);
     { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
         const uint32_t i = base + lane;
@@ -166,93 +169,6 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
             start = __shfl_sync(0xffffffffu, start, 0);
             if (more) surv[start + __popc(m & ((1u << lane) - 1u))] = i;
         }
-    }
-}
-
-// k_big with WARP-BALANCED exact tests.  In k_big the exact tests of a warp take as many rounds as its busiest
-// lane has candidates (about 5 on incoherent rays, at 2-8 active lanes: ncu, profiles/r1_*), although the warp
-// holds only ~2 candidates per ray.  Here the (ray, candidate) pairs of the 32 rays are written to a per-warp list in
-// shared memory (exclusive scan of the per-lane counts) and dealt out 32 at a time, so every round runs 32 exact
-// tests; results go back to the owning ray through a 64-bit shared-memory atomicMin on (t bits, id, list index) -
-// t > 0, so unsigned order is (t, id) order, exactly the tie rule of the per-ray loop.  The optimistic leaf gate and
-// its per-candidate fallback stay with the owner.
-#define NRCU_BIG2_WARPS 8
-template <bool GATE>
-__global__ void __launch_bounds__(32 * NRCU_BIG2_WARPS) k_big2(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
-                                                               uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
-    __shared__ BigList bl;
-    __shared__ unsigned short pairs[NRCU_BIG2_WARPS][32 * NRCU_MAX_BIG];
-    __shared__ float rays[NRCU_BIG2_WARPS][6][32];
-    __shared__ unsigned long long best[NRCU_BIG2_WARPS][32];
-    bl.load(s);
-    const uint32_t n = *n_ptr;
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    unsigned short* my_pairs = pairs[wib];
-    f4 a = mk4(0, 0, 0, 0), b = a;
-    { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
-    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
-        const uint32_t i = base + lane;
-        Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
-        RayPrep rp = prep_ray(r);
-        // pass 1: candidate mask (warp-uniform loop over the list, broadcast reads)
-        uint32_t mask = 0;
-        if (i < n) {
-            for (uint32_t k = 0; k < s.n_big; k++) {
-                f4 lo = bl.bd[2 * k], hi = bl.bd[2 * k + 1];
-                float ax = fmaf(lo.x, rp.inv.x, -rp.oinv.x), bx = fmaf(hi.x, rp.inv.x, -rp.oinv.x);
-                float ay = fmaf(lo.y, rp.inv.y, -rp.oinv.y), by = fmaf(hi.y, rp.inv.y, -rp.oinv.y);
-                float az = fmaf(lo.z, rp.inv.z, -rp.oinv.z), bz = fmaf(hi.z, rp.inv.z, -rp.oinv.z);
-                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-                if (tn <= tf) mask |= 1u << k;
-            }
-        }
-        { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; } }   // prefetch
-        // deal the (ray, candidate) pairs out over the warp
-        const uint32_t cnt = __popc(mask);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (uint32_t)off) incl += v; }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        rays[wib][0][lane] = r.o.x; rays[wib][1][lane] = r.o.y; rays[wib][2][lane] = r.o.z;
-        rays[wib][3][lane] = r.d.x; rays[wib][4][lane] = r.d.y; rays[wib][5][lane] = r.d.z;
-        best[wib][lane] = ~0ull;
-        { uint32_t pos = incl - cnt; for (uint32_t m = mask; m; m &= m - 1u) my_pairs[pos++] = (unsigned short)((lane << 5) | (uint32_t)(__ffs((int)m) - 1)); }
-        __syncwarp();
-        for (uint32_t j = lane; j < total; j += 32u) {
-            const uint32_t p = my_pairs[j], ol = p >> 5, k = p & 31u;
-            Ray pr; pr.o = mk3(rays[wib][0][ol], rays[wib][1][ol], rays[wib][2][ol]); pr.d = mk3(rays[wib][3][ol], rays[wib][4][ol], rays[wib][5][ol]);
-            float bt = NRCU_INF; int bi = -1;
-            prim_test<false>(pr, mk3(0.f), bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b, bl.m[k], bt, bi);
-            if (bi >= 0) atomicMin(&best[wib][ol], ((unsigned long long)__float_as_uint(bt) << 32) | (unsigned long long)(((uint32_t)bi << 5) | k));
-        }
-        __syncwarp();
-        bool more = false;
-        if (i < n) {
-            const unsigned long long key = best[wib][lane];
-            float best_t = NRCU_INF; int best_id = -1;
-            if (key != ~0ull) {
-                best_t = __uint_as_float((uint32_t)(key >> 32)); best_id = (int)((uint32_t)key >> 5);
-                if (GATE) {
-                    const uint32_t kb = (uint32_t)key & 31u;
-                    const vec3 ginv = gate_inverse(r);
-                    if (!bounds_intersectp_inv(bl.b[2 * kb], bl.b[2 * kb + 1], r, ginv.x, ginv.y, ginv.z)) {   // rare: gate per candidate
-                        best_t = NRCU_INF; best_id = -1;
-                        for (uint32_t m = mask; m; m &= m - 1u) {
-                            const uint32_t k = (uint32_t)(__ffs((int)m) - 1);
-                            prim_test<true>(r, ginv, bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b + 2 * k, bl.m[k], best_t, best_id);
-                        }
-                    }
-                }
-            }
-            hits[i] = make_float2(best_t, __int_as_float(best_id));
-            more = bvh_reachable(s, rp, best_t);
-        }
-        __syncwarp();   // the shared lists are rewritten by the next iteration
-        if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
-        append_survivors(more, i, surv, n_surv);
     }
 }
 
@@ -325,7 +241,7 @@ struct Lane {
 template <bool GATE>
 __device__ __forceinline__ bool fetch_ray(const DScene& s, const PathQueue& q, const uint32_t* surv, const float2* hits, uint32_t j, Lane& L) {
     const uint32_t i = surv ? surv[j] : j;
-    f4 a = q.a[i], b = q.b[i];
+    f4 a = q.a[i]; float2 b = q.b[i];
     L.r.o = mk3(a.x, a.y, a.z); L.r.d = mk3(a.w, b.x, b.y);
     L.rp = prep_ray(L.r);
     if (GATE) L.ginv = gate_inverse(L.r);
@@ -458,7 +374,7 @@ __global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace3(DScene s, PathQue
 __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hits) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    f4 a = q.a[i], b = q.b[i];
+    f4 a = q.a[i]; float2 b = q.b[i];
     Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
     float t; int id;
     closest_hit_linear<true>(s, r, t, id);
@@ -489,10 +405,10 @@ __global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScen
     // output-slot atomic has been issued, so the atomic's round trip and the loads' latency overlap (ncu on the
     // unpipelined loop: 38 % of the stall samples sat on the shuffle that waits for the atomic, 16 % on the first
     // use of the loaded entry).
-    f4 a = mk4(0, 0, 0, 0), b = a, c = a; float2 h = make_float2(0.f, 0.f);
+    f4 a = mk4(0, 0, 0, 0), c = a; float2 b = make_float2(0.f, 0.f), h = b; uint32_t br = 0;
     {
         const uint32_t i0 = warp_global * 32u + lane;
-        if (i0 < n) { a = qi.a[i0]; b = qi.b[i0]; c = qi.c[i0]; h = hits[i0]; }
+        if (i0 < n) { a = qi.a[i0]; b = qi.b[i0]; c = qi.c[i0]; h = hits[i0]; if (glass_branch) br = qi.d[i0]; }
     }
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
         uint32_t i = base + lane;
@@ -501,8 +417,8 @@ __global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScen
         uint32_t slot = 0, branch = 0;
         if (i < n) {
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
-            vec3 thr = mk3(b.z, b.w, c.x);
-            slot = (uint32_t)f2i(c.y); branch = (uint32_t)f2i(c.z);
+            vec3 thr = mk3(c.x, c.y, c.z);
+            slot = (uint32_t)f2i(c.w); branch = br;
             uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
             ps = path_vertex(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch);
             if (ps.action == PATH_TERMINATE) {
@@ -522,7 +438,7 @@ __global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScen
         if (lane == 0 && total) { start = atomicAdd(n_out_ptr, total); if (FUSE) atomicAdd(ray_counter, (unsigned long long)total); }
         {   // prefetch the next iteration's entry while the atomic is in flight
             const uint32_t inext = i + warps_total * 32u;
-            if (inext < n) { a = qi.a[inext]; b = qi.b[inext]; c = qi.c[inext]; h = hits[inext]; }
+            if (inext < n) { a = qi.a[inext]; b = qi.b[inext]; c = qi.c[inext]; h = hits[inext]; if (glass_branch) br = qi.d[inext]; }
         }
         if (total == 0) continue;   // warp-uniform
         start = __shfl_sync(0xffffffffu, start, 0);
@@ -531,86 +447,21 @@ __global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScen
         uint32_t pos1 = start + __popc(m1 & lt), pos2 = start + __popc(m1) + __popc(m2 & lt);
         if (n_out >= 1 && pos1 < out_capacity) {
             qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
-            qo.b[pos1] = mk4(ps.next.d.y, ps.next.d.z, ps.thr.x, ps.thr.y);
-            qo.c[pos1] = mk4(ps.thr.z, i2f((int)slot), i2f((int)branch), 0.f);
+            qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
+            qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)slot));
+            if (glass_branch) qo.d[pos1] = branch;
             if (FUSE) more1 = stage1<GATE>(s, bl, ps.next, pos1, hits_out);
         }
         if (FUSE) append_survivors(more1, pos1, surv, n_surv);
         if (m2) {   // warp-uniform: glass branch mode only
             if (n_out == 2 && pos2 < out_capacity) {
                 qo.a[pos2] = mk4(ps.next2.o.x, ps.next2.o.y, ps.next2.o.z, ps.next2.d.x);
-                qo.b[pos2] = mk4(ps.next2.d.y, ps.next2.d.z, ps.thr2.x, ps.thr2.y);
-                qo.c[pos2] = mk4(ps.thr2.z, i2f((int)slot), i2f((int)(branch | (1u << (d & 31u)))), 0.f);
+                qo.b[pos2] = make_float2(ps.next2.d.y, ps.next2.d.z);
+                qo.c[pos2] = mk4(ps.thr2.x, ps.thr2.y, ps.thr2.z, i2f((int)slot));
+                qo.d[pos2] = branch | (1u << (d & 31u));
                 if (FUSE) more2 = stage1<GATE>(s, bl, ps.next2, pos2, hits_out);
             }
             if (FUSE) append_survivors(more2, pos2, surv, n_surv);
-        }
-    }
-}
-
-// k_shade for the common case (no glass branching, stage 1 not fused): same arithmetic, but the output-slot
-// atomic of iteration i is consumed in iteration i+1.  The continuation ray of iteration i waits in shared
-// memory (13 words per thread, [word][thread]) while the next queue entry is shaded, so the round trip of the
-// atomic (the largest stall of the plain kernel: 38 % of its samples) is hidden behind a whole iteration of work.
-template <bool GATE>
-__global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_deferred(DScene s, uint64_t seed, uint32_t d, uint32_t sample0,
-                                                                        PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
-                                                                        PathQueue qo, uint32_t* n_out_ptr, f4* L) {
-    __shared__ float park[11 * 256];
-    float* pk = park + threadIdx.x;
-    const uint32_t n = *n_in_ptr;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t npix = s.width * s.height;
-    f4 a = mk4(0, 0, 0, 0), b = a, c = a; float2 h = make_float2(0.f, 0.f);
-    { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = qi.a[i0]; b = qi.b[i0]; c = qi.c[i0]; h = hits[i0]; } }
-    uint32_t pend_start = 0, pend_rank = 0; bool pend_mine = false, pend_any = false;   // iteration i-1's allocation
-    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
-        const uint32_t i = base + lane;
-        bool out = false;
-        PathStep ps;
-        uint32_t slot = 0;
-        if (i < n) {
-            Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
-            vec3 thr = mk3(b.z, b.w, c.x);
-            slot = (uint32_t)f2i(c.y);
-            uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
-            ps = path_vertex(s, seed, pixel, sample, d, 0u, r, thr, h.x, __float_as_int(h.y), 0);
-            if (ps.action == PATH_TERMINATE) {
-                if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f)
-                    L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);   // one path per slot, it ends once
-            } else out = true;
-        }
-        { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = qi.a[inext]; b = qi.b[inext]; c = qi.c[inext]; h = hits[inext]; } }
-        // flush iteration i-1: its atomic was issued a whole iteration ago
-        if (pend_any) {
-            const uint32_t start = __shfl_sync(0xffffffffu, pend_start, 0);
-            if (pend_mine) {
-                const uint32_t pos = start + pend_rank;
-                qo.a[pos] = mk4(pk[0 * 256], pk[1 * 256], pk[2 * 256], pk[3 * 256]);
-                qo.b[pos] = mk4(pk[4 * 256], pk[5 * 256], pk[6 * 256], pk[7 * 256]);
-                qo.c[pos] = mk4(pk[8 * 256], pk[9 * 256], i2f(0), 0.f);
-            }
-        }
-        // park iteration i and issue its atomic
-        const uint32_t m = __ballot_sync(0xffffffffu, out);
-        pend_any = m != 0; pend_mine = out; pend_rank = __popc(m & lt);
-        if (out) {
-            pk[0 * 256] = ps.next.o.x; pk[1 * 256] = ps.next.o.y; pk[2 * 256] = ps.next.o.z; pk[3 * 256] = ps.next.d.x;
-            pk[4 * 256] = ps.next.d.y; pk[5 * 256] = ps.next.d.z; pk[6 * 256] = ps.thr.x; pk[7 * 256] = ps.thr.y;
-            pk[8 * 256] = ps.thr.z; pk[9 * 256] = i2f((int)slot);
-        }
-        if (lane == 0 && m) pend_start = atomicAdd(n_out_ptr, (uint32_t)__popc(m));
-    }
-    if (pend_any) {
-        const uint32_t start = __shfl_sync(0xffffffffu, pend_start, 0);
-        if (pend_mine) {
-            const uint32_t pos = start + pend_rank;
-            qo.a[pos] = mk4(pk[0 * 256], pk[1 * 256], pk[2 * 256], pk[3 * 256]);
-            qo.b[pos] = mk4(pk[4 * 256], pk[5 * 256], pk[6 * 256], pk[7 * 256]);
-            qo.c[pos] = mk4(pk[8 * 256], pk[9 * 256], i2f(0), 0.f);
         }
     }
 }
@@ -662,7 +513,7 @@ __global__ void k_pack_rays(const float* rays6, uint32_t n, PathQueue q) {
     if (i >= n) return;
     const float* r = rays6 + 6 * (size_t)i;
     q.a[i] = mk4(r[0], r[1], r[2], r[3]);
-    q.b[i] = mk4(r[4], r[5], 1.f, 1.f);
+    q.b[i] = make_float2(r[4], r[5]);
 }
 
 }  // namespace nrcu
