@@ -461,6 +461,11 @@ static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
 static bool fuse_stage1() { static uint32_t v = env_u32("NRCU_FUSE_STAGE1", 0); return v != 0; }
 static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 32) << 20; return v; }
+static uint32_t trace_taper(int k) {
+    static uint32_t v[2] = {0xffffffffu, 0xffffffffu}; static bool init = false;
+    if (!init) { init = true; const char* e = std::getenv("NRCU_TRACE_TAPER"); unsigned a = 0xffffffffu, b = 0xffffffffu; if (e) std::sscanf(e, "%u,%u", &a, &b); v[0] = a; v[1] = b; }
+    return v[k];
+}
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
@@ -468,8 +473,14 @@ static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const ch
 // Stage 2 of the closest hit: BVH traversal of the *n_surv rays listed in `surv`, refining hits[] in place.
 template <bool GATE>
 static void launch_stage2(nrcu_ctx* ctx, const DScene& ds, PathQueue q, float2* hits, const uint32_t* surv, const uint32_t* n_surv,
-                          uint32_t* fetch, unsigned long long* rays) {
-    const unsigned grid = (unsigned)sm_count(ctx->device) * trace_blocks_per_sm();
+                          uint32_t* fetch, unsigned long long* rays, uint32_t bounce = 0) {
+    // Deep bounces hold few rays; a smaller persistent grid has a lower latency floor (fewer CTAs to start,
+    // fewer warps contending for the fetch counter) - measured: it does not, smaller grids are simply slower (6,12: -5 %),
+    // so tapering is off by default.  NRCU_TRACE_TAPER="a,b" halves the grid from bounce a and again from b.
+    unsigned per_sm = trace_blocks_per_sm();
+    if (bounce >= trace_taper(0)) per_sm = std::max(1u, per_sm / 2);
+    if (bounce >= trace_taper(1)) per_sm = std::max(1u, per_sm / 2);
+    const unsigned grid = (unsigned)sm_count(ctx->device) * per_sm;
     if (trace_variant() == 3) k_trace3<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill(), trace_w_node(), trace_w_prim());
     else if (trace_variant() == 4) k_trace2<GATE, true><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
     else k_trace2<GATE, false><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
@@ -554,8 +565,8 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
                 CTX_LAUNCH_CHECK("k_big");
             }
             if (ds.root_ref != NRCU_REF_EMPTY) {
-                if (gate) launch_stage2<true>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays);
-                else launch_stage2<false>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays);
+                if (gate) launch_stage2<true>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays, d);
+                else launch_stage2<false>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays, d);
                 CTX_LAUNCH_CHECK("k_trace");
             }
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
