@@ -37,6 +37,8 @@ WORKLOADS = {
     "cfg2_simple_cornell_1024x1024_2048spp": ("path_tracing_cornel", 1, 1024, 1024, 2048, 20, 1.0, "SimplePathTracer", 866.0),
     "cfg3_acc_bunny5k_1920x1080_1024spp": ("bunny5k_cornel", 2, 1920, 1080, 1024, 20, 16.0 / 9.0, "AccPathTracer", 2039.0),
     "cfg4_acc_gold_1920x1080_4096spp": ("pt_glass", 2, 1920, 1080, 4096, 20, 16.0 / 9.0, "AccPathTracer", 866.0),
+    # cfg5: no reference semantics; synthetic 64x32 lat-long map; meant for --gpus 8 (weak point: 34 G paths)
+    "cfg5_acc_envmap_3840x2160_4096spp": ("env_map_spheres", 2, 3840, 2160, 4096, 20, 16.0 / 9.0, "AccPathTracer", 866.0),
 }
 DEFAULT_WORKLOAD = "cfg3_acc_bunny5k_1920x1080_1024spp"
 
@@ -46,6 +48,10 @@ def load_workload(name, spp_override=None):
     scene, mode, w, h, spp, depth, aspect, comp, bpr = WORKLOADS[name]
     fs = FlatScene.load(os.path.join(REPO, "tests", "golden", scene + ".nrsc"))
     fs.width, fs.height, fs.samples_per_pixel, fs.depth, fs.cam_aspect = w, h, spp_override or spp, depth, aspect
+    if name.startswith("cfg5"):   # ambient = environment map (extension); deterministic synthetic texture
+        import numpy as np
+        g = np.random.default_rng(1)
+        fs.ambient_type, fs.ambient_environment_map = 1, fs.add_texture(g.uniform(0.0, 2.0, (32, 64, 4)).astype(np.float32))
     return fs, mode, comp, bpr
 
 
