@@ -176,6 +176,10 @@ def cuda_arm(args):
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Libraries print to fd 1 (NCCL's version banner at communicator creation): keep stdout for the ONE JSON line.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
@@ -312,7 +316,10 @@ def cuda_arm(args):
                     line["cpu_baseline"] = {"value": None, "unit": "Mpath-samples/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
             except Exception as ex:   # the GPU number stands on its own
                 line["cpu_baseline"] = {"value": None, "unit": "Mpath-samples/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
