@@ -21,7 +21,8 @@ SMS, SCHEDULERS = 148, 4
 KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "lts__t_bytes.sum", "l1tex__t_bytes.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "lts__t_sectors.sum", "SM_B.TriageCompute.l1tex__t_sectors.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
@@ -119,7 +120,7 @@ def main():
         f.write(f"\nClosest-hit kernels ({', '.join(ch)}): {ch_time/T*100:.1f} % of the render-kernel time, "
                 f"{ch_inst/ch_time/(SMS*SCHEDULERS*1965.0)*100:.1f} % of the issue-slot peak (148 SMs x 4 x 1.965 GHz), "
                 f"DRAM traffic per wave {summary['closest_hit_dram_bytes_per_step_equiv']/1e9:.2f} GB.\n")
-        f.write("\nFull captures (`ncu --set full`, one launch each at bounce 1):\n\n| kernel | time us | regs | lanes/inst | issue % | warps active % | L1 hit % | L2 hit % | DRAM R MB | DRAM W MB | long-scoreboard stall |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+        f.write("\nFull captures (`ncu --set full`, one launch each at bounce 1):\n\n| kernel | time us | regs | lanes/inst | issue % | warps active % | L1 hit % | L2 hit % | L1 GB/s (% of peak) | L2 GB/s (% of peak) | DRAM R MB | DRAM W MB | DRAM GB/s (of 6549.8) | long-scoreboard stall |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         U = {k: units[hdr.index(k)] for k in KEEP if k in hdr}
         def mb(h, k):
             v = float(h.get(k, 0) or 0)
@@ -131,7 +132,7 @@ def main():
             g = lambda k: h.get(k, "")
             f.write(f"| `{h['kernel']}` | {us(h, 'gpu__time_duration.sum'):.1f} | {g('launch__registers_per_thread')} | {g('smsp__thread_inst_executed_per_inst_executed.ratio')} | "
                     f"{float(g('smsp__issue_active.avg.pct_of_peak_sustained_active') or 0):.1f} | {float(g('sm__warps_active.avg.pct_of_peak_sustained_active') or 0):.1f} | "
-                    f"{float(g('l1tex__t_sector_hit_rate.pct') or 0):.1f} | {float(g('lts__t_sector_hit_rate.pct') or 0):.1f} | {mb(h, 'dram__bytes_read.sum'):.1f} | {mb(h, 'dram__bytes_write.sum'):.1f} | "
+                    f"{float(g('l1tex__t_sector_hit_rate.pct') or 0):.1f} | {float(g('lts__t_sector_hit_rate.pct') or 0):.1f} | {float(g('SM_B.TriageCompute.l1tex__t_sectors.sum') or 0) * 32e-9 / max(us(h, 'gpu__time_duration.sum') * 1e-6, 1e-12):.0f} ({float(g('l1tex__throughput.avg.pct_of_peak_sustained_elapsed') or 0):.0f} %) | {float(g('lts__t_sectors.sum') or 0) * 32e-9 / max(us(h, 'gpu__time_duration.sum') * 1e-6, 1e-12):.0f} ({float(g('lts__throughput.avg.pct_of_peak_sustained_elapsed') or 0):.0f} %) | {mb(h, 'dram__bytes_read.sum'):.1f} | {mb(h, 'dram__bytes_write.sum'):.1f} | {(mb(h, 'dram__bytes_read.sum') + mb(h, 'dram__bytes_write.sum')) / max(us(h, 'gpu__time_duration.sum'), 1e-9) * 1e3:.0f} ({(mb(h, 'dram__bytes_read.sum') + mb(h, 'dram__bytes_write.sum')) / max(us(h, 'gpu__time_duration.sum'), 1e-9) * 1e3 / 6549.8 * 100:.0f} %) | "
                     f"{float(g('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio') or 0):.2f} |\n")
     print(open(os.path.join(out_dir, f"{rnd}_summary.md")).read())
 
