@@ -221,7 +221,7 @@ def cuda_arm(args):
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"rays": 0, "paths": 0, "kernel_launches": 0, "ms_trace": 0.0, "ms_shade": 0.0}
+    agg = {"rays": 0, "paths": 0, "kernel_launches": 0, "ms_trace": 0.0, "ms_shade": 0.0, "ms_fused": 0.0}
     ev0.record()
     for _ in range(args.steps):
         st = step(True)
@@ -231,12 +231,13 @@ def cuda_arm(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"]], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_fused"]], dtype=torch.float64, device=dev)
     sums = torch.tensor([agg["rays"], agg["paths"], agg["kernel_launches"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, ms_trace, ms_shade = t.tolist()
+    ms, ms_trace, ms_shade, ms_fused = t.tolist()
+    ms_closest = ms_trace + ms_fused   # k_raygen (fused stage 1) + k_big + k_trace2  (+ k_shade<SHADE_STAGE1> when NRCU_PIPELINE=1)
     rays, paths, launches = sums.tolist()
     launches += args.steps * (1 if rank == 0 else 0)   # resolve
     value = paths / (ms * 1e-3) * 1e-6
@@ -279,7 +280,7 @@ def cuda_arm(args):
     closest_hit_launches = args.steps * waves * (1 + (fs.depth - 1) + fs.depth) if waves else 0
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = rays * bytes_per_ray / (ms_trace * 1e-3) * 1e-9 if ms_trace > 0 else None
+        achieved = rays * bytes_per_ray / (ms_closest * 1e-3) * 1e-9 if ms_closest > 0 else None
         line = {
             "metric": "Mpath-samples/s", "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -289,14 +290,14 @@ def cuda_arm(args):
                        "l2": "256 MB flush buffer written between steps; per-wave ray/path state (~1 GB) exceeds the 126 MB L2",
                        "glass_mode": "stochastic", "seed": args.seed},
             "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / max(paths, 1),
-            "kernel_ms": {"closest_hit": ms_trace / args.steps, "shade": ms_shade / args.steps},
+            "kernel_ms": {"closest_hit": ms_closest / args.steps, "shade": ms_shade / args.steps},
             "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "clocks": e2e_clocks},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": profile_summary().get("closest_hit", {}).get("dram_bytes_per_launch"),
                          "algorithmic_bytes_per_launch": (rays * bytes_per_ray / max(closest_hit_launches, 1)) if closest_hit_launches else None,
                          "kernel": "closest hit = k_raygen (camera rays + fused stage 1) + k_big + k_trace2", "algorithmic_bytes_per_ray": bytes_per_ray,
-                         "peak_source": peak_src, "share_of_step": ms_trace / ms if ms else None,
+                         "peak_source": peak_src, "share_of_step": ms_closest / ms if ms else None,
                          "note": "algorithmic bytes are those of the REFERENCE's traversal (SURVEY 8d); the scene is L1/L2 resident, so the "
                                  "fraction can exceed 1 and the binding limit is issue slots x warp efficiency: see 'issue' (from the committed "
                                  "ncu launch list, profiles/) and DESIGN.md section 5",

@@ -80,7 +80,7 @@ struct nrcu_ctx {
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
     PrimSources ps{};
     // wavefront state
-    DevBuf qa[2], qb[2], qc[2], qd[2], hits[2], surv, L, counters, accum_own, rgba_dev, build_scratch;
+    DevBuf qa[2], qb[2], qc[2], qd[2], hits, surv, L, counters, accum_own, rgba_dev, build_scratch;
     uint32_t queue_capacity = 0, wave_slots = 0;
     unsigned long long* d_ray_counter = nullptr;   // inside `counters`
     // stats
@@ -428,14 +428,14 @@ static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_
     // not share an HBM channel/bank phase (k_shade has been measured anywhere between 39 and 54 ms per 128 spp on
     // different boxes with identical code; the skew did not change that, it is kept as a cheap precaution).
     const size_t S = (size_t)wave_skew_kb() << 10;
-    DevBuf* bufs[] = {&ctx->qa[0], &ctx->qb[0], &ctx->qc[0], &ctx->qa[1], &ctx->qb[1], &ctx->qc[1], &ctx->hits[0], &ctx->hits[1], &ctx->surv, &ctx->L};
+    DevBuf* bufs[] = {&ctx->qa[0], &ctx->qb[0], &ctx->qc[0], &ctx->qa[1], &ctx->qb[1], &ctx->qc[1], &ctx->hits, &ctx->surv, &ctx->L};
     for (size_t j = 0; j < sizeof(bufs) / sizeof(bufs[0]); j++) bufs[j]->skew = (j + 1) * S;
     for (int k = 0; k < 2; k++) {
         CTX_CUDA(ctx->qa[k].ensure(sizeof(f4) * (size_t)capacity));
         CTX_CUDA(ctx->qb[k].ensure(sizeof(float2) * (size_t)capacity));
         CTX_CUDA(ctx->qc[k].ensure(sizeof(f4) * (size_t)capacity));
     }
-    for (int k = 0; k < 2; k++) CTX_CUDA(ctx->hits[k].ensure(sizeof(float2) * (size_t)capacity));
+    CTX_CUDA(ctx->hits.ensure(sizeof(float2) * (size_t)capacity));
     if (branch_bits) for (int k = 0; k < 2; k++) CTX_CUDA(ctx->qd[k].ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(ctx->surv.ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(ctx->L.ensure(sizeof(f4) * (size_t)slots));
@@ -459,7 +459,7 @@ static int sm_count(int device) {
 // first, batch-of-32 kernel kept for A/B measurements).
 static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
-static bool fuse_stage1() { static uint32_t v = env_u32("NRCU_FUSE_STAGE1", 0); return v != 0; }
+static bool pipeline_fused() { static uint32_t v = env_u32("NRCU_PIPELINE", 0); return v != 0; }
 static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 32) << 20; return v; }
 static uint32_t trace_taper(int k) {
     static uint32_t v[2] = {0xffffffffu, 0xffffffffu}; static bool init = false;
@@ -546,41 +546,69 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     for (uint32_t w0 = s0; w0 < s1; w0 += k) {
         const uint32_t kw = std::min(k, s1 - w0), n_slots = kw * npix;
         CTX_CUDA(cudaMemsetAsync(cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
-        const bool gate = ctx->mode == NRCU_MODE_ACC, fuse = fuse_stage1();
-        float2* hb[2] = {ctx->hits[0].as<float2>(), ctx->hits[1].as<float2>()};
+        // Per bounce d of the wave (default, NRCU_PIPELINE=0): stage 1 in k_raygen (d = 0) / k_big, k_trace* on the
+        // survivors, k_shade<SHADE_ALL>.  NRCU_PIPELINE=1 is the fused form
+        //   k_shade<SHADE_STAGE1>  every ray: stage 1 of the closest hit, then either shading at once or deferral to the survivor list
+        //   k_trace*               the survivors: BVH traversal, refining hits[]
+        //   k_shade<SHADE_SURV>    shading of the survivors
+        // which reads every ray once instead of twice and never writes the hit of 92 % of them - and is 25 % SLOWER on
+        // B200 (126.7 ms vs 40 + 45 + 9 ms per 128 spp of cfg3): the fused kernel needs 64 registers with 80 B of spills
+        // and runs the divergent exact tests and the divergent shading back to back in the same warps.  Kept for A/B.
+        const bool gate = ctx->mode == NRCU_MODE_ACC, fused = pipeline_fused();
+        float2* hb = ctx->hits.as<float2>();
         uint32_t* surv = ctx->surv.as<uint32_t>();
         const unsigned gen_grid = std::min<unsigned>(grid_for(n_slots, 256), (unsigned)sms * 8);
+        f4* Lbuf = ctx->L.as<f4>();
         if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
-        if (gate) k_raygen<true><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn, hb[0], surv, d_nsurv, d_rays);
-        else k_raygen<false><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], ctx->L.as<f4>(), d_qn, hb[0], surv, d_nsurv, d_rays);
+#define NRCU_RAYGEN(G, S1) k_raygen<G, S1><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], Lbuf, d_qn, hb, surv, d_nsurv, d_rays)
+        if (gate) { if (fused) NRCU_RAYGEN(true, false); else NRCU_RAYGEN(true, true); }
+        else { if (fused) NRCU_RAYGEN(false, false); else NRCU_RAYGEN(false, true); }
+#undef NRCU_RAYGEN
         CTX_LAUNCH_CHECK("k_raygen");
-        if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); ev_i += 2; }   // booked as closest-hit time: stage 1 of bounce 0 is most of this kernel
+        if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, fused ? 1 : 0}); ev_i += 2; }
+#define NRCU_SHADE(G, M) k_shade<G, M><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hb, qo, d_qn + d + 1, capacity, Lbuf, surv, d_nsurv + d, d_rays)
         for (uint32_t d = 0; d < ds.depth; d++) {
             PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
-            float2* hi = hb[d & 1]; float2* ho = hb[(d + 1) & 1];
-            if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
-            if (d > 0 && !fuse) {   // stage 1 of this bounce (bounce 0's ran inside k_raygen)
-                if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
-                else k_big<false><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hi, surv, d_nsurv + d, d_rays);
-                CTX_LAUNCH_CHECK("k_big");
+            const bool bvh = ds.root_ref != NRCU_REF_EMPTY;
+            if (fused) {
+                if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
+                if (gate) NRCU_SHADE(true, SHADE_STAGE1); else NRCU_SHADE(false, SHADE_STAGE1);
+                CTX_LAUNCH_CHECK("k_shade<stage1>");
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 2}); }
+                if (bvh) {
+                    if (gate) launch_stage2<true>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
+                    else launch_stage2<false>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
+                    CTX_LAUNCH_CHECK("k_trace");
+                }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 0}); }
+                if (bvh) {
+                    if (gate) NRCU_SHADE(true, SHADE_SURV); else NRCU_SHADE(false, SHADE_SURV);
+                    CTX_LAUNCH_CHECK("k_shade<surv>");
+                }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i + 2, ev_i + 3, 1}); ev_i += 4; }
+            } else {
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
+                if (d > 0) {   // stage 1 of this bounce (bounce 0's ran inside k_raygen)
+                    if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hb, surv, d_nsurv + d, d_rays);
+                    else k_big<false><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hb, surv, d_nsurv + d, d_rays);
+                    CTX_LAUNCH_CHECK("k_big");
+                }
+                if (bvh) {
+                    if (gate) launch_stage2<true>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
+                    else launch_stage2<false>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
+                    CTX_LAUNCH_CHECK("k_trace");
+                }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
+                if (gate) NRCU_SHADE(true, SHADE_ALL); else NRCU_SHADE(false, SHADE_ALL);
+                CTX_LAUNCH_CHECK("k_shade");
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
             }
-            if (ds.root_ref != NRCU_REF_EMPTY) {
-                if (gate) launch_stage2<true>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays, d);
-                else launch_stage2<false>(ctx, ds, qi, hi, surv, d_nsurv + d, d_fetch + d, d_rays, d);
-                CTX_LAUNCH_CHECK("k_trace");
-            }
-            if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
-#define NRCU_SHADE(G, F) k_shade<G, F><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hi, qo, d_qn + d + 1, capacity, ctx->L.as<f4>(), ho, surv, d_nsurv + d + 1, d_rays)
-            if (gate) { if (fuse) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
-            else { if (fuse) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
-#undef NRCU_SHADE
-            CTX_LAUNCH_CHECK("k_shade");
-            if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
             if (glass_branch) {   // only the branching mode can outgrow the queue
                 k_clamp_count<<<1, 1, 0, st>>>(d_qn + d + 1, capacity, cnt + CNT_HIGH_WATER);
                 CTX_LAUNCH_CHECK("k_clamp_count");
             }
         }
+#undef NRCU_SHADE
         k_accumulate<<<grid_for(npix, 256), 256, 0, st>>>(ctx->L.as<f4>(), d_accum, npix, kw);
         CTX_LAUNCH_CHECK("k_accumulate");
     }
@@ -594,7 +622,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         for (auto& sp : spans) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]);
-            (sp.kind == 0 ? stats->ms_trace : stats->ms_shade) += ms;
+            if (sp.kind == 0) stats->ms_trace += ms; else if (sp.kind == 1) stats->ms_shade += ms; else stats->ms_fused += ms;
         }
         unsigned long long rays; std::memcpy(&rays, h_cnt + CNT_RAYS, 8);
         stats->rays = rays; stats->paths = (uint64_t)npix * (s1 - s0);
@@ -699,7 +727,7 @@ int nrcu_render_progressive(nrcu_ctx* ctx, const nrcu_render_params* params, uin
         CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
         CTX_CUDA(cudaStreamSynchronize(st));
         total.paths += part.paths; total.rays += part.rays; total.kernel_launches += part.kernel_launches + 1;
-        total.ms_total += part.ms_total; total.ms_trace += part.ms_trace; total.ms_shade += part.ms_shade;
+        total.ms_total += part.ms_total; total.ms_trace += part.ms_trace; total.ms_shade += part.ms_shade; total.ms_fused += part.ms_fused;
         total.max_queue = std::max(total.max_queue, part.max_queue);
         total.ms_setup = part.ms_setup; total.bvh_nodes = part.bvh_nodes; total.n_primitives = part.n_primitives;
         if (on_update && on_update(user, rgba_out, p.sample_end, spp) != 0) break;
@@ -774,6 +802,7 @@ int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params
         for (int g = 0; g < n_ctx; g++) {
             stats->paths += st[g].paths; stats->rays += st[g].rays; stats->kernel_launches += st[g].kernel_launches;
             stats->ms_trace = std::max(stats->ms_trace, st[g].ms_trace); stats->ms_shade = std::max(stats->ms_shade, st[g].ms_shade);
+            stats->ms_fused = std::max(stats->ms_fused, st[g].ms_fused);
             stats->max_queue = std::max(stats->max_queue, st[g].max_queue);
         }
         stats->kernel_launches += 1;

@@ -99,17 +99,17 @@ __device__ __forceinline__ void append_survivors(bool more, uint32_t pos, uint32
     if (more) surv[start + __popc(m & ((1u << lane) - 1u))] = pos;
 }
 
-// Camera rays of one wave (slot = sample_in_wave * n_pixels + pixel) + stage 1 of their closest hit.
-template <bool GATE>
+// Camera rays of one wave (slot = sample_in_wave * n_pixels + pixel) (+ STAGE1: stage 1 of their closest hit).
+template <bool GATE, bool STAGE1>
 __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_slots, PathQueue q, f4* L, uint32_t* n_queue,
                                                float2* hits, uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
     __shared__ BigList bl;
-    bl.load(s);
+    if (STAGE1) bl.load(s);
     const uint32_t npix = s.width * s.height;
     const uint32_t stride = gridDim.x * blockDim.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *n_queue = s.depth == 0 ? 0u : n_slots;   // every slot starts one path: the bounce-0 queue is dense
-        if (s.depth != 0) atomicAdd(ray_counter, (unsigned long long)n_slots);
+        if (STAGE1 && s.depth != 0) atomicAdd(ray_counter, (unsigned long long)n_slots);
     }
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_slots; base += stride) {   // warp-uniform trip count
         const uint32_t slot = base + threadIdx.x;
@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_
                 q.b[slot] = make_float2(r.d.y, r.d.z);
                 q.c[slot] = mk4(1.f, 1.f, 1.f, i2f((int)slot));
                 if (q.d) q.d[slot] = 0u;
-                more = stage1<GATE>(s, bl, r, slot, hits);
+                if (STAGE1) more = stage1<GATE>(s, bl, r, slot, hits);
             }
         }
-        append_survivors(more, slot, surv, n_surv);
+        if (STAGE1) append_survivors(more, slot, surv, n_surv);
     }
 }
 
@@ -382,86 +382,105 @@ __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hit
 }
 
 // Shading + next-ray generation for bounce `d`; surviving paths are compacted into `qo` with one atomic per
-// warp (ballot + popc prefix).  FUSE: stage 1 of the NEXT bounce's closest hit runs here, while the new ray is
-// still in registers (it writes hits_out[pos] and appends the rays that must enter the BVH to the survivor list).
-// Measured on B200 the fused form is slower (profiles/r1_*): it pushes the kernel from 64 to 73 registers and the
-// shading kernel is latency-bound, so by default stage 1 of bounces >= 1 runs as its own kernel (k_big).
+// warp (ballot + popc prefix).  Three forms of the same loop:
+//   SHADE_ALL     every queue entry, closest hit read from `hits` (after k_big + k_trace*)
+//   SHADE_STAGE1  every queue entry, stage 1 of the closest hit computed HERE first (wide-primitive list, the ray
+//                 is in registers anyway): a ray that cannot reach the BVH any more is shaded at once - 92 % of
+//                 the rays on bunny+Cornell never touch `hits` and are read from the queue once per bounce instead
+//                 of twice; the others get their provisional hit stored and their queue position appended to the
+//                 survivor list (one atomic per warp) for k_trace* and a SHADE_SURV pass
+//   SHADE_SURV    only the entries listed in `surv`, closest hit read from `hits`
+// The queue entry of the NEXT iteration is requested right after this iteration's output-slot atomic has been
+// issued, so the atomic's round trip and the loads' latency overlap (ncu on the unpipelined loop: 38 % of the stall
+// samples sat on the shuffle that waits for the atomic, 16 % on the first use of the loaded entry).
+enum { SHADE_ALL = 0, SHADE_STAGE1 = 1, SHADE_SURV = 2 };
 #ifndef NRCU_SHADE_MINB
 #define NRCU_SHADE_MINB 4
 #endif
-template <bool GATE, bool FUSE>
-__global__ void __launch_bounds__(256, FUSE ? 1 : NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
-                                              PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
+template <bool GATE, int MODE>
+__global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
+                                              PathQueue qi, const uint32_t* n_in_ptr, float2* hits,
                                               PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L,
-                                              float2* hits_out, uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+                                              uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
     __shared__ BigList bl;
-    if (FUSE) bl.load(s);
-    const uint32_t n = *n_in_ptr;
+    if (MODE == SHADE_STAGE1) bl.load(s);
+    const uint32_t n = MODE == SHADE_SURV ? *n_surv : *n_in_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t npix = s.width * s.height;
-    // Software pipeline: the queue entry of the NEXT iteration is requested right after this iteration's
-    // output-slot atomic has been issued, so the atomic's round trip and the loads' latency overlap (ncu on the
-    // unpipelined loop: 38 % of the stall samples sat on the shuffle that waits for the atomic, 16 % on the first
-    // use of the loaded entry).
-    f4 a = mk4(0, 0, 0, 0), c = a; float2 b = make_float2(0.f, 0.f), h = b; uint32_t br = 0;
-    {
-        const uint32_t i0 = warp_global * 32u + lane;
-        if (i0 < n) { a = qi.a[i0]; b = qi.b[i0]; c = qi.c[i0]; h = hits[i0]; if (glass_branch) br = qi.d[i0]; }
-    }
+    f4 a = mk4(0, 0, 0, 0), c = a; float2 b = make_float2(0.f, 0.f), h = make_float2(NRCU_INF, __int_as_float(-1)); uint32_t br = 0, qpos = 0;
+    auto load_entry = [&](uint32_t j) {
+        if (j >= n) return;
+        qpos = MODE == SHADE_SURV ? surv[j] : j;
+        a = qi.a[qpos]; b = qi.b[qpos]; c = qi.c[qpos];
+        if (MODE != SHADE_STAGE1) h = hits[qpos];
+        if (glass_branch) br = qi.d[qpos];
+    };
+    load_entry(warp_global * 32u + lane);
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
-        uint32_t i = base + lane;
+        const uint32_t i = base + lane;
         int n_out = 0;
+        bool defer = false;
         PathStep ps;
         uint32_t slot = 0, branch = 0;
+        const uint32_t my_pos = qpos;
         if (i < n) {
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             vec3 thr = mk3(c.x, c.y, c.z);
             slot = (uint32_t)f2i(c.w); branch = br;
-            uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
-            ps = path_vertex(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch);
-            if (ps.action == PATH_TERMINATE) {
-                if (glass_branch) {   // several branches of one path share the slot
-                    if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
-                    if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
-                    if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
-                } else if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
-                    L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);   // one path per slot, it ends once: plain store into the zeroed slot
-                }
-            } else n_out = ps.action == PATH_SPLIT ? 2 : 1;
+            if (MODE == SHADE_STAGE1) {
+                RayPrep rp = prep_ray(r);
+                float bt = NRCU_INF; int bi = -1;
+                big_list_step<GATE>(s, bl.g, bl.b, bl.bd, bl.m, r, rp, gate_inverse(r), bt, bi);
+                h = make_float2(bt, __int_as_float(bi));
+                defer = bvh_reachable(s, rp, bt);
+                if (defer) hits[my_pos] = h;
+            }
+            if (!defer) {
+                uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
+                ps = path_vertex(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch);
+                if (ps.action == PATH_TERMINATE) {
+                    if (glass_branch) {   // several branches of one path share the slot
+                        if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
+                        if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
+                        if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
+                    } else if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
+                        L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);   // one path per slot, it ends once: plain store into the zeroed slot
+                    }
+                } else n_out = ps.action == PATH_SPLIT ? 2 : 1;
+            }
         }
-        // warp-aggregated allocation in the output queue
-        uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
-        uint32_t total = __popc(m1) + __popc(m2);
-        uint32_t start = 0;
-        if (lane == 0 && total) { start = atomicAdd(n_out_ptr, total); if (FUSE) atomicAdd(ray_counter, (unsigned long long)total); }
-        {   // prefetch the next iteration's entry while the atomic is in flight
-            const uint32_t inext = i + warps_total * 32u;
-            if (inext < n) { a = qi.a[inext]; b = qi.b[inext]; c = qi.c[inext]; h = hits[inext]; if (glass_branch) br = qi.d[inext]; }
+        // warp-aggregated allocation in the output queue (and, in SHADE_STAGE1, in the survivor list)
+        const uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
+        const uint32_t md = MODE == SHADE_STAGE1 ? __ballot_sync(0xffffffffu, defer) : 0u;
+        const uint32_t total = __popc(m1) + __popc(m2);
+        uint32_t start = 0, sstart = 0;
+        if (lane == 0) {
+            if (total) start = atomicAdd(n_out_ptr, total);
+            if (md) sstart = atomicAdd(n_surv, (uint32_t)__popc(md));
+            if (MODE == SHADE_STAGE1) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        }
+        load_entry(i + warps_total * 32u);   // prefetch the next iteration's entry while the atomics are in flight
+        const uint32_t lt = (1u << lane) - 1u;
+        if (md) {
+            sstart = __shfl_sync(0xffffffffu, sstart, 0);
+            if (defer) surv[sstart + __popc(md & lt)] = my_pos;
         }
         if (total == 0) continue;   // warp-uniform
         start = __shfl_sync(0xffffffffu, start, 0);
-        uint32_t lt = (1u << lane) - 1u;
-        bool more1 = false, more2 = false;
-        uint32_t pos1 = start + __popc(m1 & lt), pos2 = start + __popc(m1) + __popc(m2 & lt);
+        const uint32_t pos1 = start + __popc(m1 & lt), pos2 = start + __popc(m1) + __popc(m2 & lt);
         if (n_out >= 1 && pos1 < out_capacity) {
             qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
             qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
             qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)slot));
             if (glass_branch) qo.d[pos1] = branch;
-            if (FUSE) more1 = stage1<GATE>(s, bl, ps.next, pos1, hits_out);
         }
-        if (FUSE) append_survivors(more1, pos1, surv, n_surv);
-        if (m2) {   // warp-uniform: glass branch mode only
-            if (n_out == 2 && pos2 < out_capacity) {
-                qo.a[pos2] = mk4(ps.next2.o.x, ps.next2.o.y, ps.next2.o.z, ps.next2.d.x);
-                qo.b[pos2] = make_float2(ps.next2.d.y, ps.next2.d.z);
-                qo.c[pos2] = mk4(ps.thr2.x, ps.thr2.y, ps.thr2.z, i2f((int)slot));
-                qo.d[pos2] = branch | (1u << (d & 31u));
-                if (FUSE) more2 = stage1<GATE>(s, bl, ps.next2, pos2, hits_out);
-            }
-            if (FUSE) append_survivors(more2, pos2, surv, n_surv);
+        if (n_out == 2 && pos2 < out_capacity) {   // glass branch mode only
+            qo.a[pos2] = mk4(ps.next2.o.x, ps.next2.o.y, ps.next2.o.z, ps.next2.d.x);
+            qo.b[pos2] = make_float2(ps.next2.d.y, ps.next2.d.z);
+            qo.c[pos2] = mk4(ps.thr2.x, ps.thr2.y, ps.thr2.z, i2f((int)slot));
+            qo.d[pos2] = branch | (1u << (d & 31u));
         }
     }
 }
