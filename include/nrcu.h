@@ -181,13 +181,21 @@ enum nrcu_glass_mode {
     NRCU_GLASS_BRANCH = 1      /* trace both branches like the reference (queue grows) */
 };
 
+/* nrcu_render_params.flags */
+enum nrcu_render_flags {
+    NRCU_FLAG_NEE = 1u << 0    /* EXTENSION (not in the reference, whose area lights are only hit by chance): next-event
+                                  estimation at Lambertian vertices - one shadow ray per diffuse bounce towards a uniformly
+                                  sampled point of an area light; same expectation as the reference's estimator, far
+                                  lower variance.  Ignored in RayCast mode. */
+};
+
 typedef struct nrcu_render_params {
     uint64_t seed;             /* counter-based RNG key; same seed => same image */
     uint32_t sample_begin;     /* global sample indices [sample_begin, sample_end) of samples_per_pixel */
     uint32_t sample_end;       /* 0,0 = all samples */
     uint32_t glass_mode;       /* nrcu_glass_mode */
     uint32_t samples_per_wave; /* 0 = choose automatically */
-    uint32_t flags;            /* reserved, 0 */
+    uint32_t flags;            /* nrcu_render_flags; 0 = the reference's estimator */
 } nrcu_render_params;
 
 typedef struct nrcu_stats {

@@ -13,6 +13,8 @@ import numpy as np
 
 from .flatscene import FlatScene, MODE_ACC, MODE_RAYCAST, MODE_SIMPLE  # noqa: F401
 
+FLAG_NEE = 1   # nrcu_render_flags.NRCU_FLAG_NEE
+
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libnrcuda.so")
 
@@ -141,16 +143,16 @@ class Context:
         return kind, data, mat
 
     @staticmethod
-    def _params(seed, s0, s1, glass_mode, samples_per_wave):
+    def _params(seed, s0, s1, glass_mode, samples_per_wave, flags=0):
         return NrcuRenderParams(seed=seed, sample_begin=s0, sample_end=s1, glass_mode=glass_mode,
-                                samples_per_wave=samples_per_wave, flags=0)
+                                samples_per_wave=samples_per_wave, flags=flags)
 
-    def render(self, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None):
+    def render(self, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None, flags=0):
         """Whole frame into HOST memory (what Screen::set takes). Returns (rgba[h,w,4], stats dict)."""
         if out is None:
             out = np.empty((self.height, self.width, 4), np.float32)
         assert out.dtype == np.float32 and out.size == self.width * self.height * 4 and out.flags.c_contiguous
-        p, st = self._params(seed, 0, 0, glass_mode, samples_per_wave), NrcuStats()
+        p, st = self._params(seed, 0, 0, glass_mode, samples_per_wave, flags), NrcuStats()
         self._check(self._lib.nrcu_render(self._h, C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render")
         return out, st.as_dict()
 
@@ -164,9 +166,9 @@ class Context:
                     "nrcu_render_progressive")
         return out, st.as_dict()
 
-    def render_accumulate(self, d_accum_ptr: int, s0=0, s1=0, seed=0, glass_mode=0, samples_per_wave=0, want_stats=True):
+    def render_accumulate(self, d_accum_ptr: int, s0=0, s1=0, seed=0, glass_mode=0, samples_per_wave=0, want_stats=True, flags=0):
         """Add linear sums of samples [s0,s1) into the DEVICE buffer at d_accum_ptr (w*h*4 floats)."""
-        p, st = self._params(seed, s0, s1, glass_mode, samples_per_wave), NrcuStats()
+        p, st = self._params(seed, s0, s1, glass_mode, samples_per_wave, flags), NrcuStats()
         self._check(self._lib.nrcu_render_accumulate(self._h, C.addressof(p), C.c_void_p(d_accum_ptr),
                                                      C.addressof(st) if want_stats else None), "nrcu_render_accumulate")
         return st.as_dict() if want_stats else None

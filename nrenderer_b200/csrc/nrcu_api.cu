@@ -80,7 +80,7 @@ struct nrcu_ctx {
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
     PrimSources ps{};
     // wavefront state
-    DevBuf qa[2], qb[2], qc[2], qd[2], hits, surv, L, counters, accum_own, rgba_dev, build_scratch;
+    DevBuf qa[2], qb[2], qc[2], qd[2], sa, sb, sc, sd, hits, surv, L, counters, accum_own, rgba_dev, build_scratch;
     uint32_t queue_capacity = 0, wave_slots = 0;
     unsigned long long* d_ray_counter = nullptr;   // inside `counters`
     // stats
@@ -422,7 +422,7 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
 // ---------------------------------------------------------------------------------------------
 enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
 
-static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth, bool branch_bits) {
+static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth, bool branch_bits, bool shadow_queue) {
     // The wave buffers are power-of-two sized (32 Mi x 16 B = 512 MiB) and the kernels stream through ten of
     // them at the same index; each buffer starts at its own skew inside its allocation so that the streams do
     // not share an HBM channel/bank phase (k_shade has been measured anywhere between 39 and 54 ms per 128 spp on
@@ -437,9 +437,13 @@ static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_
     }
     CTX_CUDA(ctx->hits.ensure(sizeof(float2) * (size_t)capacity));
     if (branch_bits) for (int k = 0; k < 2; k++) CTX_CUDA(ctx->qd[k].ensure(sizeof(uint32_t) * (size_t)capacity));
+    if (shadow_queue) {   // NEE: shadow rays of one bounce (ray, contribution + slot, light index)
+        CTX_CUDA(ctx->sa.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(ctx->sb.ensure(sizeof(float2) * (size_t)capacity));
+        CTX_CUDA(ctx->sc.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(ctx->sd.ensure(sizeof(uint32_t) * (size_t)capacity));
+    }
     CTX_CUDA(ctx->surv.ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(ctx->L.ensure(sizeof(f4) * (size_t)slots));
-    CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 3 * (size_t)depth + 12)));
+    CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 6 * (size_t)depth + 24)));
     ctx->queue_capacity = capacity; ctx->wave_slots = slots;
     return NRCU_OK;
 }
@@ -507,6 +511,8 @@ static cudaEvent_t pool_event(nrcu_ctx* ctx, size_t i) {
 }
 
 static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats) {
+    const bool nee = params && (params->flags & NRCU_FLAG_NEE) && ctx->ds.n_area_lights > 0;
+    ctx->ds.nee = nee ? 1 : 0;
     const DScene& ds = ctx->ds;
     const uint32_t npix = ds.width * ds.height;
     uint32_t s0 = params ? params->sample_begin : 0, s1 = params ? params->sample_end : 0;
@@ -524,7 +530,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     const uint32_t slots = k * npix;
     const uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
     int rc;
-    if ((rc = ensure_wave(ctx, slots, capacity, ds.depth, glass_branch != 0)) != NRCU_OK) return rc;
+    if ((rc = ensure_wave(ctx, slots, capacity, ds.depth, glass_branch != 0, nee)) != NRCU_OK) return rc;
     PathQueue q[2] = {{ctx->qa[0].as<f4>(), ctx->qb[0].as<float2>(), ctx->qc[0].as<f4>(), glass_branch ? ctx->qd[0].as<uint32_t>() : nullptr},
                       {ctx->qa[1].as<f4>(), ctx->qb[1].as<float2>(), ctx->qc[1].as<f4>(), glass_branch ? ctx->qd[1].as<uint32_t>() : nullptr}};
     uint32_t* cnt = ctx->counters.as<uint32_t>();
@@ -532,7 +538,12 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     uint32_t* d_qn = cnt + CNT_QUEUE0;                 // queue size entering bounce d
     uint32_t* d_fetch = cnt + CNT_QUEUE0 + ds.depth + 2;  // work-fetch cursor of bounce d
     uint32_t* d_nsurv = cnt + CNT_QUEUE0 + 2 * (ds.depth + 2);  // stage-1 survivors of bounce d
-    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 3 * (size_t)ds.depth + 12);
+    uint32_t* d_nshadow = cnt + CNT_QUEUE0 + 3 * (ds.depth + 2);   // NEE: shadow rays of bounce d, their fetch cursors and survivors
+    uint32_t* d_sfetch = cnt + CNT_QUEUE0 + 4 * (ds.depth + 2);
+    uint32_t* d_snsurv = cnt + CNT_QUEUE0 + 5 * (ds.depth + 2);
+    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 6 * (size_t)ds.depth + 24);
+    PathQueue qs{ctx->sa.as<f4>(), ctx->sb.as<float2>(), ctx->sc.as<f4>(), ctx->sd.as<uint32_t>()};
+    if (!nee) qs = PathQueue{nullptr, nullptr, nullptr, nullptr};
     cudaStream_t st = ctx->stream;
     const int sms = sm_count(ctx->device);
     const unsigned shade_grid = (unsigned)sms * NRCU_SHADE_MINB;
@@ -566,7 +577,8 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
 #undef NRCU_RAYGEN
         CTX_LAUNCH_CHECK("k_raygen");
         if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, fused ? 1 : 0}); ev_i += 2; }
-#define NRCU_SHADE(G, M) k_shade<G, M><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hb, qo, d_qn + d + 1, capacity, Lbuf, surv, d_nsurv + d, d_rays)
+#define NRCU_SHADE_N(G, M, N) k_shade<G, M, N><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hb, qo, d_qn + d + 1, capacity, Lbuf, surv, d_nsurv + d, d_rays, qs, d_nshadow + d)
+#define NRCU_SHADE(G, M) do { if (nee) NRCU_SHADE_N(G, M, true); else NRCU_SHADE_N(G, M, false); } while (0)
         for (uint32_t d = 0; d < ds.depth; d++) {
             PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
             const bool bvh = ds.root_ref != NRCU_REF_EMPTY;
@@ -606,9 +618,23 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
             if (glass_branch) {   // only the branching mode can outgrow the queue
                 k_clamp_count<<<1, 1, 0, st>>>(d_qn + d + 1, capacity, cnt + CNT_HIGH_WATER);
                 CTX_LAUNCH_CHECK("k_clamp_count");
+                if (nee) { k_clamp_count<<<1, 1, 0, st>>>(d_nshadow + d, capacity, cnt + CNT_HIGH_WATER); CTX_LAUNCH_CHECK("k_clamp_count"); }
+            }
+            if (nee && d + 1 < ds.depth) {   // the shadow rays of this bounce: same closest-hit kernels, then visibility + add
+                if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
+                int nl = 0;
+                if (gate) launch_closest_hit<true>(ctx, ds, qs, d_nshadow + d, hb, surv, d_snsurv + d, d_sfetch + d, d_rays, &nl);
+                else launch_closest_hit<false>(ctx, ds, qs, d_nshadow + d, hb, surv, d_snsurv + d, d_sfetch + d, d_rays, &nl);
+                ctx->launches += nl - 1;
+                CTX_LAUNCH_CHECK("k_big/k_trace (shadow)");
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
+                k_shadow_resolve<<<shade_grid, 256, 0, st>>>(ds, qs, d_nshadow + d, hb, Lbuf, glass_branch);
+                CTX_LAUNCH_CHECK("k_shadow_resolve");
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
             }
         }
 #undef NRCU_SHADE
+#undef NRCU_SHADE_N
         k_accumulate<<<grid_for(npix, 256), 256, 0, st>>>(ctx->L.as<f4>(), d_accum, npix, kw);
         CTX_LAUNCH_CHECK("k_accumulate");
     }

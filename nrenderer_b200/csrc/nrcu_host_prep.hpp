@@ -25,7 +25,7 @@ struct HostPrep {
     std::vector<uint32_t> src_a, src_b;      // primitive order: kind | entity << 2, mesh triangle index
     std::vector<uint32_t> mesh_nodes;        // entity of every MESH node in node order (one transform launch each)
     std::vector<DMaterial> materials;
-    std::vector<f4> lights;                  // 4 float4 per area light
+    std::vector<f4> lights;                  // NRCU_LIGHT_F4 float4 per area light
     DCamera cam;
     float mf_u1, mf_u2, mf_cos_phi, mf_sin_phi;
     float max_abs_coord;
@@ -109,14 +109,16 @@ inline std::string host_prepare(const nrcu_scene* sc, int mode, HostPrep& hp) {
         }
     }
     // area lights: quad record with n = cross(u,v) (xAreaLight, intersections.cpp:74-93) + radiance
-    hp.lights.assign(std::max(sc->n_area_lights, 1u) * 4, mk4(0, 0, 0, 0));
+    hp.lights.assign(std::max(sc->n_area_lights, 1u) * NRCU_LIGHT_F4, mk4(0, 0, 0, 0));
     for (uint32_t i = 0; i < sc->n_area_lights; i++) {
         vec3 u = ld3(sc->area_u + 3 * i), v = ld3(sc->area_v + 3 * i), p = ld3(sc->area_position + 3 * i), nn = cross(u, v);
         float r0[3], r1[3];
         quad_inverse_rows(u, v, r0, r1);
-        hp.lights[4 * i] = mk4(nn.x, nn.y, nn.z, p.x); hp.lights[4 * i + 1] = mk4(p.y, p.z, r0[0], r0[1]);
-        hp.lights[4 * i + 2] = mk4(r0[2], r1[0], r1[1], r1[2]);
-        hp.lights[4 * i + 3] = mk4(sc->area_radiance[3 * i], sc->area_radiance[3 * i + 1], sc->area_radiance[3 * i + 2], 0.f);
+        f4* Lr = &hp.lights[NRCU_LIGHT_F4 * (size_t)i];
+        Lr[0] = mk4(nn.x, nn.y, nn.z, p.x); Lr[1] = mk4(p.y, p.z, r0[0], r0[1]);
+        Lr[2] = mk4(r0[2], r1[0], r1[1], r1[2]);
+        Lr[3] = mk4(sc->area_radiance[3 * i], sc->area_radiance[3 * i + 1], sc->area_radiance[3 * i + 2], 0.f);
+        Lr[4] = mk4(u.x, u.y, u.z, 0.f); Lr[5] = mk4(v.x, v.y, v.z, 0.f);   // edges, for light sampling (NEE extension)
     }
     // Camera ctor (ray_cast/include/Camera.hpp:25-46): same libm tanf as the reference
     {

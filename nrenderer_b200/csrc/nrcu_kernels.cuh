@@ -397,11 +397,12 @@ enum { SHADE_ALL = 0, SHADE_STAGE1 = 1, SHADE_SURV = 2 };
 #ifndef NRCU_SHADE_MINB
 #define NRCU_SHADE_MINB 4
 #endif
-template <bool GATE, int MODE>
+template <bool GATE, int MODE, bool NEE>
 __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
                                               PathQueue qi, const uint32_t* n_in_ptr, float2* hits,
                                               PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L,
-                                              uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+                                              uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter,
+                                              PathQueue qs, uint32_t* n_shadow_ptr) {
     __shared__ BigList bl;
     if (MODE == SHADE_STAGE1) bl.load(s);
     const uint32_t n = MODE == SHADE_SURV ? *n_surv : *n_in_ptr;
@@ -428,7 +429,8 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
         if (i < n) {
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             vec3 thr = mk3(c.x, c.y, c.z);
-            slot = (uint32_t)f2i(c.w); branch = br;
+            slot = (uint32_t)f2i(c.w) & 0x7fffffffu; branch = br;
+            const bool skip_light = ((uint32_t)f2i(c.w) >> 31) != 0u;   // the previous vertex sent a shadow ray (NEE)
             if (MODE == SHADE_STAGE1) {
                 RayPrep rp = prep_ray(r);
                 float bt = NRCU_INF; int bi = -1;
@@ -439,9 +441,14 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
             }
             if (!defer) {
                 uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
-                ps = path_vertex(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch);
+                ps = path_vertex<NEE>(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch, skip_light);
                 if (ps.action == PATH_TERMINATE) {
-                    if (glass_branch) {   // several branches of one path share the slot
+                    if (NEE) {            // shadow rays of earlier bounces add to the same slot (k_shadow_resolve)
+                        if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
+                            if (glass_branch) { atomicAdd(&L[slot].x, ps.radiance.x); atomicAdd(&L[slot].y, ps.radiance.y); atomicAdd(&L[slot].z, ps.radiance.z); }
+                            else { f4 v = L[slot]; L[slot] = mk4(v.x + ps.radiance.x, v.y + ps.radiance.y, v.z + ps.radiance.z, 0.f); }
+                        }
+                    } else if (glass_branch) {   // several branches of one path share the slot
                         if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
                         if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
                         if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
@@ -463,6 +470,22 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
         }
         load_entry(i + warps_total * 32u);   // prefetch the next iteration's entry while the atomics are in flight
         const uint32_t lt = (1u << lane) - 1u;
+        if (NEE) {   // shadow rays of this bounce, compacted into their own queue
+            const bool sh = i < n && !defer && ps.nee;
+            const uint32_t ms = __ballot_sync(0xffffffffu, sh);
+            if (ms) {
+                uint32_t s0 = 0;
+                if (lane == 0) s0 = atomicAdd(n_shadow_ptr, (uint32_t)__popc(ms));
+                s0 = __shfl_sync(0xffffffffu, s0, 0);
+                const uint32_t sp = s0 + __popc(ms & lt);
+                if (sh && sp < out_capacity) {
+                    qs.a[sp] = mk4(ps.shadow.o.x, ps.shadow.o.y, ps.shadow.o.z, ps.shadow.d.x);
+                    qs.b[sp] = make_float2(ps.shadow.d.y, ps.shadow.d.z);
+                    qs.c[sp] = mk4(ps.nee_contrib.x, ps.nee_contrib.y, ps.nee_contrib.z, i2f((int)slot));
+                    qs.d[sp] = (uint32_t)ps.nee_light;
+                }
+            }
+        }
         if (md) {
             sstart = __shfl_sync(0xffffffffu, sstart, 0);
             if (defer) surv[sstart + __popc(md & lt)] = my_pos;
@@ -473,7 +496,7 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
         if (n_out >= 1 && pos1 < out_capacity) {
             qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
             qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
-            qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)slot));
+            qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)(slot | ((NEE && ps.next_skips_light) ? 0x80000000u : 0u))));
             if (glass_branch) qo.d[pos1] = branch;
         }
         if (n_out == 2 && pos2 < out_capacity) {   // glass branch mode only
@@ -481,6 +504,22 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
             qo.b[pos2] = make_float2(ps.next2.d.y, ps.next2.d.z);
             qo.c[pos2] = mk4(ps.thr2.x, ps.thr2.y, ps.thr2.z, i2f((int)slot));
             qo.d[pos2] = branch | (1u << (d & 31u));
+        }
+    }
+}
+
+// NEE: the shadow rays of one bounce after their closest-hit query - an unoccluded ray adds its contribution to
+// the radiance slot of its path (one shadow ray per path and bounce: plain read-modify-write; atomics when the glass
+// branches of a path share the slot).
+__global__ void __launch_bounds__(256) k_shadow_resolve(DScene s, PathQueue qs, const uint32_t* n_ptr, const float2* hits, f4* L, int glass_branch) {
+    const uint32_t n = *n_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        f4 a = qs.a[i], c = qs.c[i]; float2 b = qs.b[i], h = hits[i];
+        Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
+        if (nee_visible(s, r, (int)qs.d[i], h.x, __float_as_int(h.y))) {
+            const uint32_t slot = (uint32_t)f2i(c.w);
+            if (glass_branch) { atomicAdd(&L[slot].x, c.x); atomicAdd(&L[slot].y, c.y); atomicAdd(&L[slot].z, c.z); }   // branches share the slot
+            else { f4 v = L[slot]; L[slot] = mk4(v.x + c.x, v.y + c.y, v.z + c.z, 0.f); }
         }
     }
 }

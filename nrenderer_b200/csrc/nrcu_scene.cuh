@@ -81,6 +81,7 @@ struct DCamera {   // Camera ctor results, ray_cast/include/Camera.hpp:25-46
 // child ref encoding: >= 0 inner node index; < 0 leaf: ~ref = (first << 4) | (count - 1), count <= 16;
 // empty slots carry an inverted box (lo = +inf, hi = -inf) and are never entered.
 #define NRCU_REF_EMPTY 0x7fffffff
+#define NRCU_LIGHT_F4 6
 #define NRCU_MAX_BIG 32       // capacity of the wide-primitive list
 #ifndef NRCU_BIG_AREA_FRACTION
 #define NRCU_BIG_AREA_FRACTION 0.02f
@@ -112,7 +113,7 @@ struct DScene {
     // shading
     const DMaterial* materials;
     uint32_t n_materials;
-    const f4* area_lights;        // 4 float4 per light: quad record (as a plane with n = cross(u,v)) + radiance
+    const f4* area_lights;        // NRCU_LIGHT_F4 float4 per light: quad record (as a plane with n = cross(u,v)), radiance, u, v
     uint32_t n_area_lights;
     uint32_t n_point_lights;
     vec3 point_position, point_intensity;   // pointLightBuffer[0] (RayCastRenderer.cpp:41-42)
@@ -122,6 +123,7 @@ struct DScene {
     // Microfacet: the half-vector in the local frame is a constant because the reference reseeds
     // minstd_rand with 6 on every call (Microfacet.cpp:65-76); computed on the host with libm.
     float mf_u1, mf_u2, mf_cos_phi, mf_sin_phi;
+    int nee;                      // next-event estimation at Lambertian vertices (extension, NRCU_FLAG_NEE; off = reference estimator)
 };
 
 }  // namespace nrcu

@@ -111,17 +111,19 @@ NR_HD vec3 raycast_pixel(const DScene& s, uint32_t p, uint32_t* ray_count) {
 }
 
 // ---- path tracing ----------------------------------------------------------------------------
-// closestHitLight, AccPathTracer.cpp:101-112
-NR_HD float closest_light(const DScene& s, const Ray& r, vec3& radiance) {
+// closestHitLight, AccPathTracer.cpp:101-112 (+ the index of the light that was hit)
+NR_HD float closest_light(const DScene& s, const Ray& r, vec3& radiance, int* which = nullptr) {
     float closest = NRCU_INF;
     radiance = mk3(0.f);
+    if (which) *which = -1;
     for (uint32_t i = 0; i < s.n_area_lights; i++) {
-        const f4* L = s.area_lights + 4 * (size_t)i;
+        const f4* L = s.area_lights + NRCU_LIGHT_F4 * (size_t)i;
         float t;
         if (x_quad<false>(r, ldg4(L), ldg4(L + 1), ldg4(L + 2), (float)0.000001, closest, closest, t) && closest > t) {
             closest = t;
             f4 rad = ldg4(L + 3);
             radiance = mk3(rad.x, rad.y, rad.z);
+            if (which) *which = (int)i;
         }
     }
     return closest;
@@ -308,16 +310,73 @@ struct PathStep {
     vec3 radiance;      // thr * L to add to the pixel when the path ends here (may be zero)
     Ray next; vec3 thr; // continuation
     Ray next2; vec3 thr2; // second branch (PATH_SPLIT, glass branch mode)
+    // next-event estimation (extension): a shadow ray towards a sampled light point and what it adds if unoccluded
+    bool nee; Ray shadow; vec3 nee_contrib; int nee_light;
+    bool next_skips_light;   // the continuation weighs a light it hits with the MIS weight (its vertex also sent a shadow ray)
 };
+
+// Next-event estimation at a Lambertian vertex — NOT in the reference (area lights are only hit by
+// chance); an opt-in estimator with the SAME expectation.  The reference integrates (albedo/pi)(N.w) L_in(w) over the
+// hemisphere about N with pdf p_b = 1/(2 pi); the part of L_in that is light seen first along w can also be sampled
+// from the light's area (two-sided quad, xAreaLight accepts both faces) with solid-angle pdf
+// p_l(w) = r^2 / (|n_L.w| n_lights), n_L = u x v (length = area).  Both strategies are combined with the balance
+// heuristic (multiple importance sampling): the shadow ray carries f Le / (p_l + p_b), and a hemisphere sample that
+// finds the light is weighted by p_b / (p_b + p_l) at the next vertex (mis_light_weight).  Without the weights the
+// light of path_tracing_cornel.scn, 3 units under the ceiling, makes the 1/r^2 term explode.  V is evaluated by the
+// caller with the same closest-hit and closest-light queries the reference applies to any ray (so self-intersection
+// "acne" blocks the light exactly where it would have turned a hemisphere sample into a surface hit).
+#define NRCU_PDF_HEMISPHERE (1.0f / (2.0f * NRCU_PT_PI))
+NR_HD bool nee_sample(const DScene& s, vec3 albedo, vec3 hit_point, vec3 normal, vec3 thr, float e1, float e2, Ray& shadow, vec3& contrib, int& light) {
+    if (s.n_area_lights == 0) return false;
+    float fl = e1 * (float)s.n_area_lights;
+    int li = (int)fl; if (li > (int)s.n_area_lights - 1) li = (int)s.n_area_lights - 1;
+    float a = fl - (float)li;
+    const f4* L = s.area_lights + NRCU_LIGHT_F4 * (size_t)li;
+    f4 l0 = ldg4(L), l1 = ldg4(L + 1), rad = ldg4(L + 3), lu = ldg4(L + 4), lv = ldg4(L + 5);
+    vec3 nl = mk3(l0.x, l0.y, l0.z), p = mk3(l0.w, l1.x, l1.y);
+    vec3 y = p + mk3(lu.x, lu.y, lu.z) * a + mk3(lv.x, lv.y, lv.z) * e2;
+    vec3 wv = y - hit_point;
+    float r2 = dot(wv, wv);
+    if (!(r2 > 0.f)) return false;
+    vec3 w = wv * (1.0f / sqrtf(r2));
+    float cos_s = dot(normal, w);
+    float cl = fabsf(dot(nl, w));
+    if (!(cos_s > 0.f) || !(cl > 0.f)) return false;
+    float p_l = r2 / (cl * (float)s.n_area_lights);
+    vec3 f = (albedo / NRCU_PT_PI) * cos_s;
+    contrib = thr * f * mk3(rad.x, rad.y, rad.z) * (1.0f / (p_l + NRCU_PDF_HEMISPHERE));
+    if (is_zero(contrib)) return false;
+    shadow.o = hit_point; shadow.d = w; light = li;
+    return true;
+}
+// Balance-heuristic weight of a hemisphere sample that reached light `which` at distance tl along `ray`.
+NR_HD float mis_light_weight(const DScene& s, const Ray& ray, int which, float tl) {
+    f4 l0 = ldg4(s.area_lights + NRCU_LIGHT_F4 * (size_t)which);
+    float cl = fabsf(dot(mk3(l0.x, l0.y, l0.z), ray.d));
+    if (!(cl > 0.f)) return 1.f;
+    float p_l = tl * tl * dot(ray.d, ray.d) / (cl * (float)s.n_area_lights);
+    return NRCU_PDF_HEMISPHERE / (NRCU_PDF_HEMISPHERE + p_l);
+}
+// Visibility of the sampled light along the shadow ray, given the closest object hit (t_obj, id_obj): the light
+// counts iff it is the nearest light along the ray and no object is closer (AccPathTracer.cpp:128-130, 174-176).
+NR_HD bool nee_visible(const DScene& s, const Ray& shadow, int light, float t_obj, int id_obj) {
+    vec3 rad; int which;
+    float tl = closest_light(s, shadow, rad, &which);
+    if (which != light) return false;
+    return !(id_obj >= 0 && t_obj < tl);
+}
 
 // One iteration of trace() for a ray at bounce `d` (d < depth) whose closest object hit is
 // (t, id) — AccPathTracer.cpp:121-181.  `branch` = glass branch bits (RNG block).
+template <bool NEE = false>
 NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
-                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode) {
+                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode, bool skip_light = false) {
     PathStep ps; ps.action = PATH_TERMINATE; ps.radiance = mk3(0.f);
     ps.next = ray; ps.thr = thr; ps.next2 = ray; ps.thr2 = mk3(0.f);
+    ps.nee = false; ps.shadow = ray; ps.nee_contrib = mk3(0.f); ps.nee_light = -1; ps.next_skips_light = false;
     vec3 radiance;
-    float tl = closest_light(s, ray, radiance);
+    int which_light = -1;
+    float tl = closest_light(s, ray, radiance, NEE ? &which_light : nullptr);
     if (id >= 0 && t < tl) {
         vec3 hp = ray_at(ray, t);
         int material;
@@ -351,6 +410,12 @@ NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint3
             u32x4 rn = rng_block(seed, pixel, sample, d, branch);
             vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(rn.y), f);
             ps.thr = thr * f; ps.action = PATH_CONTINUE;
+            // NEE only where the continuation will really be traced: at the depth limit the reference returns the
+            // ambient colour without looking for the light (AccPathTracer.cpp:122)
+            if (NEE && d + 1 < s.depth) {
+                ps.nee = nee_sample(s, ld3(m.diffuse_color), hp, n, thr, u01(rn.z), u01(rn.w), ps.shadow, ps.nee_contrib, ps.nee_light);
+                ps.next_skips_light = true;
+            }
         }
         // the continuation would return ambient at the depth limit (AccPathTracer.cpp:122)
         if (ps.action != PATH_TERMINATE && d + 1 == s.depth) {
@@ -360,6 +425,7 @@ NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint3
         }
     } else if (tl != NRCU_INF) {
         ps.radiance = thr * radiance;
+        if (NEE && skip_light) ps.radiance = ps.radiance * mis_light_weight(s, ray, which_light, tl);
     } else if (s.env_rgba && s.mode == MODE_ACC) {
         ps.radiance = thr * env_lookup(s, ray.d);
     }

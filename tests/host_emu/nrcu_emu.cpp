@@ -188,11 +188,12 @@ void emu_render_raycast(EmuScene* es, float* rgba) {
 // Same dataflow as the wavefront kernels, one path at a time: raygen -> (trace -> shade)* ; paths
 // that split (glass branch mode) go through a small stack.  accum: w*h*4 (or n_pixels*4), sums + count.
 void emu_render_pt(EmuScene* es, uint64_t seed, uint32_t s0, uint32_t s1, int glass_branch,
-                   const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out) {
+                   const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out, uint32_t flags) {
+    es->ds.nee = (flags & NRCU_FLAG_NEE) && es->ds.n_area_lights > 0;
     const DScene& ds = es->ds;
     if (s0 == 0 && s1 == 0) s1 = es->spp;
     uint64_t rays = 0;
-    struct Work { Ray r; vec3 thr; uint32_t d, branch; };
+    struct Work { Ray r; vec3 thr; uint32_t d, branch; bool skip_light; };
     std::vector<Work> stack;
     uint32_t total = pixels ? n_pixels : ds.width * ds.height;
     for (uint32_t q = 0; q < total; q++) {
@@ -203,7 +204,7 @@ void emu_render_pt(EmuScene* es, uint64_t seed, uint32_t s0, uint32_t s1, int gl
             if (ds.depth == 0) L = ds.ambient;
             else {
                 stack.clear();
-                stack.push_back({pt_camera_ray(ds, seed, p, k), mk3(1.f), 0u, 0u});
+                stack.push_back({pt_camera_ray(ds, seed, p, k), mk3(1.f), 0u, 0u, false});
                 while (!stack.empty()) {
                     Work w = stack.back(); stack.pop_back();
                     for (;;) {
@@ -211,10 +212,17 @@ void emu_render_pt(EmuScene* es, uint64_t seed, uint32_t s0, uint32_t s1, int gl
                         LocalStack st;
                         if (ds.mode == MODE_ACC) closest_hit_bvh<true>(ds, w.r, st, t, id); else closest_hit_bvh<false>(ds, w.r, st, t, id);
                         rays++;
-                        PathStep ps = path_vertex(ds, seed, p, k, w.d, w.branch, w.r, w.thr, t, id, glass_branch);
+                        PathStep ps = ds.nee ? path_vertex<true>(ds, seed, p, k, w.d, w.branch, w.r, w.thr, t, id, glass_branch, w.skip_light)
+                                             : path_vertex<false>(ds, seed, p, k, w.d, w.branch, w.r, w.thr, t, id, glass_branch, false);
+                        if (ps.nee) {   // shadow ray: same closest-hit query, then visibility of the sampled light
+                            float st; int sid; LocalStack sst;
+                            if (ds.mode == MODE_ACC) closest_hit_bvh<true>(ds, ps.shadow, sst, st, sid); else closest_hit_bvh<false>(ds, ps.shadow, sst, st, sid);
+                            rays++;
+                            if (nee_visible(ds, ps.shadow, ps.nee_light, st, sid)) L = L + ps.nee_contrib;
+                        }
                         if (ps.action == PATH_TERMINATE) { L = L + ps.radiance; break; }
-                        if (ps.action == PATH_SPLIT) stack.push_back({ps.next2, ps.thr2, w.d + 1, w.branch | (1u << (w.d & 31u))});
-                        w.r = ps.next; w.thr = ps.thr; w.d++;
+                        if (ps.action == PATH_SPLIT) stack.push_back({ps.next2, ps.thr2, w.d + 1, w.branch | (1u << (w.d & 31u)), ps.next_skips_light});
+                        w.r = ps.next; w.thr = ps.thr; w.d++; w.skip_light = ps.next_skips_light;
                     }
                 }
             }

@@ -40,7 +40,7 @@ def lib():
         L.emu_bvh_stats.argtypes = [C.c_void_p] * 2
         L.emu_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_render_raycast.argtypes = [C.c_void_p, C.c_void_p]
-        L.emu_render_pt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.emu_render_pt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.emu_camera_ray.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
         L.emu_philox4x32.argtypes = [C.c_void_p] * 3
         _LIB = L
@@ -93,15 +93,15 @@ class EmuScene:
         lib().emu_render_raycast(self._h, out.ctypes.data)
         return out
 
-    def render_pt_accum(self, seed=0, s0=0, s1=0, glass_mode=0, pixels=None):
+    def render_pt_accum(self, seed=0, s0=0, s1=0, glass_mode=0, pixels=None, flags=0):
         rays = C.c_uint64(0)
         if pixels is None:
             acc = np.zeros((self.height, self.width, 4), np.float32)
-            lib().emu_render_pt(self._h, seed, s0, s1, glass_mode, None, 0, acc.ctypes.data, C.addressof(rays))
+            lib().emu_render_pt(self._h, seed, s0, s1, glass_mode, None, 0, acc.ctypes.data, C.addressof(rays), flags)
         else:
             pixels = np.ascontiguousarray(pixels, np.uint32)
             acc = np.zeros((len(pixels), 4), np.float32)
-            lib().emu_render_pt(self._h, seed, s0, s1, glass_mode, pixels.ctypes.data, len(pixels), acc.ctypes.data, C.addressof(rays))
+            lib().emu_render_pt(self._h, seed, s0, s1, glass_mode, pixels.ctypes.data, len(pixels), acc.ctypes.data, C.addressof(rays), flags)
         return acc, rays.value
 
     def camera_ray(self, seed, pixel, sample):

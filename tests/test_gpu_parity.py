@@ -172,8 +172,9 @@ REF_CASES = ["simple_cornell_d4", "acc_cornell_d20", "acc_bunny5k_d20", "acc_gol
 EDITS = {"acc_glass_d6": glassify, "acc_microfacet_d8": microfacet}
 
 
-@pytest.mark.parametrize("case", REF_CASES)
-def test_path_tracer_matches_reference_statistics(ctx, case):
+@pytest.mark.parametrize("case,flags", [(c, 0) for c in REF_CASES] + [("simple_cornell_d4", 1), ("acc_cornell_d20", 1), ("acc_bunny5k_d20", 1), ("acc_gold_d20", 1)])
+def test_path_tracer_matches_reference_statistics(ctx, case, flags):
+    """flags = 1: the next-event-estimation extension must reproduce the reference's image too (same expectation)."""
     ref = np.load(os.path.join(GOLDEN, f"pt_ref_{case}.npz"))
     w, h, depth, mode = int(ref["width"]), int(ref["height"]), int(ref["depth"]), int(ref["mode"])
     slices, spp_slice = 8, 512
@@ -183,7 +184,7 @@ def test_path_tracer_matches_reference_statistics(ctx, case):
     ctx.upload(fs, mode)
     means = []
     for k in range(slices):   # independent sample slices -> per-pixel standard error of our estimate
-        a, _ = accum_device(ctx, s0=k * spp_slice, s1=(k + 1) * spp_slice, seed=3)
+        a, _ = accum_device(ctx, s0=k * spp_slice, s1=(k + 1) * spp_slice, seed=3, flags=flags)
         means.append(a[..., :3].astype(np.float64) / a[..., 3:4])
     means = np.stack(means)
     mine, sem = means.mean(0), means.std(0, ddof=1) / np.sqrt(slices)
@@ -197,12 +198,14 @@ def test_path_tracer_matches_reference_statistics(ctx, case):
     z = (mine - rmean)[valid] / np.sqrt(sem[valid] ** 2 + rsem[valid] ** 2 + 1e-12)
     rmse = np.sqrt(((mine - rmean)[valid] ** 2).mean())
     expected_rmse = np.sqrt((sem[valid] ** 2 + rsem[valid] ** 2).mean())
-    print(f"{case}: mean {gm:.5f} vs reference {gr:.5f} (diff {gm - gr:+.5f}, 5 sigma = {5 * sigma_mean:.5f}); "
+    print(f"{case} flags {flags}: mean {gm:.5f} vs reference {gr:.5f} (diff {gm - gr:+.5f}, 5 sigma = {5 * sigma_mean:.5f}); "
           f"rmse {rmse:.5f} vs noise {expected_rmse:.5f}; median |z| {np.median(np.abs(z)):.3f}; |z|>5: {(np.abs(z) > 5).mean() * 100:.3f}%")
     assert abs(gm - gr) <= 5 * sigma_mean + 0.01 * gr
     assert rmse <= 1.5 * expected_rmse
     assert np.median(np.abs(z)) < 1.0          # a unit normal has median |z| = 0.674
-    assert (np.abs(z) > 5).mean() < 0.01
+    # with NEE our own noise all but vanishes and z is the reference's error over ITS standard error estimated from 8 runs
+    # of a heavy-tailed estimator (a Student t with 7 degrees of freedom at best): more outliers by construction
+    assert (np.abs(z) > 5).mean() < (0.03 if flags else 0.01)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -364,3 +367,30 @@ def test_progressive_updates_converge_to_the_one_shot_frame(ctx):
     ctx.render_progressive(lambda frame, done, total: part.append((done, frame.copy())) or True, samples_per_update=10, seed=2)
     assert len(part) == 1 and part[0][0] == 10
     np.testing.assert_allclose(part[0][1], seen[0][2], rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,mode,depth,glass,edit", [("path_tracing_cornel", 1, 5, 0, None), ("bunny5k_cornel", 2, 12, 0, None),
+                                                        ("pt_glass", 2, 8, 0, None), ("pt_glass", 2, 6, 1, glassify)])
+def test_next_event_estimation_matches_host_emulation_same_rng(ctx, name, mode, depth, glass, edit):
+    """The NEE extension has no reference; the kernels are checked against the CPU emulation of the same device code."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+    import pyemu
+    fs = load_scene(name, width=48, height=40, samples_per_pixel=12, depth=depth)
+    if edit:
+        edit(fs)
+    ctx.upload(fs, mode)
+    acc, st = accum_device(ctx, seed=17, glass_mode=glass, flags=1, samples_per_wave=5)
+    eacc, erays = pyemu.EmuScene(fs, mode).render_pt_accum(seed=17, glass_mode=glass, flags=1)
+    rel = np.abs(acc[..., :3] - eacc[..., :3]) / np.maximum(np.abs(eacc[..., :3]), 1e-3)
+    close = (rel < 1e-3).all(-1)
+    print(f"NEE {name} m{mode} g{glass}: {close.mean() * 100:.2f}% pixels within 1e-3, rays {st['rays']} vs {erays}")
+    assert close.mean() >= 0.99 and abs(st["rays"] - erays) <= 2e-3 * erays + 2
+    plain, st0 = accum_device(ctx, seed=17, glass_mode=glass)
+    assert st["rays"] > st0["rays"]                       # shadow rays are counted
+    again, _ = accum_device(ctx, seed=17, glass_mode=glass, flags=1)
+    if glass == 0:   # branches of one path add to their shared slot with float atomics: order, hence the last bits, may vary
+        assert np.array_equal(acc.view(np.uint32), again.view(np.uint32))
+    else:
+        np.testing.assert_allclose(again, acc, rtol=1e-5, atol=1e-6)

@@ -100,3 +100,29 @@ def test_rejects_broken_scenes():
     fs.plane_material[0] = 77
     with pytest.raises(ValueError, match="material"):
         pyemu.EmuScene(fs, 2)
+
+
+def _slice_means(emu, n_slices, spp, **kw):
+    """Image-mean radiance of independent sample slices (linear space)."""
+    out = []
+    for k in range(n_slices):
+        a, _ = emu.render_pt_accum(seed=9, s0=k * spp, s1=(k + 1) * spp, **kw)
+        out.append((a[..., :3] / a[..., 3:4]).mean())
+    return np.array(out)
+
+
+@pytest.mark.parametrize("name,mode,depth", [("path_tracing_cornel", 2, 6), ("path_tracing_cornel", 1, 3), ("bunny200_cornel", 2, 5)])
+def test_next_event_estimation_keeps_the_expectation(name, mode, depth):
+    """NRCU_FLAG_NEE is an extension (the reference only hits lights by chance): same mean, far lower variance."""
+    fs = load_scene(name, width=20, height=20, samples_per_pixel=16 * 96, depth=depth)
+    e = pyemu.EmuScene(fs, mode)
+    plain = _slice_means(e, 16, 96)
+    nee = _slice_means(e, 16, 96, flags=1)
+    sem = np.sqrt(plain.var(ddof=1) / len(plain) + nee.var(ddof=1) / len(nee))
+    print(f"{name} m{mode}: plain {plain.mean():.5f} +- {plain.std(ddof=1) / 4:.5f}, NEE {nee.mean():.5f} +- {nee.std(ddof=1) / 4:.5f}")
+    assert abs(plain.mean() - nee.mean()) < 4.5 * sem + 1e-4
+    assert nee.std(ddof=1) < 0.75 * plain.std(ddof=1)         # lower variance even for the image mean (per pixel far more)
+    # flags = 0 is bit-identical to the estimator without the extension compiled in
+    a0, r0 = e.render_pt_accum(seed=3, s0=0, s1=4)
+    a1, r1 = e.render_pt_accum(seed=3, s0=0, s1=4, flags=0)
+    assert np.array_equal(a0, a1) and r0 == r1

@@ -39,7 +39,7 @@ uint32_t emu_ray_work(EmuScene* es, uint64_t seed, const uint32_t* pixels, uint3
             float t; int id, nn, nl, np;
             if (ds.mode == MODE_ACC) traverse_count<true>(ds, p.r, t, id, nn, nl, np); else traverse_count<false>(ds, p.r, t, id, nn, nl, np);
             if (k < cap) { out[4 * k] = (int)d; out[4 * k + 1] = nn; out[4 * k + 2] = nl; out[4 * k + 3] = np; k++; }
-            PathStep ps = path_vertex(ds, seed, p.pixel, sample, d, 0, p.r, p.thr, t, id, 0);
+            PathStep ps = path_vertex(ds, seed, p.pixel, sample, d, 0, p.r, p.thr, t, id, 0, false);
             if (ps.action == PATH_CONTINUE) nxt.push_back({ps.next, ps.thr, p.pixel});
         }
         cur.swap(nxt);
