@@ -289,7 +289,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     // Build scratch comes from ONE arena that lives in the context and only ever grows: cudaMalloc/cudaFree per
     // upload cost 5 ms in the good case and hundreds of ms when gigabytes of wave buffers are mapped (measured).
     Sub prim_node, nbox, cbox, ncount, nidmin, nidmax, nstate, nchild, nsplit_axis, nsplit_pos, ndepth, nleaf_first, nleaf_fill,
-        nwide, bins, counters, nbin_slot, wide_tmp, big_count;
+        nwide, bins, counters, nbin_slot, wide_tmp, big_count, big_cand;
     Sub* per_node[] = {&ncount, &nidmin, &nidmax, &nstate, &nchild, &nsplit_axis, &nsplit_pos, &ndepth, &nleaf_first, &nleaf_fill, &nwide, &nbin_slot};
     for (int pass = 0; pass < 2; pass++) {   // pass 0 sizes the arena, pass 1 hands out the pointers
         Carve cv{pass ? ctx->build_scratch.as<char>() : nullptr, 0};
@@ -297,7 +297,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
         nbox.p = cv.take(sizeof(int) * 6 * (size_t)cap); cbox.p = cv.take(sizeof(int) * 6 * (size_t)cap);
         for (Sub* b : per_node) b->p = cv.take(sizeof(int) * (size_t)cap);
         bins.p = cv.take(sizeof(int) * (size_t)bin_nodes * 3 * NRCU_NBINS * NRCU_BIN_WORDS);
-        counters.p = cv.take(sizeof(int) * 8); big_count.p = cv.take(sizeof(int));
+        counters.p = cv.take(sizeof(int) * 8); big_count.p = cv.take(sizeof(int) * 2); big_cand.p = cv.take(sizeof(int) * NRCU_BIG_CAND_CAP);
         wide_tmp.p = cv.take(sizeof(f4) * NRCU_BVH_NODE_F4 * (size_t)std::max(1u, n));
         if (pass == 0) CTX_CUDA(ctx->build_scratch.ensure(cv.off));
     }
@@ -318,6 +318,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     b.leaf_prims = ctx->leaf_prims.as<uint32_t>(); b.wide_nodes = wide_tmp.as<f4>();
     b.prim_geom = ctx->prim_geom.as<f4>(); b.leaf_geom = ctx->leaf_geom.as<f4>(); b.leaf_box = ctx->leaf_box.as<f4>();
     b.big_geom = ctx->big_geom.as<f4>(); b.big_box = ctx->big_box.as<f4>(); b.big_bound = ctx->big_bound.as<f4>(); b.big_meta = ctx->big_meta.as<uint32_t>(); b.big_count = big_count.as<int>();
+    b.big_cand = big_cand.as<int>(); b.big_cand_count = big_count.as<int>() + 1;
     b.inflate = max_abs_coord * (1.0f / 65536.0f);
     cudaStream_t st = ctx->stream;
     const int T = 128;
@@ -327,6 +328,8 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     k_bvh_clear<<<grid_for(cap, T), T, 0, st>>>(b, 0, cap); CTX_LAUNCH_CHECK("k_bvh_clear");
     k_bvh_init_prim<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_init_prim");
     // wide primitives leave the tree; node 0 is rebuilt from the rest
+    CTX_CUDA(cudaMemsetAsync(big_count.p, 0, 2 * sizeof(int), st));
+    k_bvh_big_candidate<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_big_candidate");
     k_bvh_select_big<<<1, 1, 0, st>>>(b, 0, 1); CTX_LAUNCH_CHECK("k_bvh_select_big");
     k_bvh_clear<<<1, 1, 0, st>>>(b, 0, 1); CTX_LAUNCH_CHECK("k_bvh_clear");
     k_bvh_init_prim_rest<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_init_prim_rest");

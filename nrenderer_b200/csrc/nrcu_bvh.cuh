@@ -85,6 +85,8 @@ struct BvhBuild {
     // wide-primitive list (outputs of bvh_select_big)
     f4* big_geom; f4* big_box; f4* big_bound; uint32_t* big_meta;   // capacity NRCU_MAX_BIG; big_bound = padded true bounds
     int* big_count;            // [1]
+    int* big_cand;             // [NRCU_BIG_CAND_CAP] ids whose box is large enough (unordered), filled by bvh_big_candidate
+    int* big_cand_count;       // [1]
     f4* wide_nodes;            // [wide capacity * 7]
     float inflate;             // absolute padding of wide-node boxes
 };
@@ -125,11 +127,22 @@ NR_HD float box_half_area(f4 lo, f4 hi) {
     float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
     return dx * dy + dy * dz + dz * dx;
 }
-// step 0b (ONE work item, after step 0 has produced the scene box in node 0): pick the "wide" primitives — box
+// step 0b (ONE work item, after steps 0 and 0a): pick the "wide" primitives — box
 // surface area >= NRCU_BIG_AREA_FRACTION of the scene box's, the NRCU_MAX_BIG largest if there are more (ties to
 // the lower id) — copy their records to the wide list in ascending id order and mark them excluded from the BVH.
 // A primitive this large is entered by most rays whatever the tree looks like (its SAH probability is ~1), so it
 // is cheaper to test it once per ray in a warp-uniform loop than to let it bloat the boxes of the top BVH levels.
+#define NRCU_BIG_CAND_CAP 1024
+// step 0a (per primitive, after step 0): collect the ids whose box is large enough, in any order
+NR_HD void bvh_big_candidate(const BvhBuild& b, int i) {
+    float rlo[3], rhi[3];
+    for (int a = 0; a < 3; a++) { rlo[a] = fkey_inv(b.nbox[a]); rhi[a] = fkey_inv(b.nbox[3 + a]); }
+    const float root_area = half_area(rlo, rhi);
+    if (!(root_area > 0.f && root_area < NRCU_INF)) return;
+    if (!(box_half_area(b.prim_bound[2 * i], b.prim_bound[2 * i + 1]) >= NRCU_BIG_AREA_FRACTION * root_area)) return;
+    int k = atomic_add_i(b.big_cand_count, 1);
+    if (k < NRCU_BIG_CAND_CAP) b.big_cand[k] = i;
+}
 NR_HD void bvh_select_big(const BvhBuild& b, int) {
     float rlo[3], rhi[3];
     for (int a = 0; a < 3; a++) { rlo[a] = fkey_inv(b.nbox[a]); rhi[a] = fkey_inv(b.nbox[3 + a]); }
@@ -137,12 +150,17 @@ NR_HD void bvh_select_big(const BvhBuild& b, int) {
     int ids[NRCU_MAX_BIG]; float areas[NRCU_MAX_BIG]; int cnt = 0;
     if (root_area > 0.f && root_area < NRCU_INF) {
         const float thr = NRCU_BIG_AREA_FRACTION * root_area;
-        for (int i = 0; i < (int)b.n_prims; i++) {
+        // the candidate list (any order) when it did not overflow, else every primitive; the selection is a total
+        // order (area descending, id ascending), so the result does not depend on the order of the candidates
+        const int n_cand = *b.big_cand_count;
+        const bool listed = n_cand <= NRCU_BIG_CAND_CAP;
+        const int n_scan = listed ? n_cand : (int)b.n_prims;
+        for (int q = 0; q < n_scan; q++) {
+            const int i = listed ? b.big_cand[q] : q;
             float ar = box_half_area(b.prim_bound[2 * i], b.prim_bound[2 * i + 1]);
             if (!(ar >= thr)) continue;
-            // keep the list sorted by (area desc, id asc); drop the smallest when full
             int pos = cnt;
-            while (pos > 0 && areas[pos - 1] < ar) pos--;
+            while (pos > 0 && (areas[pos - 1] < ar || (areas[pos - 1] == ar && ids[pos - 1] > i))) pos--;
             if (pos >= NRCU_MAX_BIG) continue;
             int last = cnt < NRCU_MAX_BIG ? cnt : NRCU_MAX_BIG - 1;
             for (int k = last; k > pos; k--) { ids[k] = ids[k - 1]; areas[k] = areas[k - 1]; }

@@ -29,6 +29,7 @@ __global__ void k_build_prims(PrimSources ps, uint32_t n, int raycast, f4* geom,
         int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= count) return; body(b, first + i); }
 NRCU_STEP_KERNEL(k_bvh_clear, node_clear)
 NRCU_STEP_KERNEL(k_bvh_init_prim, bvh_init_prim)
+NRCU_STEP_KERNEL(k_bvh_big_candidate, bvh_big_candidate)
 NRCU_STEP_KERNEL(k_bvh_select_big, bvh_select_big)
 NRCU_STEP_KERNEL(k_bvh_init_prim_rest, bvh_init_prim_rest)
 NRCU_STEP_KERNEL(k_bvh_level_prepare, bvh_level_prepare)

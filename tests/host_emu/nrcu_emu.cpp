@@ -61,6 +61,9 @@ static void emu_build_bvh(EmuScene& es) {
     counters[0] = 1;
     for (int i = 0; i < cap; i++) node_clear(b, i);
     for (uint32_t i = 0; i < n; i++) bvh_init_prim(b, (int)i);
+    std::vector<int> big_cand(NRCU_BIG_CAND_CAP); int big_cand_count = 0;
+    b.big_cand = big_cand.data(); b.big_cand_count = &big_cand_count;
+    for (uint32_t i = 0; i < n; i++) bvh_big_candidate(b, (int)i);
     bvh_select_big(b, 0);
     node_clear(b, 0);
     for (uint32_t i = 0; i < n; i++) bvh_init_prim_rest(b, (int)i);
