@@ -256,8 +256,11 @@ __device__ __forceinline__ bool fetch_ray(const DScene& s, const PathQueue& q, c
 // v2: persistent threads, "while-while" traversal and lane refill.  Every lane keeps one ray's traversal state
 // in registers; when at least `refill` lanes of the warp are idle (or all of them) the warp claims that many new
 // rays.  Leaf work is postponed until every active lane has reached a leaf (Aila & Laine's while-while).
+#ifndef NRCU_TRACE_MINB
+#define NRCU_TRACE_MINB 1
+#endif
 template <bool GATE, bool IFIF>
-__global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace2(DScene s, PathQueue q, const uint32_t* n_ptr, const uint32_t* surv, float2* hits,
+__global__ void __launch_bounds__(NRCU_TRACE_THREADS, NRCU_TRACE_MINB) k_trace2(DScene s, PathQueue q, const uint32_t* n_ptr, const uint32_t* surv, float2* hits,
                                                                uint32_t* fetch, unsigned long long* ray_counter, uint32_t refill) {
     __shared__ uint2 stack_mem[NRCU_T3_STACK * NRCU_TRACE_THREADS];
     const uint32_t n = *n_ptr;
