@@ -209,7 +209,7 @@ typedef struct nrcu_stats {
     uint32_t bvh_nodes;        /* wide nodes */
     uint32_t n_primitives;     /* primitives after mesh flattening */
     uint32_t max_queue;        /* high-water mark of the ray queue */
-    float ms_fused;            /* time inside k_shade<SHADE_STAGE1>: stage 1 of the closest hit + shading of the rays that end there */
+    float ms_fused;            /* reserved (0) */
 } nrcu_stats;
 
 /* --- lifetime ------------------------------------------------------------------------- */

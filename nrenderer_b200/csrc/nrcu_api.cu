@@ -64,6 +64,7 @@ struct Sub { void* p = nullptr; template <typename T> T* as() const { return rei
 
 }  // namespace
 
+#define NRCU_MAX_WAVES 4
 struct nrcu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -80,9 +81,11 @@ struct nrcu_ctx {
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
     PrimSources ps{};
     // wavefront state
-    DevBuf qa[2], qb[2], qc[2], qd[2], sa, sb, sc, sd, hits, surv, L, counters, accum_own, rgba_dev, build_scratch;
-    uint32_t queue_capacity = 0, wave_slots = 0;
-    unsigned long long* d_ray_counter = nullptr;   // inside `counters`
+    // wavefront state: one set per concurrent wave (NRCU_WAVES waves run side by side, each on its own stream)
+    struct WaveSet { DevBuf qa[2], qb[2], qc[2], qd[2], sa, sb, sc, sd, hits, surv, L, counters; } ws[NRCU_MAX_WAVES];
+    cudaStream_t extra_stream[NRCU_MAX_WAVES] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused: wave 0 runs on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_acc = nullptr;
+    DevBuf accum_own, rgba_dev, build_scratch;
     // stats
     float ms_setup = 0.f;
     uint32_t bvh_nodes = 0, n_big = 0;
@@ -162,6 +165,10 @@ int nrcu_destroy(nrcu_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_acc) cudaEventDestroy(ctx->ev_acc);
+    for (auto& xs : ctx->extra_stream) if (xs) { cudaStreamSynchronize(xs); cudaStreamDestroy(xs); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return NRCU_OK;
@@ -425,29 +432,29 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
 // ---------------------------------------------------------------------------------------------
 enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
 
-static int ensure_wave(nrcu_ctx* ctx, uint32_t slots, uint32_t capacity, uint32_t depth, bool branch_bits, bool shadow_queue) {
+static int ensure_wave(nrcu_ctx* ctx, int set, uint32_t slots, uint32_t capacity, uint32_t depth, bool branch_bits, bool shadow_queue) {
     // The wave buffers are power-of-two sized (32 Mi x 16 B = 512 MiB) and the kernels stream through ten of
     // them at the same index; each buffer starts at its own skew inside its allocation so that the streams do
     // not share an HBM channel/bank phase (k_shade has been measured anywhere between 39 and 54 ms per 128 spp on
     // different boxes with identical code; the skew did not change that, it is kept as a cheap precaution).
+    nrcu_ctx::WaveSet& w = ctx->ws[set];
     const size_t S = (size_t)wave_skew_kb() << 10;
-    DevBuf* bufs[] = {&ctx->qa[0], &ctx->qb[0], &ctx->qc[0], &ctx->qa[1], &ctx->qb[1], &ctx->qc[1], &ctx->hits, &ctx->surv, &ctx->L};
-    for (size_t j = 0; j < sizeof(bufs) / sizeof(bufs[0]); j++) bufs[j]->skew = (j + 1) * S;
+    DevBuf* bufs[] = {&w.qa[0], &w.qb[0], &w.qc[0], &w.qa[1], &w.qb[1], &w.qc[1], &w.hits, &w.surv, &w.L};
+    for (size_t j = 0; j < sizeof(bufs) / sizeof(bufs[0]); j++) bufs[j]->skew = (j + 1 + 9 * (size_t)set) * S;
     for (int k = 0; k < 2; k++) {
-        CTX_CUDA(ctx->qa[k].ensure(sizeof(f4) * (size_t)capacity));
-        CTX_CUDA(ctx->qb[k].ensure(sizeof(float2) * (size_t)capacity));
-        CTX_CUDA(ctx->qc[k].ensure(sizeof(f4) * (size_t)capacity));
+        CTX_CUDA(w.qa[k].ensure(sizeof(f4) * (size_t)capacity));
+        CTX_CUDA(w.qb[k].ensure(sizeof(float2) * (size_t)capacity));
+        CTX_CUDA(w.qc[k].ensure(sizeof(f4) * (size_t)capacity));
     }
-    CTX_CUDA(ctx->hits.ensure(sizeof(float2) * (size_t)capacity));
-    if (branch_bits) for (int k = 0; k < 2; k++) CTX_CUDA(ctx->qd[k].ensure(sizeof(uint32_t) * (size_t)capacity));
+    CTX_CUDA(w.hits.ensure(sizeof(float2) * (size_t)capacity));
+    if (branch_bits) for (int k = 0; k < 2; k++) CTX_CUDA(w.qd[k].ensure(sizeof(uint32_t) * (size_t)capacity));
     if (shadow_queue) {   // NEE: shadow rays of one bounce (ray, contribution + slot, light index)
-        CTX_CUDA(ctx->sa.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(ctx->sb.ensure(sizeof(float2) * (size_t)capacity));
-        CTX_CUDA(ctx->sc.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(ctx->sd.ensure(sizeof(uint32_t) * (size_t)capacity));
+        CTX_CUDA(w.sa.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(w.sb.ensure(sizeof(float2) * (size_t)capacity));
+        CTX_CUDA(w.sc.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(w.sd.ensure(sizeof(uint32_t) * (size_t)capacity));
     }
-    CTX_CUDA(ctx->surv.ensure(sizeof(uint32_t) * (size_t)capacity));
-    CTX_CUDA(ctx->L.ensure(sizeof(f4) * (size_t)slots));
-    CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 6 * (size_t)depth + 24)));
-    ctx->queue_capacity = capacity; ctx->wave_slots = slots;
+    CTX_CUDA(w.surv.ensure(sizeof(uint32_t) * (size_t)capacity));
+    CTX_CUDA(w.L.ensure(sizeof(f4) * (size_t)slots));
+    CTX_CUDA(w.counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 6 * (size_t)depth + 24)));
     return NRCU_OK;
 }
 
@@ -466,8 +473,7 @@ static int sm_count(int device) {
 // first, batch-of-32 kernel kept for A/B measurements).
 static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
-static bool pipeline_fused() { static uint32_t v = env_u32("NRCU_PIPELINE", 0); return v != 0; }
-static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 32) << 20; return v; }
+static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 128) << 20; return v; }
 static uint32_t trace_taper(int k) {
     static uint32_t v[2] = {0xffffffffu, 0xffffffffu}; static bool init = false;
     if (!init) { init = true; const char* e = std::getenv("NRCU_TRACE_TAPER"); unsigned a = 0xffffffffu, b = 0xffffffffu; if (e) std::sscanf(e, "%u,%u", &a, &b); v[0] = a; v[1] = b; }
@@ -477,32 +483,38 @@ static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE",
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
 
+static int concurrent_waves() { static uint32_t v = env_u32("NRCU_WAVES", 2); return (int)std::min<uint32_t>(std::max<uint32_t>(v, 1), NRCU_MAX_WAVES); }
+// CTAs per SM of each kernel when two waves share the machine (tuning knobs)
+static unsigned dual_big() { static uint32_t v = env_u32("NRCU_DUAL_BIG", 8); return v ? v : 1; }
+static unsigned dual_shade() { static uint32_t v = env_u32("NRCU_DUAL_SHADE", 4); return v ? v : 1; }
+static unsigned dual_trace() { static uint32_t v = env_u32("NRCU_DUAL_TRACE", 8); return v ? v : 1; }
+
 // Stage 2 of the closest hit: BVH traversal of the *n_surv rays listed in `surv`, refining hits[] in place.
 template <bool GATE>
-static void launch_stage2(nrcu_ctx* ctx, const DScene& ds, PathQueue q, float2* hits, const uint32_t* surv, const uint32_t* n_surv,
+static void launch_stage2(nrcu_ctx* ctx, cudaStream_t st, unsigned share, const DScene& ds, PathQueue q, float2* hits, const uint32_t* surv, const uint32_t* n_surv,
                           uint32_t* fetch, unsigned long long* rays, uint32_t bounce = 0) {
     // Deep bounces hold few rays; a smaller persistent grid has a lower latency floor (fewer CTAs to start,
     // fewer warps contending for the fetch counter) - measured: it does not, smaller grids are simply slower (6,12: -5 %),
     // so tapering is off by default.  NRCU_TRACE_TAPER="a,b" halves the grid from bounce a and again from b.
-    unsigned per_sm = trace_blocks_per_sm();
+    unsigned per_sm = share > 1 ? dual_trace() : trace_blocks_per_sm();   // share = 2: two waves run side by side, about half an SM each
     if (bounce >= trace_taper(0)) per_sm = std::max(1u, per_sm / 2);
     if (bounce >= trace_taper(1)) per_sm = std::max(1u, per_sm / 2);
     const unsigned grid = (unsigned)sm_count(ctx->device) * per_sm;
-    if (trace_variant() == 3) k_trace3<GATE><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill(), trace_w_node(), trace_w_prim());
-    else if (trace_variant() == 4) k_trace2<GATE, true><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
-    else k_trace2<GATE, false><<<grid, NRCU_TRACE_THREADS, 0, ctx->stream>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
+    if (trace_variant() == 3) k_trace3<GATE><<<grid, NRCU_TRACE_THREADS, 0, st>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill(), trace_w_node(), trace_w_prim());
+    else if (trace_variant() == 4) k_trace2<GATE, true><<<grid, NRCU_TRACE_THREADS, 0, st>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
+    else k_trace2<GATE, false><<<grid, NRCU_TRACE_THREADS, 0, st>>>(ds, q, n_surv, surv, hits, fetch, rays, trace_refill());
 }
 
 // Closest hit for the first *n_ptr entries of queue `q` into hits[] (the stand-alone form used by
 // nrcu_trace_batch; the renderer fuses stage 1 into the kernels that generate the rays): stage 1 (wide
 // primitives, every ray) then stage 2 (BVH traversal of the survivors).
 template <bool GATE>
-static void launch_closest_hit(nrcu_ctx* ctx, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* surv,
+static void launch_closest_hit(nrcu_ctx* ctx, cudaStream_t st, unsigned share, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* surv,
                                uint32_t* n_surv, uint32_t* fetch, unsigned long long* rays, int* launches) {
-    k_big<GATE><<<(unsigned)sm_count(ctx->device) * 8, 256, 0, ctx->stream>>>(ds, q, n_ptr, hits, surv, n_surv, rays);
+    k_big<GATE><<<(unsigned)sm_count(ctx->device) * (share > 1 ? dual_big() : 8), 256, 0, st>>>(ds, q, n_ptr, hits, surv, n_surv, rays);
     (*launches)++;
     if (ds.root_ref == NRCU_REF_EMPTY) return;
-    launch_stage2<GATE>(ctx, ds, q, hits, surv, n_surv, fetch, rays);
+    launch_stage2<GATE>(ctx, st, share, ds, q, hits, surv, n_surv, fetch, rays);
     (*launches)++;
 }
 
@@ -523,135 +535,154 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     if (s1 < s0) { ctx->error = "sample_end < sample_begin"; return NRCU_ERR_INVALID; }
     const uint64_t seed = params ? params->seed : 0;
     const int glass_branch = params && params->glass_mode == NRCU_GLASS_BRANCH;
-    // wave size: k samples of every pixel, about NRCU_WAVE_SLOTS (default 32 Mi) paths in flight.  Bigger waves
-    // amortise the per-launch latency floor of the deep bounces (few rays, ~50 us per persistent launch) over
-    // more paths; 32 Mi slots cost ~4 GB of the 180 GB HBM.
-    uint32_t k = params ? params->samples_per_wave : 0;
-    if (k == 0) k = std::max<uint32_t>(1, wave_slots_target() / npix);
+    // Wave size: k samples of every pixel; NRCU_WAVE_MSLOTS (default 128 Mi, ~15 GB of the 180 GB HBM) path slots
+    // are in flight, split over NRCU_WAVES (default 2) waves that run side by side on their own streams with
+    // full-size persistent grids.  Bigger waves amortise the latency floor of the deep bounces (few rays, ~50 us per
+    // persistent launch); concurrent waves let the SMs interleave CTAs of an issue-bound kernel of one wave
+    // (k_big: 76 % issue-active) with CTAs of a latency-bound kernel of the other (k_shade: 45 %) and hide every
+    // kernel's tail behind the other wave's work.  Measured on cfg3: 1 wave x 32 Mi 2.14, 2 x 64 Mi 2.68,
+    // 4 x 64 Mi 2.71 Gpath-samples/s.  The accumulation order is fixed by events, so the image is bit-identical.
+    const bool explicit_k = params && params->samples_per_wave != 0;
+    uint32_t k = explicit_k ? params->samples_per_wave : std::max<uint32_t>(1, wave_slots_target() / npix);
     k = std::min<uint32_t>(k, std::max<uint32_t>(1, s1 - s0));
     if ((uint64_t)k * npix > 0x7fffffffull) k = std::max<uint32_t>(1, (uint32_t)(0x7fffffffull / npix));
+    int NP = glass_branch ? 1 : std::min<int>(concurrent_waves(), (int)(s1 - s0));
+    if (NP > 1 && !explicit_k) k = std::max<uint32_t>(1, k / (uint32_t)NP);
+    NP = std::min<int>(NP, (int)((s1 - s0 + k - 1) / k));
+    const unsigned share = (unsigned)NP;
     const uint32_t slots = k * npix;
     const uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
     int rc;
-    if ((rc = ensure_wave(ctx, slots, capacity, ds.depth, glass_branch != 0, nee)) != NRCU_OK) return rc;
-    PathQueue q[2] = {{ctx->qa[0].as<f4>(), ctx->qb[0].as<float2>(), ctx->qc[0].as<f4>(), glass_branch ? ctx->qd[0].as<uint32_t>() : nullptr},
-                      {ctx->qa[1].as<f4>(), ctx->qb[1].as<float2>(), ctx->qc[1].as<f4>(), glass_branch ? ctx->qd[1].as<uint32_t>() : nullptr}};
-    uint32_t* cnt = ctx->counters.as<uint32_t>();
-    unsigned long long* d_rays = reinterpret_cast<unsigned long long*>(cnt + CNT_RAYS);
-    uint32_t* d_qn = cnt + CNT_QUEUE0;                 // queue size entering bounce d
-    uint32_t* d_fetch = cnt + CNT_QUEUE0 + ds.depth + 2;  // work-fetch cursor of bounce d
-    uint32_t* d_nsurv = cnt + CNT_QUEUE0 + 2 * (ds.depth + 2);  // stage-1 survivors of bounce d
-    uint32_t* d_nshadow = cnt + CNT_QUEUE0 + 3 * (ds.depth + 2);   // NEE: shadow rays of bounce d, their fetch cursors and survivors
-    uint32_t* d_sfetch = cnt + CNT_QUEUE0 + 4 * (ds.depth + 2);
-    uint32_t* d_snsurv = cnt + CNT_QUEUE0 + 5 * (ds.depth + 2);
+    for (int p = 0; p < NP; p++) if ((rc = ensure_wave(ctx, p, slots, capacity, ds.depth, glass_branch != 0, nee)) != NRCU_OK) return rc;
+    cudaStream_t S[NRCU_MAX_WAVES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
+    if (NP > 1) {
+        for (int p = 1; p < NP; p++) {
+            if (!ctx->extra_stream[p]) CTX_CUDA(cudaStreamCreateWithFlags(&ctx->extra_stream[p], cudaStreamNonBlocking));
+            S[p] = ctx->extra_stream[p];
+        }
+        if (!ctx->ev_fork) { CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+                             CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_acc, cudaEventDisableTiming)); }
+    }
+    // shared by both waves: ray counter and high-water mark live in set 0's counter block
+    uint32_t* cnt0 = ctx->ws[0].counters.as<uint32_t>();
+    unsigned long long* d_rays = reinterpret_cast<unsigned long long*>(cnt0 + CNT_RAYS);
     const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 6 * (size_t)ds.depth + 24);
-    PathQueue qs{ctx->sa.as<f4>(), ctx->sb.as<float2>(), ctx->sc.as<f4>(), ctx->sd.as<uint32_t>()};
-    if (!nee) qs = PathQueue{nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t st = ctx->stream;
     const int sms = sm_count(ctx->device);
-    const unsigned shade_grid = (unsigned)sms * NRCU_SHADE_MINB;
-    const bool timing = stats != nullptr;
+    const unsigned shade_grid = (unsigned)sms * (NP > 1 ? dual_shade() : NRCU_SHADE_MINB), big_grid = (unsigned)sms * (NP > 1 ? dual_big() : 8);
+    const bool timing = stats != nullptr, gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
     size_t ev_i = 0;
     struct Span { size_t a, b; int kind; };
     std::vector<Span> spans;
-    CTX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * CNT_QUEUE0, st));
-    if (timing) CTX_CUDA(cudaEventRecord(ctx->ev_begin, st));
-    uint64_t launches0 = ctx->launches;
-    for (uint32_t w0 = s0; w0 < s1; w0 += k) {
-        const uint32_t kw = std::min(k, s1 - w0), n_slots = kw * npix;
-        CTX_CUDA(cudaMemsetAsync(cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
-        // Per bounce d of the wave (default, NRCU_PIPELINE=0): stage 1 in k_raygen (d = 0) / k_big, k_trace* on the
-        // survivors, k_shade<SHADE_ALL>.  NRCU_PIPELINE=1 is the fused form
-        //   k_shade<SHADE_STAGE1>  every ray: stage 1 of the closest hit, then either shading at once or deferral to the survivor list
-        //   k_trace*               the survivors: BVH traversal, refining hits[]
-        //   k_shade<SHADE_SURV>    shading of the survivors
-        // which reads every ray once instead of twice and never writes the hit of 92 % of them - and is 25 % SLOWER on
-        // B200 (126.7 ms vs 40 + 45 + 9 ms per 128 spp of cfg3): the fused kernel needs 64 registers with 80 B of spills
-        // and runs the divergent exact tests and the divergent shading back to back in the same warps.  Kept for A/B.
-        const bool gate = ctx->mode == NRCU_MODE_ACC, fused = pipeline_fused();
-        float2* hb = ctx->hits.as<float2>();
-        uint32_t* surv = ctx->surv.as<uint32_t>();
-        const unsigned gen_grid = std::min<unsigned>(grid_for(n_slots, 256), (unsigned)sms * 8);
-        f4* Lbuf = ctx->L.as<f4>();
-        if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
-#define NRCU_RAYGEN(G, S1) k_raygen<G, S1><<<gen_grid, 256, 0, st>>>(ds, seed, w0, n_slots, q[0], Lbuf, d_qn, hb, surv, d_nsurv, d_rays)
-        if (gate) { if (fused) NRCU_RAYGEN(true, false); else NRCU_RAYGEN(true, true); }
-        else { if (fused) NRCU_RAYGEN(false, false); else NRCU_RAYGEN(false, true); }
-#undef NRCU_RAYGEN
-        CTX_LAUNCH_CHECK("k_raygen");
-        if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, fused ? 1 : 0}); ev_i += 2; }
-#define NRCU_SHADE_N(G, M, N) k_shade<G, M, N><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, w0, qi, d_qn + d, hb, qo, d_qn + d + 1, capacity, Lbuf, surv, d_nsurv + d, d_rays, qs, d_nshadow + d)
-#define NRCU_SHADE(G, M) do { if (nee) NRCU_SHADE_N(G, M, true); else NRCU_SHADE_N(G, M, false); } while (0)
+    CTX_CUDA(cudaMemsetAsync(cnt0, 0, sizeof(uint32_t) * CNT_QUEUE0, S[0]));
+    if (timing) CTX_CUDA(cudaEventRecord(ctx->ev_begin, S[0]));
+    if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_fork, S[0])); for (int p = 1; p < NP; p++) CTX_CUDA(cudaStreamWaitEvent(S[p], ctx->ev_fork, 0)); }
+    const uint64_t launches0 = ctx->launches;
+    bool acc_recorded = false;
+
+    struct Pipe {
+        bool live; uint32_t w0, kw, n_slots;
+        PathQueue q[2], qs; uint32_t* cnt; uint32_t *d_qn, *d_fetch, *d_nsurv, *d_nshadow, *d_sfetch, *d_snsurv;
+        float2* hb; uint32_t* surv; f4* L; cudaStream_t st;
+    } P[NRCU_MAX_WAVES];
+    for (int p = 0; p < NP; p++) {
+        nrcu_ctx::WaveSet& w = ctx->ws[p];
+        Pipe& pp = P[p];
+        pp.live = false; pp.st = S[p];
+        for (int j = 0; j < 2; j++) pp.q[j] = PathQueue{w.qa[j].as<f4>(), w.qb[j].as<float2>(), w.qc[j].as<f4>(), glass_branch ? w.qd[j].as<uint32_t>() : nullptr};
+        pp.qs = nee ? PathQueue{w.sa.as<f4>(), w.sb.as<float2>(), w.sc.as<f4>(), w.sd.as<uint32_t>()} : PathQueue{nullptr, nullptr, nullptr, nullptr};
+        pp.cnt = w.counters.as<uint32_t>();
+        pp.d_qn = pp.cnt + CNT_QUEUE0;                          // queue size entering bounce d
+        pp.d_fetch = pp.cnt + CNT_QUEUE0 + ds.depth + 2;        // work-fetch cursor of bounce d
+        pp.d_nsurv = pp.cnt + CNT_QUEUE0 + 2 * (ds.depth + 2);  // stage-1 survivors of bounce d
+        pp.d_nshadow = pp.cnt + CNT_QUEUE0 + 3 * (ds.depth + 2);   // NEE: shadow rays of bounce d, their fetch cursors and survivors
+        pp.d_sfetch = pp.cnt + CNT_QUEUE0 + 4 * (ds.depth + 2);
+        pp.d_snsurv = pp.cnt + CNT_QUEUE0 + 5 * (ds.depth + 2);
+        pp.hb = w.hits.as<float2>(); pp.surv = w.surv.as<uint32_t>(); pp.L = w.L.as<f4>();
+    }
+
+    for (uint32_t g0 = s0; g0 < s1; g0 += k * (uint32_t)NP) {
+        // ---- camera rays (+ stage 1 of their closest hit) of the waves of this group ------------------------------
+        for (int p = 0; p < NP; p++) {
+            Pipe& pp = P[p];
+            pp.w0 = g0 + (uint32_t)p * k; pp.live = pp.w0 < s1;
+            if (!pp.live) continue;
+            pp.kw = std::min(k, s1 - pp.w0); pp.n_slots = pp.kw * npix;
+            cudaStream_t st = pp.st;
+            CTX_CUDA(cudaMemsetAsync(pp.cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
+            const unsigned gen_grid = std::min<unsigned>(grid_for(pp.n_slots, 256), (unsigned)sms * 8);
+            if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
+            if (gate) k_raygen<true, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, d_rays);
+            else k_raygen<false, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, d_rays);
+            CTX_LAUNCH_CHECK("k_raygen");
+            if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); ev_i += 2; }   // booked as closest-hit time: stage 1 of bounce 0 is most of this kernel
+        }
+        // ---- bounces: stage 1 (k_big; bounce 0's ran inside k_raygen), stage 2 (k_trace*) on the survivors, k_shade ---
         for (uint32_t d = 0; d < ds.depth; d++) {
-            PathQueue qi = q[d & 1], qo = q[(d + 1) & 1];
-            const bool bvh = ds.root_ref != NRCU_REF_EMPTY;
-            if (fused) {
+            for (int p = 0; p < NP; p++) {
+                Pipe& pp = P[p];
+                if (!pp.live) continue;
+                cudaStream_t st = pp.st;
+                PathQueue qi = pp.q[d & 1], qo = pp.q[(d + 1) & 1];
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
-                if (gate) NRCU_SHADE(true, SHADE_STAGE1); else NRCU_SHADE(false, SHADE_STAGE1);
-                CTX_LAUNCH_CHECK("k_shade<stage1>");
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 2}); }
-                if (bvh) {
-                    if (gate) launch_stage2<true>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
-                    else launch_stage2<false>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
-                    CTX_LAUNCH_CHECK("k_trace");
-                }
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 0}); }
-                if (bvh) {
-                    if (gate) NRCU_SHADE(true, SHADE_SURV); else NRCU_SHADE(false, SHADE_SURV);
-                    CTX_LAUNCH_CHECK("k_shade<surv>");
-                }
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i + 2, ev_i + 3, 1}); ev_i += 4; }
-            } else {
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i), st); }
-                if (d > 0) {   // stage 1 of this bounce (bounce 0's ran inside k_raygen)
-                    if (gate) k_big<true><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hb, surv, d_nsurv + d, d_rays);
-                    else k_big<false><<<(unsigned)sms * 8, 256, 0, st>>>(ds, qi, d_qn + d, hb, surv, d_nsurv + d, d_rays);
+                if (d > 0) {
+                    if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
+                    else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
                     CTX_LAUNCH_CHECK("k_big");
                 }
                 if (bvh) {
-                    if (gate) launch_stage2<true>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
-                    else launch_stage2<false>(ctx, ds, qi, hb, surv, d_nsurv + d, d_fetch + d, d_rays, d);
+                    if (gate) launch_stage2<true>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + d, pp.d_fetch + d, d_rays, d);
+                    else launch_stage2<false>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + d, pp.d_fetch + d, d_rays, d);
                     CTX_LAUNCH_CHECK("k_trace");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
-                if (gate) NRCU_SHADE(true, SHADE_ALL); else NRCU_SHADE(false, SHADE_ALL);
+#define NRCU_SHADE(G, N) k_shade<G, N><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, pp.d_qn + d, pp.hb, qo, pp.d_qn + d + 1, capacity, pp.L, pp.qs, pp.d_nshadow + d)
+                if (gate) { if (nee) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
+                else { if (nee) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
+#undef NRCU_SHADE
                 CTX_LAUNCH_CHECK("k_shade");
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
-            }
-            if (glass_branch) {   // only the branching mode can outgrow the queue
-                k_clamp_count<<<1, 1, 0, st>>>(d_qn + d + 1, capacity, cnt + CNT_HIGH_WATER);
-                CTX_LAUNCH_CHECK("k_clamp_count");
-                if (nee) { k_clamp_count<<<1, 1, 0, st>>>(d_nshadow + d, capacity, cnt + CNT_HIGH_WATER); CTX_LAUNCH_CHECK("k_clamp_count"); }
-            }
-            if (nee && d + 1 < ds.depth) {   // the shadow rays of this bounce: same closest-hit kernels, then visibility + add
-                if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
-                int nl = 0;
-                if (gate) launch_closest_hit<true>(ctx, ds, qs, d_nshadow + d, hb, surv, d_snsurv + d, d_sfetch + d, d_rays, &nl);
-                else launch_closest_hit<false>(ctx, ds, qs, d_nshadow + d, hb, surv, d_snsurv + d, d_sfetch + d, d_rays, &nl);
-                ctx->launches += nl - 1;
-                CTX_LAUNCH_CHECK("k_big/k_trace (shadow)");
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
-                k_shadow_resolve<<<shade_grid, 256, 0, st>>>(ds, qs, d_nshadow + d, hb, Lbuf, glass_branch);
-                CTX_LAUNCH_CHECK("k_shadow_resolve");
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
+                if (glass_branch) {   // only the branching mode can outgrow the queue
+                    k_clamp_count<<<1, 1, 0, st>>>(pp.d_qn + d + 1, capacity, cnt0 + CNT_HIGH_WATER);
+                    CTX_LAUNCH_CHECK("k_clamp_count");
+                    if (nee) { k_clamp_count<<<1, 1, 0, st>>>(pp.d_nshadow + d, capacity, cnt0 + CNT_HIGH_WATER); CTX_LAUNCH_CHECK("k_clamp_count"); }
+                }
+                if (nee && d + 1 < ds.depth) {   // the shadow rays of this bounce: same closest-hit kernels, then visibility + add
+                    if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
+                    int nl = 0;
+                    if (gate) launch_closest_hit<true>(ctx, st, share, ds, pp.qs, pp.d_nshadow + d, pp.hb, pp.surv, pp.d_snsurv + d, pp.d_sfetch + d, d_rays, &nl);
+                    else launch_closest_hit<false>(ctx, st, share, ds, pp.qs, pp.d_nshadow + d, pp.hb, pp.surv, pp.d_snsurv + d, pp.d_sfetch + d, d_rays, &nl);
+                    ctx->launches += nl - 1;
+                    CTX_LAUNCH_CHECK("k_big/k_trace (shadow)");
+                    if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
+                    k_shadow_resolve<<<shade_grid, 256, 0, st>>>(ds, pp.qs, pp.d_nshadow + d, pp.hb, pp.L, glass_branch);
+                    CTX_LAUNCH_CHECK("k_shadow_resolve");
+                    if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
+                }
             }
         }
-#undef NRCU_SHADE
-#undef NRCU_SHADE_N
-        k_accumulate<<<grid_for(npix, 256), 256, 0, st>>>(ctx->L.as<f4>(), d_accum, npix, kw);
-        CTX_LAUNCH_CHECK("k_accumulate");
+        // ---- accum += the waves' samples, in sample order whatever stream a wave ran on -----------------------------
+        for (int p = 0; p < NP; p++) {
+            Pipe& pp = P[p];
+            if (!pp.live) continue;
+            if (NP > 1 && acc_recorded) CTX_CUDA(cudaStreamWaitEvent(pp.st, ctx->ev_acc, 0));
+            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw);
+            CTX_LAUNCH_CHECK("k_accumulate");
+            if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_acc, pp.st)); acc_recorded = true; }
+        }
     }
+    for (int p = 1; p < NP; p++) { CTX_CUDA(cudaEventRecord(ctx->ev_join, S[p])); CTX_CUDA(cudaStreamWaitEvent(S[0], ctx->ev_join, 0)); }
     if (timing) {
+        cudaStream_t st = S[0];
         CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
         uint32_t h_cnt[CNT_QUEUE0];
-        CTX_CUDA(cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        CTX_CUDA(cudaMemcpyAsync(h_cnt, cnt0, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         CTX_CUDA(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof(*stats));
         CTX_CUDA(cudaEventElapsedTime(&stats->ms_total, ctx->ev_begin, ctx->ev_end));
-        for (auto& sp : spans) {
+        for (auto& sp : spans) {   // with two streams the spans of the two waves overlap: the sums exceed ms_total
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]);
-            if (sp.kind == 0) stats->ms_trace += ms; else if (sp.kind == 1) stats->ms_shade += ms; else stats->ms_fused += ms;
+            if (sp.kind == 0) stats->ms_trace += ms; else stats->ms_shade += ms;
         }
         unsigned long long rays; std::memcpy(&rays, h_cnt + CNT_RAYS, 8);
         stats->rays = rays; stats->paths = (uint64_t)npix * (s1 - s0);
@@ -691,8 +722,8 @@ int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out
     cudaStream_t st = ctx->stream;
     CTX_CUDA(ctx->rgba_dev.ensure(sizeof(f4) * (size_t)npix));
     if (ctx->mode == NRCU_MODE_RAYCAST) {
-        CTX_CUDA(ctx->counters.ensure(sizeof(uint32_t) * 64));
-        unsigned long long* d_rays = ctx->counters.as<unsigned long long>();
+        CTX_CUDA(ctx->ws[0].counters.ensure(sizeof(uint32_t) * 64));
+        unsigned long long* d_rays = ctx->ws[0].counters.as<unsigned long long>();
         CTX_CUDA(cudaMemsetAsync(d_rays, 0, 8, st));
         uint64_t launches0 = ctx->launches;
         CTX_CUDA(cudaEventRecord(ctx->ev_begin, st));
@@ -860,8 +891,8 @@ int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim
     uint32_t* c = cnt.as<uint32_t>();
     int nl = 0;
     if (ctx->mode == NRCU_MODE_RAYCAST) { k_trace_linear_rc<<<grid_for(n, 128), 128, 0, st>>>(ctx->ds, q, n, hits.as<float2>()); nl = 1; }
-    else if (ctx->mode == NRCU_MODE_ACC) launch_closest_hit<true>(ctx, ctx->ds, q, c + 2, hits.as<float2>(), surv.as<uint32_t>(), c + 4, c + 3, reinterpret_cast<unsigned long long*>(c), &nl);
-    else launch_closest_hit<false>(ctx, ctx->ds, q, c + 2, hits.as<float2>(), surv.as<uint32_t>(), c + 4, c + 3, reinterpret_cast<unsigned long long*>(c), &nl);
+    else if (ctx->mode == NRCU_MODE_ACC) launch_closest_hit<true>(ctx, st, 1, ctx->ds, q, c + 2, hits.as<float2>(), surv.as<uint32_t>(), c + 4, c + 3, reinterpret_cast<unsigned long long*>(c), &nl);
+    else launch_closest_hit<false>(ctx, st, 1, ctx->ds, q, c + 2, hits.as<float2>(), surv.as<uint32_t>(), c + 4, c + 3, reinterpret_cast<unsigned long long*>(c), &nl);
     ctx->launches += nl - 1;
     CTX_LAUNCH_CHECK("k_big/k_trace");
     std::vector<float2> h(n);

@@ -386,96 +386,69 @@ __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hit
 }
 
 // Shading + next-ray generation for bounce `d`; surviving paths are compacted into `qo` with one atomic per
-// warp (ballot + popc prefix).  Three forms of the same loop:
-//   SHADE_ALL     every queue entry, closest hit read from `hits` (after k_big + k_trace*)
-//   SHADE_STAGE1  every queue entry, stage 1 of the closest hit computed HERE first (wide-primitive list, the ray
-//                 is in registers anyway): a ray that cannot reach the BVH any more is shaded at once - 92 % of
-//                 the rays on bunny+Cornell never touch `hits` and are read from the queue once per bounce instead
-//                 of twice; the others get their provisional hit stored and their queue position appended to the
-//                 survivor list (one atomic per warp) for k_trace* and a SHADE_SURV pass
-//   SHADE_SURV    only the entries listed in `surv`, closest hit read from `hits`
-// The queue entry of the NEXT iteration is requested right after this iteration's output-slot atomic has been
-// issued, so the atomic's round trip and the loads' latency overlap (ncu on the unpipelined loop: 38 % of the stall
-// samples sat on the shuffle that waits for the atomic, 16 % on the first use of the loaded entry).
-enum { SHADE_ALL = 0, SHADE_STAGE1 = 1, SHADE_SURV = 2 };
+// warp (ballot + popc prefix).  The queue entry of the NEXT iteration is requested right after this iteration's
+// output-slot atomic has been issued, so the atomic's round trip and the loads' latency overlap (ncu on the
+// unpipelined loop: 38 % of the stall samples sat on the shuffle that waits for the atomic, 16 % on the first use of
+// the loaded entry).  Fusing stage 1 of the closest hit into this kernel - after the shading (next ray still in
+// registers) or before it (SHADE_STAGE1: rays that end at stage 1 shaded at once, the rest deferred) - was built and
+// measured three times and lost every time (profiles/r1_history.md): 64 -> 73 registers or spills, and two
+// divergent phases back to back in the same warps.
 #ifndef NRCU_SHADE_MINB
 #define NRCU_SHADE_MINB 4
 #endif
-template <bool GATE, int MODE, bool NEE>
+template <bool GATE, bool NEE>
 __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
-                                              PathQueue qi, const uint32_t* n_in_ptr, float2* hits,
+                                              PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
                                               PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L,
-                                              uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter,
                                               PathQueue qs, uint32_t* n_shadow_ptr) {
-    __shared__ BigList bl;
-    if (MODE == SHADE_STAGE1) bl.load(s);
-    const uint32_t n = MODE == SHADE_SURV ? *n_surv : *n_in_ptr;
+    const uint32_t n = *n_in_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t npix = s.width * s.height;
-    f4 a = mk4(0, 0, 0, 0), c = a; float2 b = make_float2(0.f, 0.f), h = make_float2(NRCU_INF, __int_as_float(-1)); uint32_t br = 0, qpos = 0;
+    f4 a = mk4(0, 0, 0, 0), c = a; float2 b = make_float2(0.f, 0.f), h = b; uint32_t br = 0;
     auto load_entry = [&](uint32_t j) {
         if (j >= n) return;
-        qpos = MODE == SHADE_SURV ? surv[j] : j;
-        a = qi.a[qpos]; b = qi.b[qpos]; c = qi.c[qpos];
-        if (MODE != SHADE_STAGE1) h = hits[qpos];
-        if (glass_branch) br = qi.d[qpos];
+        a = qi.a[j]; b = qi.b[j]; c = qi.c[j]; h = hits[j];
+        if (glass_branch) br = qi.d[j];
     };
     load_entry(warp_global * 32u + lane);
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
         const uint32_t i = base + lane;
         int n_out = 0;
-        bool defer = false;
         PathStep ps;
         uint32_t slot = 0, branch = 0;
-        const uint32_t my_pos = qpos;
         if (i < n) {
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             vec3 thr = mk3(c.x, c.y, c.z);
             slot = (uint32_t)f2i(c.w) & 0x7fffffffu; branch = br;
             const bool skip_light = ((uint32_t)f2i(c.w) >> 31) != 0u;   // the previous vertex sent a shadow ray (NEE)
-            if (MODE == SHADE_STAGE1) {
-                RayPrep rp = prep_ray(r);
-                float bt = NRCU_INF; int bi = -1;
-                big_list_step<GATE>(s, bl.g, bl.b, bl.bd, bl.m, r, rp, gate_inverse(r), bt, bi);
-                h = make_float2(bt, __int_as_float(bi));
-                defer = bvh_reachable(s, rp, bt);
-                if (defer) hits[my_pos] = h;
-            }
-            if (!defer) {
-                uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
-                ps = path_vertex<NEE>(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch, skip_light);
-                if (ps.action == PATH_TERMINATE) {
-                    if (NEE) {            // shadow rays of earlier bounces add to the same slot (k_shadow_resolve)
-                        if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
-                            if (glass_branch) { atomicAdd(&L[slot].x, ps.radiance.x); atomicAdd(&L[slot].y, ps.radiance.y); atomicAdd(&L[slot].z, ps.radiance.z); }
-                            else { f4 v = L[slot]; L[slot] = mk4(v.x + ps.radiance.x, v.y + ps.radiance.y, v.z + ps.radiance.z, 0.f); }
-                        }
-                    } else if (glass_branch) {   // several branches of one path share the slot
-                        if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
-                        if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
-                        if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
-                    } else if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
-                        L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);   // one path per slot, it ends once: plain store into the zeroed slot
+            uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
+            ps = path_vertex<NEE>(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch, skip_light);
+            if (ps.action == PATH_TERMINATE) {
+                if (NEE) {            // shadow rays of earlier bounces add to the same slot (k_shadow_resolve)
+                    if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
+                        if (glass_branch) { atomicAdd(&L[slot].x, ps.radiance.x); atomicAdd(&L[slot].y, ps.radiance.y); atomicAdd(&L[slot].z, ps.radiance.z); }
+                        else { f4 v = L[slot]; L[slot] = mk4(v.x + ps.radiance.x, v.y + ps.radiance.y, v.z + ps.radiance.z, 0.f); }
                     }
-                } else n_out = ps.action == PATH_SPLIT ? 2 : 1;
-            }
+                } else if (glass_branch) {   // several branches of one path share the slot
+                    if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
+                    if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
+                    if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
+                } else if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
+                    L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);   // one path per slot, it ends once: plain store into the zeroed slot
+                }
+            } else n_out = ps.action == PATH_SPLIT ? 2 : 1;
         }
-        // warp-aggregated allocation in the output queue (and, in SHADE_STAGE1, in the survivor list)
+        // warp-aggregated allocation in the output queue
         const uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
-        const uint32_t md = MODE == SHADE_STAGE1 ? __ballot_sync(0xffffffffu, defer) : 0u;
         const uint32_t total = __popc(m1) + __popc(m2);
-        uint32_t start = 0, sstart = 0;
-        if (lane == 0) {
-            if (total) start = atomicAdd(n_out_ptr, total);
-            if (md) sstart = atomicAdd(n_surv, (uint32_t)__popc(md));
-            if (MODE == SHADE_STAGE1) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
-        }
-        load_entry(i + warps_total * 32u);   // prefetch the next iteration's entry while the atomics are in flight
+        uint32_t start = 0;
+        if (lane == 0 && total) start = atomicAdd(n_out_ptr, total);
+        load_entry(i + warps_total * 32u);   // prefetch the next iteration's entry while the atomic is in flight
         const uint32_t lt = (1u << lane) - 1u;
         if (NEE) {   // shadow rays of this bounce, compacted into their own queue
-            const bool sh = i < n && !defer && ps.nee;
+            const bool sh = i < n && ps.nee;
             const uint32_t ms = __ballot_sync(0xffffffffu, sh);
             if (ms) {
                 uint32_t s0 = 0;
@@ -489,10 +462,6 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
                     qs.d[sp] = (uint32_t)ps.nee_light;
                 }
             }
-        }
-        if (md) {
-            sstart = __shfl_sync(0xffffffffu, sstart, 0);
-            if (defer) surv[sstart + __popc(md & lt)] = my_pos;
         }
         if (total == 0) continue;   // warp-uniform
         start = __shfl_sync(0xffffffffu, start, 0);
