@@ -120,7 +120,9 @@ def main():
         f.write(f"\nClosest-hit kernels ({', '.join(ch)}): {ch_time/T*100:.1f} % of the render-kernel time, "
                 f"{ch_inst/ch_time/(SMS*SCHEDULERS*1965.0)*100:.1f} % of the issue-slot peak (148 SMs x 4 x 1.965 GHz), "
                 f"DRAM traffic per wave {summary['closest_hit_dram_bytes_per_step_equiv']/1e9:.2f} GB.\n")
-        f.write("\nFull captures (`ncu --set full`, one launch each at bounce 1):\n\n| kernel | time us | regs | lanes/inst | issue % | warps active % | L1 hit % | L2 hit % | L1 GB/s (% of peak) | L2 GB/s (% of peak) | DRAM R MB | DRAM W MB | DRAM GB/s (of 6549.8) | long-scoreboard stall |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        f.write("\nncu serialises kernel launches: the two waves that run side by side in the real run (NRCU_WAVES=2, +25 %) appear back to back here, "
+                "so the shares above are per-kernel work shares, not wall-clock shares of the overlapped run.\n")
+        f.write("\nFull captures (`ncu --set full`, one launch each, early bounces of the first waves):\n\n| kernel | time us | regs | lanes/inst | issue % | warps active % | L1 hit % | L2 hit % | L1 GB/s (% of peak) | L2 GB/s (% of peak) | DRAM R MB | DRAM W MB | DRAM GB/s (of 6549.8) | long-scoreboard stall |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         U = {k: units[hdr.index(k)] for k in KEEP if k in hdr}
         def mb(h, k):
             v = float(h.get(k, 0) or 0)
