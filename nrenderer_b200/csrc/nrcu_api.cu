@@ -484,10 +484,10 @@ static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM",
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
 
 static int concurrent_waves() { static uint32_t v = env_u32("NRCU_WAVES", 2); return (int)std::min<uint32_t>(std::max<uint32_t>(v, 1), NRCU_MAX_WAVES); }
-// CTAs per SM of each kernel when two waves share the machine (tuning knobs)
-static unsigned dual_big() { static uint32_t v = env_u32("NRCU_DUAL_BIG", 8); return v ? v : 1; }
-static unsigned dual_shade() { static uint32_t v = env_u32("NRCU_DUAL_SHADE", 4); return v ? v : 1; }
-static unsigned dual_trace() { static uint32_t v = env_u32("NRCU_DUAL_TRACE", 8); return v ? v : 1; }
+// CTAs per SM of each kernel when several waves share the machine (tuning knobs; full-size grids measured best)
+static unsigned dual_big() { static uint32_t v = env_u32("NRCU_CONC_BIG", 8); return v ? v : 1; }
+static unsigned dual_shade() { static uint32_t v = env_u32("NRCU_CONC_SHADE", 4); return v ? v : 1; }
+static unsigned dual_trace() { static uint32_t v = env_u32("NRCU_CONC_TRACE", 8); return v ? v : 1; }
 
 // Stage 2 of the closest hit: BVH traversal of the *n_surv rays listed in `surv`, refining hits[] in place.
 template <bool GATE>
