@@ -546,9 +546,9 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     uint32_t k = explicit_k ? params->samples_per_wave : std::max<uint32_t>(1, wave_slots_target() / npix);
     k = std::min<uint32_t>(k, std::max<uint32_t>(1, s1 - s0));
     if ((uint64_t)k * npix > 0x7fffffffull) k = std::max<uint32_t>(1, (uint32_t)(0x7fffffffull / npix));
-    int NP = glass_branch ? 1 : std::min<int>(concurrent_waves(), (int)(s1 - s0));
+    int NP = glass_branch ? 1 : std::max(1, std::min<int>(concurrent_waves(), (int)(s1 - s0)));
     if (NP > 1 && !explicit_k) k = std::max<uint32_t>(1, k / (uint32_t)NP);
-    NP = std::min<int>(NP, (int)((s1 - s0 + k - 1) / k));
+    NP = std::max(1, std::min<int>(NP, (int)((s1 - s0 + k - 1) / k)));   // also with no samples at all: one (idle) wave set
     const unsigned share = (unsigned)NP;
     const uint32_t slots = k * npix;
     const uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;

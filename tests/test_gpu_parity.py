@@ -394,3 +394,27 @@ def test_next_event_estimation_matches_host_emulation_same_rng(ctx, name, mode, 
         assert np.array_equal(acc.view(np.uint32), again.view(np.uint32))
     else:
         np.testing.assert_allclose(again, acc, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_degenerate_requests(ctx):
+    """Zero samples, an empty sample slice, a 1x1 frame, depth 1 and a scene without lights: no crash, sane frames."""
+    import torch
+    fs = load_scene("path_tracing_cornel", width=8, height=8, samples_per_pixel=0, depth=4)
+    ctx.upload(fs, 2)
+    acc = torch.zeros(8, 8, 4, device="cuda:0"); torch.cuda.synchronize()
+    st = ctx.render_accumulate(acc.data_ptr())
+    assert st["paths"] == 0 and st["rays"] == 0 and float(acc.abs().sum()) == 0.0
+    fs = load_scene("path_tracing_cornel", width=1, height=1, samples_per_pixel=3, depth=1)
+    ctx.upload(fs, 2)
+    img, st = ctx.render()
+    assert img.shape == (1, 1, 4) and np.isfinite(img).all() and st["paths"] == 3 and st["rays"] == 3
+    st = ctx.render_accumulate(torch.zeros(1, 1, 4, device="cuda:0").data_ptr(), s0=2, s1=2)
+    assert st["paths"] == 0
+    fs = load_scene("path_tracing_cornel", width=16, height=16, samples_per_pixel=4, depth=5)
+    for name in ("area_radiance", "area_position", "area_u", "area_v"):
+        setattr(fs, name, getattr(fs, name)[:0])
+    ctx.upload(fs, 2)
+    for flags in (0, 1):           # NEE with nothing to sample is the plain estimator
+        img, st = ctx.render(flags=flags)
+        assert float(np.abs(img[..., :3]).sum()) == 0.0 and (img[..., 3] == 1).all()
