@@ -479,6 +479,7 @@ static uint32_t trace_taper(int k) {
     if (!init) { init = true; const char* e = std::getenv("NRCU_TRACE_TAPER"); unsigned a = 0xffffffffu, b = 0xffffffffu; if (e) std::sscanf(e, "%u,%u", &a, &b); v[0] = a; v[1] = b; }
     return v[k];
 }
+static bool big_balanced() { static uint32_t v = env_u32("NRCU_BIG_BALANCED", 1); return v != 0; }
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
@@ -625,7 +626,11 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
                 PathQueue qi = pp.q[d & 1], qo = pp.q[(d + 1) & 1];
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                 if (d > 0) {
-                    if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
+                    if (big_balanced()) {
+                        if (gate) k_big_balanced<true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
+                        else k_big_balanced<false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
+                    }
+                    else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
                     else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
                     CTX_LAUNCH_CHECK("k_big");
                 }

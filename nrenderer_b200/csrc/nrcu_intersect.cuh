@@ -227,6 +227,12 @@ NR_HD void prim_test(const Ray& ray, vec3 ginv, f4 g0, f4 g1, f4 g2, const f4* b
 }
 // Exact IEEE reciprocals of the direction for the leaf gate (BVH.hpp:97).
 NR_HD vec3 gate_inverse(const Ray& ray) { return mk3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z); }
+// The same from an already prepared ray: prep_ray's reciprocal IS the exact one unless it was clamped (|d| <= 1e-18),
+// which almost never happens - the three divisions are only redone in that case.
+NR_HD vec3 gate_inverse(const Ray& ray, const RayPrep& rp) {
+    if (fabsf(ray.d.x) > 1e-18f && fabsf(ray.d.y) > 1e-18f && fabsf(ray.d.z) > 1e-18f) return rp.inv;
+    return gate_inverse(ray);
+}
 
 // The same for leaf slot `slot` of the leaf-ordered arrays.
 template <bool GATE>

@@ -85,7 +85,7 @@ template <bool GATE>
 __device__ __forceinline__ bool stage1(const DScene& s, const BigList& bl, const Ray& r, uint32_t pos, float2* hits) {
     RayPrep rp = prep_ray(r);
     float best_t = NRCU_INF; int best_id = -1;
-    big_list_step<GATE>(s, bl.g, bl.b, bl.bd, bl.m, r, rp, gate_inverse(r), best_t, best_id);
+    big_list_step<GATE>(s, bl.g, bl.b, bl.bd, bl.m, r, rp, gate_inverse(r, rp), best_t, best_id);
     hits[pos] = make_float2(best_t, __int_as_float(best_id));
     return bvh_reachable(s, rp, best_t);
 }
@@ -173,6 +173,95 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
     }
 }
 
+// k_big with WARP-BALANCED exact tests.  In k_big the exact tests of a warp take as many rounds as its busiest
+// lane has candidates (about 5 on incoherent rays, at 2-8 active lanes), although the warp holds only ~2 candidates
+// per ray: 18 of 32 lanes per instruction overall (ncu).  Here pass 1 also builds, per warp, the list of (ray, wide
+// primitive) candidate pairs in shared memory - primitive-major, by ballot/popc inside the warp-uniform slab loop -
+// and the exact tests run 32 pairs at a time: consecutive lanes test the SAME primitive against different rays
+// (uniform kind, broadcast reads of the record).  A test reads its ray from shared memory, culls against the owner's
+// best hit so far and publishes a hit with a 64-bit shared-memory atomicMin on (t bits, id, list index): t > 0, so
+// unsigned order is (t, id) order, the tie rule of the per-ray loop.  The optimistic leaf gate and its
+// per-candidate fallback stay with the owning lane.
+#define NRCU_BIGB_WARPS 8
+template <bool GATE>
+__global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
+                                                                       uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+    __shared__ BigList bl;
+    __shared__ unsigned short pairs[NRCU_BIGB_WARPS][32 * NRCU_MAX_BIG];
+    __shared__ float rays[NRCU_BIGB_WARPS][6][32];
+    __shared__ unsigned long long best[NRCU_BIGB_WARPS][32];
+    bl.load(s);
+    const uint32_t n = *n_ptr;
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned short* my_pairs = pairs[wib];
+    f4 a = mk4(0, 0, 0, 0); float2 b = make_float2(0.f, 0.f);
+    { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
+    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
+        const uint32_t i = base + lane;
+        Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
+        const RayPrep rp = prep_ray(r);
+        rays[wib][0][lane] = r.o.x; rays[wib][1][lane] = r.o.y; rays[wib][2][lane] = r.o.z;
+        rays[wib][3][lane] = r.d.x; rays[wib][4][lane] = r.d.y; rays[wib][5][lane] = r.d.z;
+        best[wib][lane] = ~0ull;
+        // pass 1: slab test of every wide primitive (warp-uniform loop, broadcast reads) -> candidate pairs, primitive-major
+        uint32_t mask = 0, total = 0;
+        for (uint32_t k = 0; k < s.n_big; k++) {
+            f4 lo = bl.bd[2 * k], hi = bl.bd[2 * k + 1];
+            float ax = fmaf(lo.x, rp.inv.x, -rp.oinv.x), bx = fmaf(hi.x, rp.inv.x, -rp.oinv.x);
+            float ay = fmaf(lo.y, rp.inv.y, -rp.oinv.y), by = fmaf(hi.y, rp.inv.y, -rp.oinv.y);
+            float az = fmaf(lo.z, rp.inv.z, -rp.oinv.z), bz = fmaf(hi.z, rp.inv.z, -rp.oinv.z);
+            float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+            float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            const bool cand = i < n && tn <= tf;
+            const uint32_t m = __ballot_sync(0xffffffffu, cand);
+            if (cand) { my_pairs[total + __popc(m & lt)] = (unsigned short)(lane | (k << 5)); mask |= 1u << k; }
+            total += __popc(m);
+        }
+        { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; } }   // prefetch
+        __syncwarp();
+        // pass 2: 32 exact tests per round
+        for (uint32_t jb = 0; jb < total; jb += 32u) {
+            const uint32_t j = jb + lane;
+            if (j < total) {
+                const uint32_t p = my_pairs[j], ol = p & 31u, k = p >> 5;
+                Ray pr; pr.o = mk3(rays[wib][0][ol], rays[wib][1][ol], rays[wib][2][ol]); pr.d = mk3(rays[wib][3][ol], rays[wib][4][ol], rays[wib][5][ol]);
+                const uint32_t hi32 = (uint32_t)(best[wib][ol] >> 32);
+                float bt = hi32 == 0xffffffffu ? NRCU_INF : __uint_as_float(hi32);   // the owner's best so far: only culls
+                int bi = 0x7fffffff;                                                  // accept ties: atomicMin settles them by id
+                prim_test<false>(pr, mk3(0.f), bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b, bl.m[k], bt, bi);
+                if (bi != 0x7fffffff) atomicMin(&best[wib][ol], ((unsigned long long)__float_as_uint(bt) << 32) | (unsigned long long)(((uint32_t)bi << 5) | k));
+            }
+        }
+        __syncwarp();
+        bool more = false;
+        if (i < n) {
+            const unsigned long long key = best[wib][lane];
+            float best_t = NRCU_INF; int best_id = -1;
+            if (key != ~0ull) {
+                best_t = __uint_as_float((uint32_t)(key >> 32)); best_id = (int)((uint32_t)key >> 5);
+                if (GATE) {
+                    const uint32_t kb = (uint32_t)key & 31u;
+                    const vec3 ginv = gate_inverse(r, rp);
+                    if (!bounds_intersectp_inv(bl.b[2 * kb], bl.b[2 * kb + 1], r, ginv.x, ginv.y, ginv.z)) {   // rare: gate per candidate
+                        best_t = NRCU_INF; best_id = -1;
+                        for (uint32_t m = mask; m; m &= m - 1u) {
+                            const uint32_t k = (uint32_t)(__ffs((int)m) - 1);
+                            prim_test<true>(r, ginv, bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b + 2 * k, bl.m[k], best_t, best_id);
+                        }
+                    }
+                }
+            }
+            hits[i] = make_float2(best_t, __int_as_float(best_id));
+            more = bvh_reachable(s, rp, best_t);
+        }
+        __syncwarp();   // the shared lists are rewritten by the next iteration
+        if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        append_survivors(more, i, surv, n_surv);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Closest hit, stage 2: BVH4 traversal of the surviving rays
 // ---------------------------------------------------------------------------------------------
@@ -245,7 +334,7 @@ __device__ __forceinline__ bool fetch_ray(const DScene& s, const PathQueue& q, c
     f4 a = q.a[i]; float2 b = q.b[i];
     L.r.o = mk3(a.x, a.y, a.z); L.r.d = mk3(a.w, b.x, b.y);
     L.rp = prep_ray(L.r);
-    if (GATE) L.ginv = gate_inverse(L.r);
+    if (GATE) L.ginv = gate_inverse(L.r, L.rp);
     L.best_t = NRCU_INF; L.best_id = -1;
     if (surv) { float2 h = hits[i]; L.best_t = h.x; L.best_id = __float_as_int(h.y); }
     L.sp = 0; L.idx = i;
