@@ -551,10 +551,25 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     if (NP > 1 && !explicit_k) k = std::max<uint32_t>(1, k / (uint32_t)NP);
     NP = std::max(1, std::min<int>(NP, (int)((s1 - s0 + k - 1) / k)));   // also with no samples at all: one (idle) wave set
     const unsigned share = (unsigned)NP;
-    const uint32_t slots = k * npix;
-    const uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
+    uint32_t slots = k * npix;
+    uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
     int rc;
-    for (int p = 0; p < NP; p++) if ((rc = ensure_wave(ctx, p, slots, capacity, ds.depth, glass_branch != 0, nee)) != NRCU_OK) return rc;
+    for (;;) {   // the default wave size assumes a B200's 180 GB; on a fuller or smaller device shrink the waves instead of failing
+        rc = NRCU_OK;
+        for (int p = 0; p < NP && rc == NRCU_OK; p++) rc = ensure_wave(ctx, p, slots, capacity, ds.depth, glass_branch != 0, nee);
+        if (rc == NRCU_OK) break;
+        cudaError_t last = cudaGetLastError();
+        (void)last;
+        if (explicit_k || k == 1 || ctx->error.find("out of memory") == std::string::npos) return rc;
+        for (int p = 0; p < NP; p++) {
+            nrcu_ctx::WaveSet& w = ctx->ws[p];
+            DevBuf* all[] = {&w.qa[0], &w.qa[1], &w.qb[0], &w.qb[1], &w.qc[0], &w.qc[1], &w.qd[0], &w.qd[1], &w.sa, &w.sb, &w.sc, &w.sd, &w.hits, &w.surv, &w.L};
+            for (DevBuf* bfr : all) bfr->release();
+        }
+        k = std::max<uint32_t>(1, k / 2);
+        slots = k * npix;
+        capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
+    }
     cudaStream_t S[NRCU_MAX_WAVES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
     if (NP > 1) {
         for (int p = 1; p < NP; p++) {
