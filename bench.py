@@ -237,7 +237,7 @@ def cuda_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     ms, ms_trace, ms_shade, ms_fused = t.tolist()
-    ms_closest = ms_trace + ms_fused   # k_raygen (fused stage 1) + k_big + k_trace2  (+ k_shade<SHADE_STAGE1> when NRCU_PIPELINE=1)
+    ms_closest = ms_trace + ms_fused   # k_raygen (fused stage 1) + k_big_balanced + k_trace2 (ms_fused is a reserved field, 0)
     rays, paths, launches = sums.tolist()
     launches += args.steps * (1 if rank == 0 else 0)   # resolve
     value = paths / (ms * 1e-3) * 1e-6
@@ -296,7 +296,7 @@ def cuda_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": profile_summary().get("closest_hit", {}).get("dram_bytes_per_launch"),
                          "algorithmic_bytes_per_launch": (rays * bytes_per_ray / max(closest_hit_launches, 1)) if closest_hit_launches else None,
-                         "kernel": "closest hit = k_raygen (camera rays + fused stage 1) + k_big + k_trace2", "algorithmic_bytes_per_ray": bytes_per_ray,
+                         "kernel": "closest hit = k_raygen (camera rays + fused stage 1) + k_big_balanced + k_trace2", "algorithmic_bytes_per_ray": bytes_per_ray,
                          "peak_source": peak_src, "share_of_step": ms_closest / ms if ms else None, "concurrent_waves": 2,
                          "note": "two waves run side by side on two streams, so kernel times (summed per launch) overlap and their share of the step can exceed 1; "
                                  "algorithmic bytes are those of the REFERENCE's traversal (SURVEY 8d); the scene is L1/L2 resident, so the "
