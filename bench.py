@@ -221,7 +221,7 @@ def cuda_arm(args):
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"rays": 0, "paths": 0, "kernel_launches": 0, "ms_trace": 0.0, "ms_shade": 0.0, "ms_fused": 0.0}
+    agg = {"rays": 0, "paths": 0, "kernel_launches": 0, "ms_trace": 0.0, "ms_shade": 0.0, "ms_stage2": 0.0}
     ev0.record()
     for _ in range(args.steps):
         st = step(True)
@@ -231,13 +231,13 @@ def cuda_arm(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_fused"]], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_stage2"]], dtype=torch.float64, device=dev)
     sums = torch.tensor([agg["rays"], agg["paths"], agg["kernel_launches"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, ms_trace, ms_shade, ms_fused = t.tolist()
-    ms_closest = ms_trace + ms_fused   # k_raygen (fused stage 1) + k_big_balanced + k_trace2 (ms_fused is a reserved field, 0)
+    ms, ms_trace, ms_shade, ms_stage2 = t.tolist()
+    ms_closest = ms_trace               # k_raygen (fused stage 1) + k_big_balanced + k_trace2; ms_stage2 = the k_trace2 part
     rays, paths, launches = sums.tolist()
     launches += args.steps * (1 if rank == 0 else 0)   # resolve
     value = paths / (ms * 1e-3) * 1e-6
@@ -290,7 +290,7 @@ def cuda_arm(args):
                        "l2": "256 MB flush buffer written between steps; per-wave ray/path state (~7 GB) exceeds the 126 MB L2",
                        "glass_mode": "stochastic", "seed": args.seed},
             "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / max(paths, 1),
-            "kernel_ms": {"closest_hit": ms_closest / args.steps, "shade": ms_shade / args.steps},
+            "kernel_ms": {"closest_hit": ms_closest / args.steps, "of_which_bvh_traversal": ms_stage2 / args.steps, "shade": ms_shade / args.steps},
             "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "clocks": e2e_clocks},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
@@ -303,6 +303,17 @@ def cuda_arm(args):
                                  "fraction can exceed 1 and the binding limit is issue slots x warp efficiency: see 'issue' (from the committed "
                                  "ncu launch list, profiles/) and DESIGN.md section 5",
                          "issue": profile_summary().get("issue")},
+            # the same kernels against the HBM roofline with THIS implementation's algorithmic bytes per ray
+            "roofline_kernels": [
+                {"kernel": "k_shade", "bound": "hbm", "algorithmic_bytes_per_ray": 88.0, "achieved": rays * 88.0 / (ms_shade * 1e-3) * 1e-9 if ms_shade > 0 else None,
+                 "peak": peak, "unit": "GB/s", "frac": rays * 88.0 / (ms_shade * 1e-3) * 1e-9 / peak if ms_shade > 0 else None,
+                 "traffic": profile_summary().get("kernels", {}).get("k_shade<1, 0>", {}).get("dram_bytes_per_launch")},
+                {"kernel": "k_raygen + k_big_balanced (stage 1)", "bound": "issue", "algorithmic_bytes_per_ray": 36.0,
+                 "achieved": rays * 36.0 / ((ms_trace - ms_stage2) * 1e-3) * 1e-9 if ms_trace > ms_stage2 else None, "peak": peak, "unit": "GB/s",
+                 "frac": rays * 36.0 / ((ms_trace - ms_stage2) * 1e-3) * 1e-9 / peak if ms_trace > ms_stage2 else None,
+                 "traffic": profile_summary().get("kernels", {}).get("k_big_balanced<1>", {}).get("dram_bytes_per_launch"),
+                 "issue_active_pct": profile_summary().get("kernels", {}).get("k_big_balanced<1>", {}).get("issue_active_pct")},
+            ],
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

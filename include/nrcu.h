@@ -209,7 +209,7 @@ typedef struct nrcu_stats {
     uint32_t bvh_nodes;        /* wide nodes */
     uint32_t n_primitives;     /* primitives after mesh flattening */
     uint32_t max_queue;        /* high-water mark of the ray queue */
-    float ms_fused;            /* reserved (0) */
+    float ms_stage2;           /* the part of ms_trace spent in the BVH traversal kernels (k_trace*) */
 } nrcu_stats;
 
 /* --- lifetime ------------------------------------------------------------------------- */

@@ -649,18 +649,19 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
                     else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
                     CTX_LAUNCH_CHECK("k_big");
                 }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i, ev_i + 3, 0}); }
                 if (bvh) {
                     if (gate) launch_stage2<true>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + d, pp.d_fetch + d, d_rays, d);
                     else launch_stage2<false>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + d, pp.d_fetch + d, d_rays, d);
                     CTX_LAUNCH_CHECK("k_trace");
                 }
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i + 3, ev_i + 1, 2}); }
 #define NRCU_SHADE(G, N) k_shade<G, N><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, pp.d_qn + d, pp.hb, qo, pp.d_qn + d + 1, capacity, pp.L, pp.qs, pp.d_nshadow + d)
                 if (gate) { if (nee) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
                 else { if (nee) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
 #undef NRCU_SHADE
                 CTX_LAUNCH_CHECK("k_shade");
-                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 4; }
                 if (glass_branch) {   // only the branching mode can outgrow the queue
                     k_clamp_count<<<1, 1, 0, st>>>(pp.d_qn + d + 1, capacity, cnt0 + CNT_HIGH_WATER);
                     CTX_LAUNCH_CHECK("k_clamp_count");
@@ -702,7 +703,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         for (auto& sp : spans) {   // with two streams the spans of the two waves overlap: the sums exceed ms_total
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]);
-            if (sp.kind == 0) stats->ms_trace += ms; else stats->ms_shade += ms;
+            if (sp.kind == 0) stats->ms_trace += ms; else if (sp.kind == 2) { stats->ms_trace += ms; stats->ms_stage2 += ms; } else stats->ms_shade += ms;
         }
         unsigned long long rays; std::memcpy(&rays, h_cnt + CNT_RAYS, 8);
         stats->rays = rays; stats->paths = (uint64_t)npix * (s1 - s0);
@@ -807,7 +808,7 @@ int nrcu_render_progressive(nrcu_ctx* ctx, const nrcu_render_params* params, uin
         CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
         CTX_CUDA(cudaStreamSynchronize(st));
         total.paths += part.paths; total.rays += part.rays; total.kernel_launches += part.kernel_launches + 1;
-        total.ms_total += part.ms_total; total.ms_trace += part.ms_trace; total.ms_shade += part.ms_shade; total.ms_fused += part.ms_fused;
+        total.ms_total += part.ms_total; total.ms_trace += part.ms_trace; total.ms_shade += part.ms_shade; total.ms_stage2 += part.ms_stage2;
         total.max_queue = std::max(total.max_queue, part.max_queue);
         total.ms_setup = part.ms_setup; total.bvh_nodes = part.bvh_nodes; total.n_primitives = part.n_primitives;
         if (on_update && on_update(user, rgba_out, p.sample_end, spp) != 0) break;
@@ -882,7 +883,7 @@ int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params
         for (int g = 0; g < n_ctx; g++) {
             stats->paths += st[g].paths; stats->rays += st[g].rays; stats->kernel_launches += st[g].kernel_launches;
             stats->ms_trace = std::max(stats->ms_trace, st[g].ms_trace); stats->ms_shade = std::max(stats->ms_shade, st[g].ms_shade);
-            stats->ms_fused = std::max(stats->ms_fused, st[g].ms_fused);
+            stats->ms_stage2 = std::max(stats->ms_stage2, st[g].ms_stage2);
             stats->max_queue = std::max(stats->max_queue, st[g].max_queue);
         }
         stats->kernel_launches += 1;
