@@ -84,7 +84,7 @@ struct DCamera {   // Camera ctor results, ray_cast/include/Camera.hpp:25-46
 #define NRCU_LIGHT_F4 6
 #define NRCU_MAX_BIG 32       // capacity of the wide-primitive list
 #ifndef NRCU_BIG_AREA_FRACTION
-#define NRCU_BIG_AREA_FRACTION 0.02f
+#define NRCU_BIG_AREA_FRACTION 0.01f
 #endif
 //   // a primitive is "wide" when its box has >= this fraction of the scene box's surface area
 
