@@ -14,7 +14,10 @@
 // read from / written to `.nrsc` flat-scene fixtures so that it works where /root/reference is absent.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <chrono>
+#include <cstdint>
+#include <cstring>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -44,13 +47,53 @@ void Asset::updateLightGlDrawData(LightItem&) {}
 
 using namespace NRenderer;
 
+// Minimal PNG writer (8-bit RGB, zlib "stored" blocks: no compressor needed, any viewer reads it).
+namespace {
+uint32_t crc32_update(uint32_t c, const unsigned char* p, size_t n) {
+    static uint32_t table[256];
+    if (!table[1]) for (uint32_t i = 0; i < 256; i++) { uint32_t v = i; for (int k = 0; k < 8; k++) v = (v >> 1) ^ (0xEDB88320u & (0u - (v & 1u))); table[i] = v; }
+    for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    return c;
+}
+void be32(std::vector<unsigned char>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back((unsigned char)(x >> s)); }
+void png_chunk(std::ofstream& o, const char* tag, const std::vector<unsigned char>& body) {
+    std::vector<unsigned char> c; be32(c, (uint32_t)body.size());
+    c.insert(c.end(), tag, tag + 4); c.insert(c.end(), body.begin(), body.end());
+    be32(c, crc32_update(0xFFFFFFFFu, c.data() + 4, c.size() - 4) ^ 0xFFFFFFFFu);
+    o.write((const char*)c.data(), c.size());
+}
+void write_png_rgb8(std::ofstream& o, const std::vector<unsigned char>& rgb, unsigned w, unsigned h) {
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1A, '\n'};
+    o.write((const char*)sig, 8);
+    std::vector<unsigned char> ihdr; be32(ihdr, w); be32(ihdr, h);
+    for (unsigned char b : {8, 2, 0, 0, 0}) ihdr.push_back(b);          // 8 bit, colour type 2 (RGB)
+    png_chunk(o, "IHDR", ihdr);
+    std::vector<unsigned char> raw; raw.reserve((size_t)h * (3 * (size_t)w + 1));
+    for (unsigned y = 0; y < h; y++) { raw.push_back(0); raw.insert(raw.end(), rgb.begin() + (size_t)y * 3 * w, rgb.begin() + (size_t)(y + 1) * 3 * w); }
+    std::vector<unsigned char> z = {0x78, 0x01};
+    uint32_t a = 1, b = 0;
+    for (size_t i = 0; i < raw.size(); i++) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+    for (size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+        size_t n = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + n >= raw.size() ? 1 : 0);
+        z.push_back((unsigned char)(n & 0xFF)); z.push_back((unsigned char)(n >> 8));
+        z.push_back((unsigned char)(~n & 0xFF)); z.push_back((unsigned char)((~n >> 8) & 0xFF));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        if (raw.empty()) break;
+    }
+    be32(z, (b << 16) | a);
+    png_chunk(o, "IDAT", z);
+    png_chunk(o, "IEND", {});
+}
+}  // namespace
+
 static void usage() {
     std::fprintf(stderr,
         "usage: nr_headless [--scn F|--obj F]... | --flat F.nrsc\n"
         "         [--mesh-material K] [--texture IMG] [--env-map TEXIDX]\n"
         "         [--w W --h H --depth D --spp S --aspect A --ambient R G B]\n"
         "         [--dump-flat OUT.nrsc]\n"
-        "         [--plugin LIB.so]... [--component NAME --out FRAME.f32|.ppm|.pfm] [--repeat N] [--list]\n");
+        "         [--plugin LIB.so]... [--component NAME --out FRAME.f32|.ppm|.png|.pfm] [--repeat N] [--list]\n");
 }
 
 int main(int argc, char** argv) {
@@ -169,22 +212,20 @@ int main(int argc, char** argv) {
     unsigned sw = screen.getWidth(), sh = screen.getHeight();
     if (!out.empty()) {
         // The reference has no image export at all.  By extension:
-        //   .ppm  8-bit RGB of the published frame (already sqrt-gamma'd and clamped by Screen::set), row 0 = top
+        //   .ppm / .png  8-bit RGB of the published frame (already sqrt-gamma'd and clamped by Screen::set), row 0 = top
         //   .pfm  RGB fp32, little endian, rows bottom-to-top as the format requires
         //   else  raw RGBA fp32 exactly as getServer().screen holds it (what the parity tests read)
         const RGBA* px = screen.getPixels();
         auto ends_with = [&](const char* ext) { std::string e(ext); return out.size() >= e.size() && out.compare(out.size() - e.size(), e.size(), e) == 0; };
         std::ofstream o(out, std::ios::binary);
-        if (ends_with(".ppm")) {
-            o << "P6\n" << sw << " " << sh << "\n255\n";
-            std::vector<unsigned char> row(3 * (size_t)sw);
-            for (unsigned y = 0; y < sh; y++) {
-                for (unsigned x = 0; x < sw; x++) for (int c = 0; c < 3; c++) {
-                    float v = px[(size_t)y * sw + x][c]; v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
-                    row[3 * x + c] = (unsigned char)(v * 255.f + 0.5f);
-                }
-                o.write((const char*)row.data(), row.size());
+        if (ends_with(".ppm") || ends_with(".png")) {
+            std::vector<unsigned char> rgb(3 * (size_t)sw * sh);
+            for (size_t i = 0; i < (size_t)sw * sh; i++) for (int c = 0; c < 3; c++) {
+                float v = px[i][c]; v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+                rgb[3 * i + c] = (unsigned char)(v * 255.f + 0.5f);
             }
+            if (ends_with(".png")) write_png_rgb8(o, rgb, sw, sh);
+            else { o << "P6\n" << sw << " " << sh << "\n255\n"; o.write((const char*)rgb.data(), rgb.size()); }
         } else if (ends_with(".pfm")) {
             o << "PF\n" << sw << " " << sh << "\n-1.0\n";
             std::vector<float> row(3 * (size_t)sw);

@@ -62,12 +62,12 @@ def test_cuda_plugins_register_through_the_reference_factory():
 
 @pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
 def test_harness_image_writers(tmp_path):
-    """--out by extension: raw RGBA fp32, .pfm (bottom-up RGB fp32) and .ppm (8-bit) hold the same published frame."""
+    """--out by extension: raw RGBA fp32, .pfm (bottom-up RGB fp32) and .ppm / .png (8-bit) hold the same published frame."""
     env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
     base = [os.path.join(po.REF_DIR, "nr_headless"), "--flat", os.path.join(GOLDEN, "ray_cast_cornel.nrsc"), "--w", "40", "--h", "30",
             "--plugin", os.path.join(po.REF_DIR, po.REF_PLUGINS["RayCast"]), "--component", "RayCast", "--out"]
-    raw, pfm, ppm = tmp_path / "f.f32", tmp_path / "f.pfm", tmp_path / "f.ppm"
-    for o in (raw, pfm, ppm):
+    raw, pfm, ppm, png = tmp_path / "f.f32", tmp_path / "f.pfm", tmp_path / "f.ppm", tmp_path / "f.png"
+    for o in (raw, pfm, ppm, png):
         subprocess.run(base + [str(o)], check=True, env=env, capture_output=True)
     img = np.fromfile(raw, np.float32).reshape(30, 40, 4)
     head, data = pfm.read_bytes().split(b"-1.0\n", 1)
@@ -77,3 +77,17 @@ def test_harness_image_writers(tmp_path):
     assert head == b"P6\n40 30\n"
     want = (np.clip(img[..., :3], 0, 1) * 255 + 0.5).astype(np.uint8)
     assert np.array_equal(np.frombuffer(data, np.uint8).reshape(30, 40, 3), want)
+    # PNG: signature, chunk CRCs, zlib stream (stored blocks + adler32) and the scanlines (filter byte 0)
+    import struct, zlib
+    blob = png.read_bytes()
+    assert blob[:8] == b"\x89PNG\r\n\x1a\n"
+    off, chunks = 8, []
+    while off < len(blob):
+        n, tag = struct.unpack(">I4s", blob[off:off + 8])
+        body = blob[off + 8:off + 8 + n]
+        assert struct.unpack(">I", blob[off + 8 + n:off + 12 + n])[0] == zlib.crc32(tag + body)
+        chunks.append((tag, body)); off += 12 + n
+    assert [t for t, _ in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+    assert struct.unpack(">IIBBBBB", chunks[0][1]) == (40, 30, 8, 2, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(30, 1 + 3 * 40)
+    assert not rows[:, 0].any() and np.array_equal(rows[:, 1:].reshape(30, 40, 3), want)
