@@ -52,10 +52,11 @@ def load_library() -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
-        raise NrcuError(f"{LIB_PATH} is missing: build it with `python -m nrenderer_b200.build` "
+    path = os.environ.get("NRCU_LIBRARY") or LIB_PATH   # NRCU_LIBRARY: an experiment build (build.py --variant)
+    if not os.path.exists(path):
+        raise NrcuError(f"{path} is missing: build it with `python -m nrenderer_b200.build` "
                         "(there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
     L.nrcu_abi_version.restype = i32
     L.nrcu_device_count.restype = i32

@@ -33,12 +33,16 @@ def cuda_sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(REPO, "include", "nrcu.h")]
 
 
-def build_cuda(force=False, verbose=False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> nrenderer_b200/libnrcuda.so"""
-    if not force and not _newer(LIB, cuda_sources()):
-        return LIB
+def build_cuda(force=False, verbose=False, variant=None, defines=()) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> nrenderer_b200/libnrcuda.so
+
+    `variant` + `defines` build an experiment copy, libnrcuda.<variant>.so, with extra -D flags (same-call A/B
+    measurements: api.py loads the library named by NRCU_LIBRARY instead of the default one)."""
+    lib = LIB if not variant else os.path.join(PKG, f"libnrcuda.{variant}.so")
+    if not force and not variant and not _newer(lib, cuda_sources()):
+        return lib
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + [f"-I{REPO}/include", f"-I{CSRC}", os.path.join(CSRC, "nrcu_api.cu"), "-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + [f"-I{REPO}/include", f"-I{CSRC}", os.path.join(CSRC, "nrcu_api.cu"), "-o", lib]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -46,7 +50,7 @@ def build_cuda(force=False, verbose=False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return lib
 
 
 def plugin_path(mode: int) -> str:
@@ -79,5 +83,9 @@ def build_plugins(force=False):
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:   # python -m nrenderer_b200.build --variant TAG -DFOO=1 ...
+        tag = sys.argv[sys.argv.index("--variant") + 1]
+        print(build_cuda(force=True, verbose="-v" in sys.argv, variant=tag, defines=[a for a in sys.argv if a.startswith("-D")]))
+        sys.exit(0)
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_plugins(force="--force" in sys.argv))
