@@ -44,7 +44,7 @@ NR_HD void build_prim(const PrimSources& ps, uint32_t i, int raycast, f4* geom, 
         vec3 c = ld3(ps.sphere_position + 3 * e); float r = ps.sphere_radius[e];
         material = ps.sphere_material[e];
         geom[3 * i] = mk4(c.x, c.y, c.z, r); geom[3 * i + 1] = mk4(0, 0, 0, 0); geom[3 * i + 2] = mk4(0, 0, 0, 0);
-        shade[i] = mk4(0, 0, 0, i2f(material));
+        shade[i] = mk4(0, 0, 0, i2f((int)(((uint32_t)material << 2) | kind)));
         lo = c - r; hi = c + r;
         if (export16) { float* o = export16 + 16 * (size_t)i; for (int k = 0; k < 16; k++) o[k] = 0.f; st3(o, c); o[3] = r; }
     } else if (kind == KIND_PLANE) {
@@ -54,7 +54,7 @@ NR_HD void build_prim(const PrimSources& ps, uint32_t i, int raycast, f4* geom, 
         float r0[3], r1[3];
         quad_inverse_rows(u, v, r0, r1);
         geom[3 * i] = mk4(nn.x, nn.y, nn.z, p.x); geom[3 * i + 1] = mk4(p.y, p.z, r0[0], r0[1]); geom[3 * i + 2] = mk4(r0[2], r1[0], r1[1], r1[2]);
-        shade[i] = mk4(nn.x, nn.y, nn.z, i2f(material));
+        shade[i] = mk4(nn.x, nn.y, nn.z, i2f((int)(((uint32_t)material << 2) | kind)));
         // Bounds3(Plane*), Bounds3.hpp:52-78 (uses the stored, un-normalised normal)
         vec3 p1 = p, p2 = p + u, p3 = p + v, p4 = p + u + v, en = 0.01f * n0;
         p1 = p1 - en; p2 = p2 - en; p3 = p3 + en; p4 = p4 + en;
@@ -79,7 +79,7 @@ NR_HD void build_prim(const PrimSources& ps, uint32_t i, int raycast, f4* geom, 
         if (raycast) nrm = normalize(nrm);              // ray_cast/.../intersections.cpp:9
         vec3 e1 = v2 - v1, e2 = v3 - v1;
         geom[3 * i] = mk4(v1.x, v1.y, v1.z, e1.x); geom[3 * i + 1] = mk4(e1.y, e1.z, e2.x, e2.y); geom[3 * i + 2] = mk4(e2.z, 0.f, 0.f, 0.f);
-        shade[i] = mk4(nrm.x, nrm.y, nrm.z, i2f(material));
+        shade[i] = mk4(nrm.x, nrm.y, nrm.z, i2f((int)(((uint32_t)material << 2) | kind)));
         lo = vmin(v1, vmin(v2, v3)); hi = vmax(v1, vmax(v2, v3));
         if (export16) { float* o = export16 + 16 * (size_t)i; for (int k = 0; k < 16; k++) o[k] = 0.f; st3(o, v1); st3(o + 3, v2); st3(o + 6, v3); st3(o + 9, nrm); }
     }

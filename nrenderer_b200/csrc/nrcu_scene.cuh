@@ -8,7 +8,7 @@
 //                  inverse(mat3(u, v, cross(u,v))) — the reference inverts this matrix per test
 //                  (intersections.cpp:64-66); the rows are a pure function of (u,v), so they are
 //                  precomputed with the same operation order and give bit-identical results.
-//   prim_shade[i]        (normal.xyz, material index bits) read once per hit by the shading kernel
+//   prim_shade[i]        (normal.xyz, kind | material << 2 as bits) read once per hit by the shading kernel
 //   prim_box[2i..2i+1]   (min.xyz -)(max.xyz -): the reference's Bounds3 of the leaf (Bounds3.hpp:35-103),
 //                        used for the AccPathTracer leaf gate and as BVH build input
 //   prim_meta[i]         kind | material << 2

@@ -57,9 +57,11 @@ NR_HD Ray pt_camera_ray(const DScene& s, uint64_t seed, uint32_t p, uint32_t sam
 
 // Surface normal of primitive `id` at the hit point.  Spheres: (hit - c)/r, outward even from the
 // inside (intersections.cpp:44-45); everything else: the stored normal (normalised at upload for RayCast).
-NR_HD vec3 hit_normal(const DScene& s, int id, uint32_t kind, vec3 hit_point, int& material) {
+// The record's w word is prim_meta[id] again (kind | material << 2): one gather per hit instead of two.
+NR_HD vec3 hit_normal(const DScene& s, int id, vec3 hit_point, int& material) {
     f4 sh = ldg4(s.prim_shade + id);
-    material = f2i(sh.w);
+    const uint32_t kind = (uint32_t)f2i(sh.w) & 3u;
+    material = (int)((uint32_t)f2i(sh.w) >> 2);
     if (kind == KIND_SPHERE) {
         f4 g0 = ldg4(s.prim_geom + 3 * (size_t)id);
         return (hit_point - mk3(g0.x, g0.y, g0.z)) / g0.w;
@@ -93,7 +95,7 @@ NR_HD vec3 raycast_pixel(const DScene& s, uint32_t p, uint32_t* ray_count) {
         if (id >= 0) {
             vec3 hp = ray_at(r, t);
             int material;
-            vec3 n = hit_normal(s, id, ldg_u32(s.prim_meta + id) & 3u, hp, material);
+            vec3 n = hit_normal(s, id, hp, material);
             vec3 out = normalize(s.point_position - hp);
             if (!(dot(out, n) < 0)) {
                 float distance = length(s.point_position - hp);
@@ -380,8 +382,7 @@ NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint3
     if (id >= 0 && t < tl) {
         vec3 hp = ray_at(ray, t);
         int material;
-        uint32_t kind = ldg_u32(s.prim_meta + id) & 3u;
-        vec3 n = hit_normal(s, id, kind, hp, material);
+        vec3 n = hit_normal(s, id, hp, material);
         const DMaterial& m = s.materials[material];
         uint32_t type = s.mode == MODE_ACC ? m.type : 0u;
         if (type == 2u) {
