@@ -57,6 +57,11 @@ struct DevBuf {
 
 static uint32_t env_u32(const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? (uint32_t)std::atoi(e) : dflt; }
 static uint32_t wave_skew_kb() { static uint32_t v = env_u32("NRCU_WAVE_SKEW_KB", 68); return v; }
+// Words between two device counters of a wave.  Every counter is the target of lane-0 atomics from all warps of a
+// kernel; the L2 serialises atomics per address and per slice (tools/micro/atomic_bench.cu: two addresses 128 B apart
+// are no faster than one), so the counters that kernels of the concurrent waves hammer at the same time are kept on
+// lines of their own.
+static size_t counter_stride() { static uint32_t v = env_u32("NRCU_COUNTER_STRIDE", 32); return (size_t)(v < 1 ? 1 : (v > 1024 ? 1024 : v)); }
 
 // sub-allocation of the BVH build arena
 struct Carve { char* base; size_t off; void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; } };
@@ -430,7 +435,7 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
 // ---------------------------------------------------------------------------------------------
 // rendering
 // ---------------------------------------------------------------------------------------------
-enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 4 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
+enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 64 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
 
 static int ensure_wave(nrcu_ctx* ctx, int set, uint32_t slots, uint32_t capacity, uint32_t depth, bool branch_bits, bool shadow_queue) {
     // The wave buffers are power-of-two sized (32 Mi x 16 B = 512 MiB) and the kernels stream through ten of
@@ -454,7 +459,7 @@ static int ensure_wave(nrcu_ctx* ctx, int set, uint32_t slots, uint32_t capacity
     }
     CTX_CUDA(w.surv.ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(w.L.ensure(sizeof(f4) * (size_t)slots));
-    CTX_CUDA(w.counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + 6 * (size_t)depth + 24)));
+    CTX_CUDA(w.counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + counter_stride() * (6 * (size_t)depth + 24))));
     return NRCU_OK;
 }
 
@@ -579,17 +584,17 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         if (!ctx->ev_fork) { CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
                              CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_acc, cudaEventDisableTiming)); }
     }
-    // shared by both waves: ray counter and high-water mark live in set 0's counter block
+    // the high-water mark lives in set 0's counter block; every wave counts its rays in its own block
     uint32_t* cnt0 = ctx->ws[0].counters.as<uint32_t>();
-    unsigned long long* d_rays = reinterpret_cast<unsigned long long*>(cnt0 + CNT_RAYS);
-    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + 6 * (size_t)ds.depth + 24);
+    const size_t CS = counter_stride();
+    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + CS * (6 * (size_t)ds.depth + 24));
     const int sms = sm_count(ctx->device);
     const unsigned shade_grid = (unsigned)sms * (NP > 1 ? dual_shade() : NRCU_SHADE_MINB), big_grid = (unsigned)sms * (NP > 1 ? dual_big() : 8);
     const bool timing = stats != nullptr, gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
     size_t ev_i = 0;
     struct Span { size_t a, b; int kind; };
     std::vector<Span> spans;
-    CTX_CUDA(cudaMemsetAsync(cnt0, 0, sizeof(uint32_t) * CNT_QUEUE0, S[0]));
+    for (int p = 0; p < NP; p++) CTX_CUDA(cudaMemsetAsync(ctx->ws[p].counters.p, 0, sizeof(uint32_t) * CNT_QUEUE0, S[0]));
     if (timing) CTX_CUDA(cudaEventRecord(ctx->ev_begin, S[0]));
     if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_fork, S[0])); for (int p = 1; p < NP; p++) CTX_CUDA(cudaStreamWaitEvent(S[p], ctx->ev_fork, 0)); }
     const uint64_t launches0 = ctx->launches;
@@ -598,7 +603,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     struct Pipe {
         bool live; uint32_t w0, kw, n_slots;
         PathQueue q[2], qs; uint32_t* cnt; uint32_t *d_qn, *d_fetch, *d_nsurv, *d_nshadow, *d_sfetch, *d_snsurv;
-        float2* hb; uint32_t* surv; f4* L; cudaStream_t st;
+        float2* hb; uint32_t* surv; f4* L; cudaStream_t st; unsigned long long* d_rays;
     } P[NRCU_MAX_WAVES];
     for (int p = 0; p < NP; p++) {
         nrcu_ctx::WaveSet& w = ctx->ws[p];
@@ -607,12 +612,14 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         for (int j = 0; j < 2; j++) pp.q[j] = PathQueue{w.qa[j].as<f4>(), w.qb[j].as<float2>(), w.qc[j].as<f4>(), glass_branch ? w.qd[j].as<uint32_t>() : nullptr};
         pp.qs = nee ? PathQueue{w.sa.as<f4>(), w.sb.as<float2>(), w.sc.as<f4>(), w.sd.as<uint32_t>()} : PathQueue{nullptr, nullptr, nullptr, nullptr};
         pp.cnt = w.counters.as<uint32_t>();
-        pp.d_qn = pp.cnt + CNT_QUEUE0;                          // queue size entering bounce d
-        pp.d_fetch = pp.cnt + CNT_QUEUE0 + ds.depth + 2;        // work-fetch cursor of bounce d
-        pp.d_nsurv = pp.cnt + CNT_QUEUE0 + 2 * (ds.depth + 2);  // stage-1 survivors of bounce d
-        pp.d_nshadow = pp.cnt + CNT_QUEUE0 + 3 * (ds.depth + 2);   // NEE: shadow rays of bounce d, their fetch cursors and survivors
-        pp.d_sfetch = pp.cnt + CNT_QUEUE0 + 4 * (ds.depth + 2);
-        pp.d_snsurv = pp.cnt + CNT_QUEUE0 + 5 * (ds.depth + 2);
+        pp.d_rays = reinterpret_cast<unsigned long long*>(pp.cnt + CNT_RAYS);
+        // counter (kind, bounce d) sits CS * (kind * (depth + 2) + d) words into the block
+        pp.d_qn = pp.cnt + CNT_QUEUE0;                               // queue size entering bounce d
+        pp.d_fetch = pp.cnt + CNT_QUEUE0 + CS * (ds.depth + 2);      // work-fetch cursor of bounce d
+        pp.d_nsurv = pp.cnt + CNT_QUEUE0 + CS * 2 * (ds.depth + 2);  // stage-1 survivors of bounce d
+        pp.d_nshadow = pp.cnt + CNT_QUEUE0 + CS * 3 * (ds.depth + 2);   // NEE: shadow rays of bounce d, their fetch cursors and survivors
+        pp.d_sfetch = pp.cnt + CNT_QUEUE0 + CS * 4 * (ds.depth + 2);
+        pp.d_snsurv = pp.cnt + CNT_QUEUE0 + CS * 5 * (ds.depth + 2);
         pp.hb = w.hits.as<float2>(); pp.surv = w.surv.as<uint32_t>(); pp.L = w.L.as<f4>();
     }
 
@@ -627,8 +634,8 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
             CTX_CUDA(cudaMemsetAsync(pp.cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
             const unsigned gen_grid = std::min<unsigned>(grid_for(pp.n_slots, 256), (unsigned)sms * 8);
             if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
-            if (gate) k_raygen<true, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, d_rays);
-            else k_raygen<false, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, d_rays);
+            if (gate) k_raygen<true, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, pp.d_rays);
+            else k_raygen<false, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, pp.d_rays);
             CTX_LAUNCH_CHECK("k_raygen");
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); ev_i += 2; }   // booked as closest-hit time: stage 1 of bounce 0 is most of this kernel
         }
@@ -642,40 +649,40 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                 if (d > 0) {
                     if (big_balanced()) {
-                        if (gate) k_big_balanced<true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
-                        else k_big_balanced<false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
+                        if (gate) k_big_balanced<true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
+                        else k_big_balanced<false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
                     }
-                    else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
-                    else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + d, pp.hb, pp.surv, pp.d_nsurv + d, d_rays);
+                    else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
+                    else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
                     CTX_LAUNCH_CHECK("k_big");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i, ev_i + 3, 0}); }
                 if (bvh) {
-                    if (gate) launch_stage2<true>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + d, pp.d_fetch + d, d_rays, d);
-                    else launch_stage2<false>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + d, pp.d_fetch + d, d_rays, d);
+                    if (gate) launch_stage2<true>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_fetch + CS * d, pp.d_rays, d);
+                    else launch_stage2<false>(ctx, st, share, ds, qi, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_fetch + CS * d, pp.d_rays, d);
                     CTX_LAUNCH_CHECK("k_trace");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i + 3, ev_i + 1, 2}); }
-#define NRCU_SHADE(G, N) k_shade<G, N><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, pp.d_qn + d, pp.hb, qo, pp.d_qn + d + 1, capacity, pp.L, pp.qs, pp.d_nshadow + d)
+#define NRCU_SHADE(G, N) k_shade<G, N><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, pp.d_qn + CS * d, pp.hb, qo, pp.d_qn + CS * (d + 1), capacity, pp.L, pp.qs, pp.d_nshadow + CS * d)
                 if (gate) { if (nee) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
                 else { if (nee) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
 #undef NRCU_SHADE
                 CTX_LAUNCH_CHECK("k_shade");
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 4; }
                 if (glass_branch) {   // only the branching mode can outgrow the queue
-                    k_clamp_count<<<1, 1, 0, st>>>(pp.d_qn + d + 1, capacity, cnt0 + CNT_HIGH_WATER);
+                    k_clamp_count<<<1, 1, 0, st>>>(pp.d_qn + CS * (d + 1), capacity, cnt0 + CNT_HIGH_WATER);
                     CTX_LAUNCH_CHECK("k_clamp_count");
-                    if (nee) { k_clamp_count<<<1, 1, 0, st>>>(pp.d_nshadow + d, capacity, cnt0 + CNT_HIGH_WATER); CTX_LAUNCH_CHECK("k_clamp_count"); }
+                    if (nee) { k_clamp_count<<<1, 1, 0, st>>>(pp.d_nshadow + CS * d, capacity, cnt0 + CNT_HIGH_WATER); CTX_LAUNCH_CHECK("k_clamp_count"); }
                 }
                 if (nee && d + 1 < ds.depth) {   // the shadow rays of this bounce: same closest-hit kernels, then visibility + add
                     if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                     int nl = 0;
-                    if (gate) launch_closest_hit<true>(ctx, st, share, ds, pp.qs, pp.d_nshadow + d, pp.hb, pp.surv, pp.d_snsurv + d, pp.d_sfetch + d, d_rays, &nl);
-                    else launch_closest_hit<false>(ctx, st, share, ds, pp.qs, pp.d_nshadow + d, pp.hb, pp.surv, pp.d_snsurv + d, pp.d_sfetch + d, d_rays, &nl);
+                    if (gate) launch_closest_hit<true>(ctx, st, share, ds, pp.qs, pp.d_nshadow + CS * d, pp.hb, pp.surv, pp.d_snsurv + CS * d, pp.d_sfetch + CS * d, pp.d_rays, &nl);
+                    else launch_closest_hit<false>(ctx, st, share, ds, pp.qs, pp.d_nshadow + CS * d, pp.hb, pp.surv, pp.d_snsurv + CS * d, pp.d_sfetch + CS * d, pp.d_rays, &nl);
                     ctx->launches += nl - 1;
                     CTX_LAUNCH_CHECK("k_big/k_trace (shadow)");
                     if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
-                    k_shadow_resolve<<<shade_grid, 256, 0, st>>>(ds, pp.qs, pp.d_nshadow + d, pp.hb, pp.L, glass_branch);
+                    k_shadow_resolve<<<shade_grid, 256, 0, st>>>(ds, pp.qs, pp.d_nshadow + CS * d, pp.hb, pp.L, glass_branch);
                     CTX_LAUNCH_CHECK("k_shadow_resolve");
                     if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 3; }
                 }
@@ -695,9 +702,10 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     if (timing) {
         cudaStream_t st = S[0];
         CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
-        uint32_t h_cnt[CNT_QUEUE0];
-        CTX_CUDA(cudaMemcpyAsync(h_cnt, cnt0, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        uint32_t h_cnt[4], h_wave[NRCU_MAX_WAVES][4];
+        for (int p = 0; p < NP; p++) CTX_CUDA(cudaMemcpyAsync(h_wave[p], ctx->ws[p].counters.p, sizeof(h_wave[p]), cudaMemcpyDeviceToHost, st));
         CTX_CUDA(cudaStreamSynchronize(st));
+        std::memcpy(h_cnt, h_wave[0], sizeof(h_cnt));
         std::memset(stats, 0, sizeof(*stats));
         CTX_CUDA(cudaEventElapsedTime(&stats->ms_total, ctx->ev_begin, ctx->ev_end));
         for (auto& sp : spans) {   // with two streams the spans of the two waves overlap: the sums exceed ms_total
@@ -705,7 +713,8 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
             cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]);
             if (sp.kind == 0) stats->ms_trace += ms; else if (sp.kind == 2) { stats->ms_trace += ms; stats->ms_stage2 += ms; } else stats->ms_shade += ms;
         }
-        unsigned long long rays; std::memcpy(&rays, h_cnt + CNT_RAYS, 8);
+        unsigned long long rays = 0;
+        for (int p = 0; p < NP; p++) { unsigned long long r; std::memcpy(&r, h_wave[p] + CNT_RAYS, 8); rays += r; }
         stats->rays = rays; stats->paths = (uint64_t)npix * (s1 - s0);
         stats->kernel_launches = ctx->launches - launches0;
         stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
