@@ -72,6 +72,19 @@ def profile_summary():
         return {}
 
 
+def issue_roofline(workload, paths, ms, clocks, world=1):
+    """The binding roofline: warp instructions per path sample (committed ncu launch list of this workload) x the paths of
+    the timed region / its live CUDA-event time, against 148 SMs x 4 schedulers x the SM clock sampled during the run."""
+    d = dict(profile_summary().get("issue") or {})
+    wipp = d.get("warp_inst_per_path_sample")
+    if wipp and workload == DEFAULT_WORKLOAD and ms > 0:
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak = 148 * 4 * mhz * world              # warp instructions per microsecond, all GPUs
+        d["step"] = {"bound": "issue", "achieved": wipp * paths / (ms * 1e3), "peak": peak, "unit": "warp-inst/us", "frac": wipp * paths / (ms * 1e3) / peak,
+                     "sm_mhz": mhz, "note": "whole step, all kernels, both concurrent waves"}
+    return d
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -302,7 +315,7 @@ def cuda_arm(args):
                                  "algorithmic bytes are those of the REFERENCE's traversal (SURVEY 8d); the scene is L1/L2 resident, so the "
                                  "fraction can exceed 1 and the binding limit is issue slots x warp efficiency: see 'issue' (from the committed "
                                  "ncu launch list, profiles/) and DESIGN.md section 5",
-                         "issue": profile_summary().get("issue")},
+                         "issue": issue_roofline(args.workload, paths, ms, clocks, world)},
             # the same kernels against the HBM roofline with THIS implementation's algorithmic bytes per ray
             "roofline_kernels": [
                 {"kernel": "k_shade", "bound": "hbm", "algorithmic_bytes_per_ray": 88.0, "achieved": rays * 88.0 / (ms_shade * 1e-3) * 1e-9 if ms_shade > 0 else None,

@@ -88,3 +88,13 @@ def test_product_does_not_touch_the_oracle():
                     assert not re.search(pat, txt, flags=re.M), (f, pat)
     out = os.popen(f"ldd {pkg}/libnrcuda.so").read()
     assert "oracle" not in out and "emu" not in out
+
+
+def test_missing_library_is_a_loud_failure(tmp_path):
+    """The binding never falls back: a library path that does not exist (NRCU_LIBRARY names an experiment build) raises."""
+    code = ("import os; os.environ['NRCU_LIBRARY'] = %r\n"
+            "from nrenderer_b200 import api\n"
+            "try:\n    api.load_library()\nexcept api.NrcuError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n") % str(tmp_path / "libnrcuda.nope.so")
+    import subprocess, sys
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=REPO).stdout
+    assert "RAISED True" in out

@@ -18,6 +18,7 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SMS, SCHEDULERS = 148, 4
+PATHS_PER_WAVE = 32 * 1920 * 1080   # bench.py default workload (cfg3): 64 Mi path slots per wave -> 32 spp of 1080p
 KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -77,6 +78,12 @@ def main():
                           warp_inst=a["warp_inst"], threads_per_inst=round(a["lane_inst"] / max(a["warp_inst"], 1), 2),
                           issue_active_pct=round(a["issue_w"] / max(a["time_us"], 1e-9), 1),
                           dram_bytes_per_launch=round(a["dram"] / a["launches"]), dram_gbs=round(a["dram"] / (a["time_us"] * 1e-6) * 1e-9, 1))
+    # warp instructions of the complete waves in the capture (everything up to the last k_accumulate), per path sample:
+    # a wave of the bench workload is 32 samples of 1920 x 1080 pixels
+    last_acc = max((i for i, d in enumerate(render) if d["kernel"].startswith("k_accumulate")), default=-1)
+    n_waves = sum(1 for d in render if d["kernel"].startswith("k_accumulate"))
+    inst_complete = sum(d.get("smsp__inst_executed.sum", 0) for d in render[:last_acc + 1])
+    warp_inst_per_path = inst_complete / (n_waves * PATHS_PER_WAVE) if n_waves else None
     ch = [k for k in kernels if k.startswith(("k_raygen", "k_big", "k_trace"))]
     ch_time = sum(kernels[k]["time_us"] for k in ch)
     ch_inst = sum(kernels[k]["warp_inst"] for k in ch)
@@ -100,7 +107,8 @@ def main():
         # closest-hit DRAM traffic per captured unit of work, and the issue-slot utilisation of the closest-hit kernels:
         # warp instructions issued / (elapsed cycles x 148 SMs x 4 schedulers), clock from the capture (1.965 GHz locked by ncu --clock-control none = application clocks)
         "closest_hit_dram_bytes_per_step_equiv": None,
-        "issue": {"closest_hit_warp_inst_per_us": round(ch_inst / ch_time, 1),
+        "issue": {"warp_inst_per_path_sample": warp_inst_per_path, "complete_waves_in_capture": n_waves, "paths_per_wave": PATHS_PER_WAVE,
+                  "closest_hit_warp_inst_per_us": round(ch_inst / ch_time, 1),
                   "peak_warp_inst_per_us_at_1965MHz": SMS * SCHEDULERS * 1965.0,
                   "frac_of_issue_peak": round(ch_inst / ch_time / (SMS * SCHEDULERS * 1965.0), 4),
                   "threads_per_inst": {k: kernels[k]["threads_per_inst"] for k in ch},
