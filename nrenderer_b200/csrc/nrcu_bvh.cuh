@@ -83,7 +83,7 @@ struct BvhBuild {
     f4* leaf_geom;             // [n_prims * 3] prim_geom in leaf order
     f4* leaf_box;              // [n_prims * 2] prim_box in leaf order
     // wide-primitive list (outputs of bvh_select_big)
-    f4* big_geom; f4* big_box; f4* big_bound; uint32_t* big_meta;   // capacity NRCU_MAX_BIG; big_bound = padded true bounds
+    f4* big_geom; f4* big_box; f4* big_bound; uint32_t* big_meta;   // capacity NRCU_MAX_BIG; big_bound = padded true bounds as (centre, half extent)
     int* big_count;            // [1]
     int* big_cand;             // [NRCU_BIG_CAND_CAP] ids whose box is large enough (unordered), filled by bvh_big_candidate
     int* big_cand_count;       // [1]
@@ -184,7 +184,12 @@ NR_HD void bvh_select_big(const BvhBuild& b, int) {
         f4 lo = b.prim_bound[2 * (size_t)id], hi = b.prim_bound[2 * (size_t)id + 1];
         float px = b.inflate + 1e-6f * fmaxf(fabsf(lo.x), fabsf(hi.x)), py = b.inflate + 1e-6f * fmaxf(fabsf(lo.y), fabsf(hi.y)),
               pz = b.inflate + 1e-6f * fmaxf(fabsf(lo.z), fabsf(hi.z));
-        b.big_bound[2 * k] = mk4(lo.x - px, lo.y - py, lo.z - pz, 0.f); b.big_bound[2 * k + 1] = mk4(hi.x + px, hi.y + py, hi.z + pz, 0.f);
+        // stored as (centre, half extent) for the three-FFMA slab test (slab_center_extent, nrcu_intersect.cuh); the half
+        // extent is rounded outwards so that [c - h, c + h] contains the padded box
+        const float l3[3] = {lo.x - px, lo.y - py, lo.z - pz}, h3[3] = {hi.x + px, hi.y + py, hi.z + pz};
+        float c3[3], e3[3];
+        for (int q = 0; q < 3; q++) { c3[q] = 0.5f * l3[q] + 0.5f * h3[q]; e3[q] = fmaxf(h3[q] - c3[q], c3[q] - l3[q]) * 1.000001f + 1e-30f; }
+        b.big_bound[2 * k] = mk4(c3[0], c3[1], c3[2], 0.f); b.big_bound[2 * k + 1] = mk4(e3[0], e3[1], e3[2], 0.f);
         b.big_meta[k] = ((uint32_t)id << 2) | (b.prim_meta[id] & 3u);
         b.prim_node[id] = NRCU_PRIM_EXCLUDED;
     }
@@ -364,11 +369,13 @@ NR_HD void bvh_wide_emit(const BvhBuild& b, int n) {
             for (int a = 0; a < 3; a++) {
                 float l = fkey_inv(b.nbox[c * 6 + a]), h = fkey_inv(b.nbox[c * 6 + 3 + a]);
                 float pad = b.inflate + 1e-6f * fmaxf(fabsf(l), fabsf(h));
-                lo[a][k] = l - pad; hi[a][k] = h + pad;
+                // stored as centre (lo[][]) and half extent rounded outwards (hi[][]): see NRCU_SLAB in node_step
+                const float pl = l - pad, ph = h + pad, c0 = 0.5f * pl + 0.5f * ph;
+                lo[a][k] = c0; hi[a][k] = fmaxf(ph - c0, c0 - pl) * 1.000001f + 1e-30f;
             }
             ref[k] = b.nstate[c] == BNODE_LEAF ? leaf_ref(b, c) : b.nwide[c];
         } else {
-            for (int a = 0; a < 3; a++) { lo[a][k] = NRCU_INF; hi[a][k] = NRCU_INF; }   // never entered (see closest_hit_bvh)
+            for (int a = 0; a < 3; a++) { lo[a][k] = NRCU_INF; hi[a][k] = 0.f; }   // centre at infinity: never entered (see closest_hit_bvh)
             ref[k] = NRCU_REF_EMPTY;
         }
     }

@@ -181,13 +181,13 @@ NR_HD int node_step(const DScene& s, const RayPrep& rp, int cur, float best_t, S
     const f4* n = s.nodes + (size_t)cur * NRCU_BVH_NODE_F4;
     f4 lox = ldg4(n), hix = ldg4(n + 1), loy = ldg4(n + 2), hiy = ldg4(n + 3), loz = ldg4(n + 4), hiz = ldg4(n + 5);
     i4 refs = ldg4i(n + 6);
+    // lo* = centres, hi* = half extents: per axis m = c/d - o/d, near = m - h/|d|, far = m + h/|d| (three FFMAs, no min/max)
+    const float aix = fabsf(rp.inv.x), aiy = fabsf(rp.inv.y), aiz = fabsf(rp.inv.z);
     float t0, t1, t2, t3;
 #define NRCU_SLAB(k, out) do { \
-    float ax = fmaf(lox.k, rp.inv.x, -rp.oinv.x), bx = fmaf(hix.k, rp.inv.x, -rp.oinv.x); \
-    float ay = fmaf(loy.k, rp.inv.y, -rp.oinv.y), by = fmaf(hiy.k, rp.inv.y, -rp.oinv.y); \
-    float az = fmaf(loz.k, rp.inv.z, -rp.oinv.z), bz = fmaf(hiz.k, rp.inv.z, -rp.oinv.z); \
-    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
-    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
+    float mx = fmaf(lox.k, rp.inv.x, -rp.oinv.x), my = fmaf(loy.k, rp.inv.y, -rp.oinv.y), mz = fmaf(loz.k, rp.inv.z, -rp.oinv.z); \
+    float tn = fmaxf(fmaxf(fmaf(-hix.k, aix, mx), fmaf(-hiy.k, aiy, my)), fmaxf(fmaf(-hiz.k, aiz, mz), 0.0f)); \
+    float tf = fminf(fminf(fmaf(hix.k, aix, mx), fmaf(hiy.k, aiy, my)), fminf(fmaf(hiz.k, aiz, mz), best_t)); \
     out = (tn <= tf) ? tn : NRCU_INF; } while (0)
     NRCU_SLAB(x, t0); NRCU_SLAB(y, t1); NRCU_SLAB(z, t2); NRCU_SLAB(w, t3);
 #undef NRCU_SLAB
@@ -264,17 +264,22 @@ NR_HD int ctz32(uint32_t x) {
 // tested; if it passes, it is also the closest of the gate-passing primitives (same t order, same lowest-id tie
 // rule).  Only when the winner fails its gate (zero-thickness box or a grazing hit) are the candidates walked
 // again with the gate applied per candidate.
+// Conservative slab test against a box stored as (centre c, half extent h): per axis m = c/d - o/d, near = m - h/|d|,
+// far = m + h/|d| - three FFMAs and no per-axis min/max (13 instead of 16 instructions per box).  `nox` is -o.x/d.x, or
+// -inf to make the test fail for a lane that holds no ray.  tn <= tf means "may be hit at t >= 0".
+NR_HD void slab_center_extent(f4 c, f4 h, const RayPrep& rp, vec3 ainv, float nox, float& tn, float& tf) {
+    const float mx = fmaf(c.x, rp.inv.x, nox), my = fmaf(c.y, rp.inv.y, -rp.oinv.y), mz = fmaf(c.z, rp.inv.z, -rp.oinv.z);
+    tn = fmaxf(fmaxf(fmaf(-h.x, ainv.x, mx), fmaf(-h.y, ainv.y, my)), fmaxf(fmaf(-h.z, ainv.z, mz), 0.0f));
+    tf = fminf(fminf(fmaf(h.x, ainv.x, mx), fmaf(h.y, ainv.y, my)), fmaf(h.z, ainv.z, mz));
+}
 template <bool GATE>
 NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const f4* bound, const uint32_t* meta,
                          const Ray& ray, const RayPrep& rp, vec3 ginv, float& best_t, int& best_id) {
     uint32_t mask = 0;
+    const vec3 ainv = mk3(fabsf(rp.inv.x), fabsf(rp.inv.y), fabsf(rp.inv.z));
     for (uint32_t k = 0; k < s.n_big; k++) {
-        f4 lo = bound[2 * k], hi = bound[2 * k + 1];
-        float ax = fmaf(lo.x, rp.inv.x, -rp.oinv.x), bx = fmaf(hi.x, rp.inv.x, -rp.oinv.x);
-        float ay = fmaf(lo.y, rp.inv.y, -rp.oinv.y), by = fmaf(hi.y, rp.inv.y, -rp.oinv.y);
-        float az = fmaf(lo.z, rp.inv.z, -rp.oinv.z), bz = fmaf(hi.z, rp.inv.z, -rp.oinv.z);
-        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        float tn, tf;
+        slab_center_extent(bound[2 * k], bound[2 * k + 1], rp, ainv, -rp.oinv.x, tn, tf);
         if (tn <= tf) mask |= 1u << k;
     }
     uint32_t kb = 0;

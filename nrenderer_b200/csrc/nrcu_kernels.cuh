@@ -190,16 +190,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
     __shared__ unsigned short pairs[NRCU_BIGB_WARPS][32 * NRCU_MAX_BIG];
     __shared__ float rays[NRCU_BIGB_WARPS][6][32];
     __shared__ unsigned long long best[NRCU_BIGB_WARPS][32];
-    __shared__ f4 ce[NRCU_MAX_BIG * 2];
     bl.load(s);
-    for (uint32_t k = threadIdx.x; k < s.n_big; k += blockDim.x) {   // (centre, half extent) of the padded bounds, h rounded up
-        const f4 lo = bl.bd[2 * k], hi = bl.bd[2 * k + 1];
-        const float cx = 0.5f * lo.x + 0.5f * hi.x, cy = 0.5f * lo.y + 0.5f * hi.y, cz = 0.5f * lo.z + 0.5f * hi.z;
-        ce[2 * k] = mk4(cx, cy, cz, 0.f);
-        ce[2 * k + 1] = mk4(fmaxf(hi.x - cx, cx - lo.x) * 1.000001f + 1e-30f, fmaxf(hi.y - cy, cy - lo.y) * 1.000001f + 1e-30f,
-                            fmaxf(hi.z - cz, cz - lo.z) * 1.000001f + 1e-30f, 0.f);
-    }
-    __syncthreads();
     const uint32_t n = *n_ptr;
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, lt = (1u << lane) - 1u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -216,20 +207,14 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
         best[wib][lane] = ~0ull;
         // pass 1: slab test of every wide primitive (warp-uniform loop, broadcast reads) -> candidate pairs, primitive-major
         uint32_t total = 0;
-        // Slab test in centre / half-extent form: per axis m = c/d - o/d, near = m - h/|d|, far = m + h/|d| - three
-        // FFMAs and no per-axis min/max (13 instead of 16 instructions per primitive).  ce[] holds (c, h) of the padded
-        // bounds with h rounded outwards; the test stays a conservative pre-filter (the padding, 1e-6 relative plus an
-        // absolute term, exceeds the few ulps either form can be off by).
         // Lanes past the end of the queue: an x offset of -inf puts near and far at -inf, so tf = -inf < 0 <= tn and the
         // lane never becomes a candidate (prep_ray clamps 1/d to +-1e18, the products stay finite: no NaN) - one
         // predicate less per primitive than testing i < n inside the loop.
         const float nox = i < n ? -rp.oinv.x : -NRCU_INF;
-        const float aix = fabsf(rp.inv.x), aiy = fabsf(rp.inv.y), aiz = fabsf(rp.inv.z);
+        const vec3 ainv = mk3(fabsf(rp.inv.x), fabsf(rp.inv.y), fabsf(rp.inv.z));
         for (uint32_t k = 0; k < s.n_big; k++) {
-            const f4 c = ce[2 * k], h = ce[2 * k + 1];
-            const float mx = fmaf(c.x, rp.inv.x, nox), my = fmaf(c.y, rp.inv.y, -rp.oinv.y), mz = fmaf(c.z, rp.inv.z, -rp.oinv.z);
-            const float tn = fmaxf(fmaxf(fmaf(-h.x, aix, mx), fmaf(-h.y, aiy, my)), fmaxf(fmaf(-h.z, aiz, mz), 0.0f));
-            const float tf = fminf(fminf(fmaf(h.x, aix, mx), fmaf(h.y, aiy, my)), fmaf(h.z, aiz, mz));
+            float tn, tf;
+            slab_center_extent(bl.bd[2 * k], bl.bd[2 * k + 1], rp, ainv, nox, tn, tf);
             const bool cand = tn <= tf;
             const uint32_t m = __ballot_sync(0xffffffffu, cand);
             if (cand) my_pairs[total + __popc(m & lt)] = (unsigned short)(lane | (k << 5));
@@ -312,13 +297,13 @@ __device__ __forceinline__ int node_step3(const DScene& s, const RayPrep& rp, in
     const f4* nd = s.nodes + (size_t)cur * NRCU_BVH_NODE_F4;
     f4 lox = ldg4(nd), hix = ldg4(nd + 1), loy = ldg4(nd + 2), hiy = ldg4(nd + 3), loz = ldg4(nd + 4), hiz = ldg4(nd + 5);
     i4 refs = ldg4i(nd + 6);
+    // lo* = centres, hi* = half extents: per axis m = c/d - o/d, near = m - h/|d|, far = m + h/|d| (three FFMAs, no min/max)
+    const float aix = fabsf(rp.inv.x), aiy = fabsf(rp.inv.y), aiz = fabsf(rp.inv.z);
     float t0, t1, t2, t3;
 #define NRCU_SLAB(k, out) do { \
-    float ax = fmaf(lox.k, rp.inv.x, -rp.oinv.x), bx = fmaf(hix.k, rp.inv.x, -rp.oinv.x); \
-    float ay = fmaf(loy.k, rp.inv.y, -rp.oinv.y), by = fmaf(hiy.k, rp.inv.y, -rp.oinv.y); \
-    float az = fmaf(loz.k, rp.inv.z, -rp.oinv.z), bz = fmaf(hiz.k, rp.inv.z, -rp.oinv.z); \
-    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
-    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
+    float mx = fmaf(lox.k, rp.inv.x, -rp.oinv.x), my = fmaf(loy.k, rp.inv.y, -rp.oinv.y), mz = fmaf(loz.k, rp.inv.z, -rp.oinv.z); \
+    float tn = fmaxf(fmaxf(fmaf(-hix.k, aix, mx), fmaf(-hiy.k, aiy, my)), fmaxf(fmaf(-hiz.k, aiz, mz), 0.0f)); \
+    float tf = fminf(fminf(fmaf(hix.k, aix, mx), fmaf(hiy.k, aiy, my)), fminf(fmaf(hiz.k, aiz, mz), best_t)); \
     out = (tn <= tf) ? tn : NRCU_INF; } while (0)
     NRCU_SLAB(x, t0); NRCU_SLAB(y, t1); NRCU_SLAB(z, t2); NRCU_SLAB(w, t3);
 #undef NRCU_SLAB

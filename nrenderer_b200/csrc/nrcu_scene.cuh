@@ -73,7 +73,7 @@ struct DCamera {   // Camera ctor results, ray_cast/include/Camera.hpp:25-46
     float lens_radius;
 };
 
-#define NRCU_BVH_NODE_F4 7   // float4s per BVH4 node: lox hix loy hiy loz hiz (4 children each) + 4 child refs
+#define NRCU_BVH_NODE_F4 7   // float4s per BVH4 node: cx hx cy hy cz hz (centre / half extent of the padded boxes, 4 children each) + 4 child refs
 #ifndef NRCU_LEAF_MAX
 #define NRCU_LEAF_MAX 4
 #endif
@@ -106,7 +106,7 @@ struct DScene {
     // tested by every ray in a warp-uniform loop (k_big) before the traversal starts; see nrcu_bvh.cuh
     const f4* big_geom;           // 3 per wide primitive
     const f4* big_box;            // 2 per wide primitive (leaf gate)
-    const f4* big_bound;          // 2 per wide primitive: padded true bounds (conservative pre-test)
+    const f4* big_bound;          // 2 per wide primitive: padded true bounds as (centre, half extent) (conservative pre-test)
     const uint32_t* big_meta;     // (prim id << 2) | kind; planes first, then triangles, then spheres
     uint32_t n_big;
     vec3 bvh_lo, bvh_hi;          // padded bounds of everything inside the BVH (lo > hi when it is empty)
