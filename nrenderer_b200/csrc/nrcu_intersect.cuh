@@ -256,14 +256,6 @@ NR_HD int ctz32(uint32_t x) {
     return __builtin_ctz(x);
 #endif
 }
-// The wide primitives (DScene::big_*), tested by every ray before the traversal (best_t = inf, best_id = -1 on entry).
-//   pass 1  every lane walks the same list: conservative slab test of each primitive's padded bounds -> candidate
-//           bit mask (warp-uniform loop, shared-memory broadcasts, no divergence);
-//   pass 2  each lane runs the exact reference test on its own candidates only (typically 2-3 of them).
-// The leaf gate is applied optimistically: the ungated closest hit is found first and only the winner's box is
-// tested; if it passes, it is also the closest of the gate-passing primitives (same t order, same lowest-id tie
-// rule).  Only when the winner fails its gate (zero-thickness box or a grazing hit) are the candidates walked
-// again with the gate applied per candidate.
 // Conservative slab test against a box stored as (centre c, half extent h): per axis m = c/d - o/d, near = m - h/|d|,
 // far = m + h/|d| - three FFMAs and no per-axis min/max (13 instead of 16 instructions per box).  `nox` is -o.x/d.x, or
 // -inf to make the test fail for a lane that holds no ray.  tn <= tf means "may be hit at t >= 0".
@@ -272,6 +264,14 @@ NR_HD void slab_center_extent(f4 c, f4 h, const RayPrep& rp, vec3 ainv, float no
     tn = fmaxf(fmaxf(fmaf(-h.x, ainv.x, mx), fmaf(-h.y, ainv.y, my)), fmaxf(fmaf(-h.z, ainv.z, mz), 0.0f));
     tf = fminf(fminf(fmaf(h.x, ainv.x, mx), fmaf(h.y, ainv.y, my)), fmaf(h.z, ainv.z, mz));
 }
+// The wide primitives (DScene::big_*), tested by every ray before the traversal (best_t = inf, best_id = -1 on entry).
+//   pass 1  every lane walks the same list: conservative slab test of each primitive's padded bounds -> candidate
+//           bit mask (warp-uniform loop, shared-memory broadcasts, no divergence);
+//   pass 2  each lane runs the exact reference test on its own candidates only (typically 2-3 of them).
+// The leaf gate is applied optimistically: the ungated closest hit is found first and only the winner's box is
+// tested; if it passes, it is also the closest of the gate-passing primitives (same t order, same lowest-id tie
+// rule).  Only when the winner fails its gate (zero-thickness box or a grazing hit) are the candidates walked
+// again with the gate applied per candidate.
 template <bool GATE>
 NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const f4* bound, const uint32_t* meta,
                          const Ray& ray, const RayPrep& rp, vec3 ginv, float& best_t, int& best_id) {
