@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
 // unsigned order is (t, id) order, the tie rule of the per-ray loop.  The optimistic leaf gate and its
 // per-candidate fallback stay with the owning lane.
 #define NRCU_BIGB_WARPS 8
+#define NRCU_BEST_NONE 0x7f800000ffffffffull
 template <bool GATE>
 __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
                                                                        uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
         const RayPrep rp = prep_ray(r);
         rays[wib][0][lane] = r.o.x; rays[wib][1][lane] = r.o.y; rays[wib][2][lane] = r.o.z;
         rays[wib][3][lane] = r.d.x; rays[wib][4][lane] = r.d.y; rays[wib][5][lane] = r.d.z;
-        best[wib][lane] = ~0ull;
+        best[wib][lane] = NRCU_BEST_NONE;   // t = +inf, id = all ones: reads back as "nothing yet" without a special case
         // pass 1: slab test of every wide primitive (warp-uniform loop, broadcast reads) -> candidate pairs, primitive-major
         uint32_t total = 0;
         // Lanes past the end of the queue: an x offset of -inf puts near and far at -inf, so tf = -inf < 0 <= tn and the
@@ -228,8 +229,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
             if (j < total) {
                 const uint32_t p = my_pairs[j], ol = p & 31u, k = p >> 5;
                 Ray pr; pr.o = mk3(rays[wib][0][ol], rays[wib][1][ol], rays[wib][2][ol]); pr.d = mk3(rays[wib][3][ol], rays[wib][4][ol], rays[wib][5][ol]);
-                const uint32_t hi32 = (uint32_t)(best[wib][ol] >> 32);
-                float bt = hi32 == 0xffffffffu ? NRCU_INF : __uint_as_float(hi32);   // the owner's best so far: only culls
+                float bt = __uint_as_float((uint32_t)(best[wib][ol] >> 32));   // the owner's best so far (+inf: none): only culls
                 int bi = 0x7fffffff;                                                  // accept ties: atomicMin settles them by id
                 prim_test<false>(pr, mk3(0.f), bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b, bl.m[k], bt, bi);
                 if (bi != 0x7fffffff) atomicMin(&best[wib][ol], ((unsigned long long)__float_as_uint(bt) << 32) | (unsigned long long)(((uint32_t)bi << 5) | k));
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
         if (i < n) {
             const unsigned long long key = best[wib][lane];
             float best_t = NRCU_INF; int best_id = -1;
-            if (key != ~0ull) {
+            if (key != NRCU_BEST_NONE) {
                 best_t = __uint_as_float((uint32_t)(key >> 32)); best_id = (int)((uint32_t)key >> 5);
                 if (GATE) {
                     const uint32_t kb = (uint32_t)key & 31u;
