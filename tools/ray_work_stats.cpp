@@ -46,4 +46,34 @@ uint32_t emu_ray_work(EmuScene* es, uint64_t seed, const uint32_t* pixels, uint3
     }
     return k;
 }
+
+// Stage-1 statistics for the same ray population: out[k*2..] = (bounce, candidate bit mask of the wide list after the
+// conservative slab test) in wavefront queue order.  Returns the ray count.
+uint32_t emu_stage1_masks(EmuScene* es, uint64_t seed, const uint32_t* pixels, uint32_t n_pixels, uint32_t sample, uint32_t* out, uint32_t cap) {
+    const DScene& ds = es->ds;
+    struct P { Ray r; vec3 thr; uint32_t pixel; };
+    std::vector<P> cur, nxt;
+    for (uint32_t q = 0; q < n_pixels; q++) cur.push_back({pt_camera_ray(ds, seed, pixels[q], sample), mk3(1.f), pixels[q]});
+    uint32_t k = 0;
+    for (uint32_t d = 0; d < ds.depth && !cur.empty(); d++) {
+        nxt.clear();
+        for (auto& p : cur) {
+            RayPrep rp = prep_ray(p.r);
+            const vec3 ainv = mk3(fabsf(rp.inv.x), fabsf(rp.inv.y), fabsf(rp.inv.z));
+            uint32_t mask = 0;
+            for (uint32_t b = 0; b < ds.n_big; b++) {
+                float tn, tf;
+                slab_center_extent(ds.big_bound[2 * b], ds.big_bound[2 * b + 1], rp, ainv, -rp.oinv.x, tn, tf);
+                if (tn <= tf) mask |= 1u << b;
+            }
+            if (k < cap) { out[2 * k] = d; out[2 * k + 1] = mask; k++; }
+            float t; int id, nn, nl, np;
+            if (ds.mode == MODE_ACC) traverse_count<true>(ds, p.r, t, id, nn, nl, np); else traverse_count<false>(ds, p.r, t, id, nn, nl, np);
+            PathStep ps = path_vertex(ds, seed, p.pixel, sample, d, 0, p.r, p.thr, t, id, 0, false);
+            if (ps.action == PATH_CONTINUE) nxt.push_back({ps.next, ps.thr, p.pixel});
+        }
+        cur.swap(nxt);
+    }
+    return k;
+}
 }

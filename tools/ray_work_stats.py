@@ -43,6 +43,25 @@ def main():
     allc = CN * out[:, 1] + CP * out[:, 3]
     print(f"all: nodes {out[:,1].mean():.2f} leaves {out[:,2].mean():.2f} prims {out[:,3].mean():.2f} ideal lane-instr/ray {allc.mean():.0f} = {allc.mean()/32:.1f} warp-instr/ray at 100% SIMD")
     print(f"rays entering the BVH: {(out[:,1]>0).mean()*100:.1f}%"); frac_heavy = (out[:, 1] > 8).mean(); print(f"rays with > 8 node steps: {frac_heavy*100:.1f}% carrying {allc[out[:,1]>8].sum()/allc.sum()*100:.1f}% of the work")
+    # stage 1: candidates of the wide list per ray, and how well the balanced pass 2 of k_big_balanced fills its rounds
+    L.emu_stage1_masks.restype = C.c_uint32
+    L.emu_stage1_masks.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    sm = np.zeros((cap, 2), np.uint32)
+    n1 = L.emu_stage1_masks(h, 0, pix.ctypes.data, len(pix), 0, sm.ctypes.data, cap)
+    sm = sm[:n1]
+    nb = int(st[6])
+    bits = ((sm[:, 1][:, None] >> np.arange(nb)[None, :]) & 1).astype(np.int32)
+    cand = bits.sum(1)
+    print(f"stage 1: {nb} wide primitives; candidates per ray mean {cand.mean():.2f} p50 {np.median(cand):.0f} p90 {np.percentile(cand, 90):.0f} max {cand.max()}")
+    print("         candidate rate per wide primitive:", " ".join(f"{x:.2f}" for x in bits.mean(0)))
+    for d in (0, 1, 2, 5):
+        m = cand[sm[:, 0] == d]
+        k = len(m) // 32 * 32
+        if not k: continue
+        pairs = m[:k].reshape(-1, 32).sum(1)
+        rounds = np.ceil(pairs / 32)
+        print(f"         bounce {d}: pairs per warp {pairs.mean():6.1f}, rounds {rounds.mean():.2f}, lanes filled {pairs.sum() / (32 * rounds.sum()) * 100:.1f} % "
+              f"(per-lane loop instead: {m[:k].reshape(-1, 32).max(1).mean():.2f} rounds at {m[:k].mean() / m[:k].reshape(-1, 32).max(1).mean() * 100:.0f} %)")
 
 if __name__ == "__main__":
     main()
