@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define NRCU_ABI_VERSION 1
+#define NRCU_ABI_VERSION 2
 
 typedef struct nrcu_ctx nrcu_ctx;
 
@@ -49,7 +49,10 @@ enum nrcu_status {
     NRCU_ERR_CUDA = 2,        /* a CUDA runtime call or kernel failed */
     NRCU_ERR_INVALID = 3,     /* bad argument / malformed scene */
     NRCU_ERR_STATE = 4,       /* call order violated (e.g. render before upload) */
-    NRCU_ERR_NCCL = 5         /* multi-device reduce failed */
+    NRCU_ERR_PEER = 5,        /* multi-device reduce failed: a peer's partial frame could be neither mapped nor copied */
+    NRCU_ERR_OVERFLOW = 6     /* a fixed-capacity device structure overflowed - a traversal stack (a hit may have been missed)
+                                 or the ray queue of the branching glass mode even at one sample per wave - so the frame
+                                 would be wrong: it is reported, never returned as NRCU_OK */
 };
 
 /* Which reference component the context reproduces. */
@@ -189,13 +192,26 @@ enum nrcu_render_flags {
                                   lower variance.  Ignored in RayCast mode. */
 };
 
+/* How the (pixel, sample) paths are scheduled onto the GPU.  Both schedulers trace exactly the same paths (the RNG is
+ * keyed by pixel, sample and bounce); only the fp32 order in which a pixel's samples are summed differs. */
+enum nrcu_scheduler {
+    NRCU_SCHED_AUTO  = 0,      /* NRCU_SCHED environment variable ("waves" / "regen"), else the library default */
+    NRCU_SCHED_WAVES = 1,      /* per-bounce wavefront: k samples of every pixel per wave, queues compacted after every bounce,
+                                  samples summed in sample order (the image does not depend on the wave size) */
+    NRCU_SCHED_REGEN = 2       /* path regeneration: K slots per pixel, a slot whose path ends starts its next sample in place;
+                                  no compaction, no per-bounce launches.  Samples are summed per slot, then over the K slots.
+                                  Falls back to WAVES for NEE, the branching glass mode and depth 0 */
+};
+
 typedef struct nrcu_render_params {
     uint64_t seed;             /* counter-based RNG key; same seed => same image */
     uint32_t sample_begin;     /* global sample indices [sample_begin, sample_end) of samples_per_pixel */
     uint32_t sample_end;       /* 0,0 = all samples */
     uint32_t glass_mode;       /* nrcu_glass_mode */
-    uint32_t samples_per_wave; /* 0 = choose automatically */
+    uint32_t samples_per_wave; /* WAVES: samples per wave, 0 = choose automatically; a non-zero value selects WAVES under AUTO.
+                                  REGEN (explicitly selected): slots per pixel K, 0 = automatic */
     uint32_t flags;            /* nrcu_render_flags; 0 = the reference's estimator */
+    uint32_t scheduler;        /* nrcu_scheduler */
 } nrcu_render_params;
 
 typedef struct nrcu_stats {
@@ -208,8 +224,12 @@ typedef struct nrcu_stats {
     float ms_setup;            /* scene preparation + BVH build at upload time */
     uint32_t bvh_nodes;        /* wide nodes */
     uint32_t n_primitives;     /* primitives after mesh flattening */
-    uint32_t max_queue;        /* high-water mark of the ray queue */
+    uint32_t max_queue;        /* high-water mark of the ray queue (branching glass mode: the unclamped demand) */
     float ms_stage2;           /* the part of ms_trace spent in the BVH traversal kernels (k_trace*) */
+    uint32_t scheduler;        /* nrcu_scheduler that ran (WAVES or REGEN) */
+    uint32_t iterations;       /* REGEN: stage-1/stage-2/shade rounds; WAVES: waves x bounces */
+    uint32_t wave_retries;     /* branching glass mode: waves re-rendered with fewer samples because the queue overflowed */
+    uint32_t reserved;
 } nrcu_stats;
 
 /* --- lifetime ------------------------------------------------------------------------- */

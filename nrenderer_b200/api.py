@@ -14,6 +14,8 @@ import numpy as np
 from .flatscene import FlatScene, MODE_ACC, MODE_RAYCAST, MODE_SIMPLE  # noqa: F401
 
 FLAG_NEE = 1   # nrcu_render_flags.NRCU_FLAG_NEE
+SCHED_AUTO, SCHED_WAVES, SCHED_REGEN = 0, 1, 2   # nrcu_scheduler
+ERR_OVERFLOW = 6
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libnrcuda.so")
@@ -31,13 +33,14 @@ class NrcuError(RuntimeError):
 
 class NrcuRenderParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
-                ("glass_mode", C.c_uint32), ("samples_per_wave", C.c_uint32), ("flags", C.c_uint32)]
+                ("glass_mode", C.c_uint32), ("samples_per_wave", C.c_uint32), ("flags", C.c_uint32), ("scheduler", C.c_uint32)]
 
 
 class NrcuStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_setup", C.c_float),
-                ("bvh_nodes", C.c_uint32), ("n_primitives", C.c_uint32), ("max_queue", C.c_uint32), ("ms_stage2", C.c_float)]
+                ("bvh_nodes", C.c_uint32), ("n_primitives", C.c_uint32), ("max_queue", C.c_uint32), ("ms_stage2", C.c_float),
+                ("scheduler", C.c_uint32), ("iterations", C.c_uint32), ("wave_retries", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -115,7 +118,9 @@ class Context:
 
     def _check(self, rc, what):
         if rc != 0:
-            raise NrcuError(f"{what} failed ({rc}): {self._lib.nrcu_last_error(self._h).decode()}")
+            err = NrcuError(f"{what} failed ({rc}): {self._lib.nrcu_last_error(self._h).decode()}")
+            err.status = rc
+            raise err
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._lib.nrcu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "nrcu_set_stream")
@@ -144,16 +149,16 @@ class Context:
         return kind, data, mat
 
     @staticmethod
-    def _params(seed, s0, s1, glass_mode, samples_per_wave, flags=0):
+    def _params(seed, s0, s1, glass_mode, samples_per_wave, flags=0, scheduler=0):
         return NrcuRenderParams(seed=seed, sample_begin=s0, sample_end=s1, glass_mode=glass_mode,
-                                samples_per_wave=samples_per_wave, flags=flags)
+                                samples_per_wave=samples_per_wave, flags=flags, scheduler=scheduler)
 
-    def render(self, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None, flags=0):
+    def render(self, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None, flags=0, scheduler=0):
         """Whole frame into HOST memory (what Screen::set takes). Returns (rgba[h,w,4], stats dict)."""
         if out is None:
             out = np.empty((self.height, self.width, 4), np.float32)
         assert out.dtype == np.float32 and out.size == self.width * self.height * 4 and out.flags.c_contiguous
-        p, st = self._params(seed, 0, 0, glass_mode, samples_per_wave, flags), NrcuStats()
+        p, st = self._params(seed, 0, 0, glass_mode, samples_per_wave, flags, scheduler), NrcuStats()
         self._check(self._lib.nrcu_render(self._h, C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render")
         return out, st.as_dict()
 
@@ -167,9 +172,9 @@ class Context:
                     "nrcu_render_progressive")
         return out, st.as_dict()
 
-    def render_accumulate(self, d_accum_ptr: int, s0=0, s1=0, seed=0, glass_mode=0, samples_per_wave=0, want_stats=True, flags=0):
+    def render_accumulate(self, d_accum_ptr: int, s0=0, s1=0, seed=0, glass_mode=0, samples_per_wave=0, want_stats=True, flags=0, scheduler=0):
         """Add linear sums of samples [s0,s1) into the DEVICE buffer at d_accum_ptr (w*h*4 floats)."""
-        p, st = self._params(seed, s0, s1, glass_mode, samples_per_wave, flags), NrcuStats()
+        p, st = self._params(seed, s0, s1, glass_mode, samples_per_wave, flags, scheduler), NrcuStats()
         self._check(self._lib.nrcu_render_accumulate(self._h, C.addressof(p), C.c_void_p(d_accum_ptr),
                                                      C.addressof(st) if want_stats else None), "nrcu_render_accumulate")
         return st.as_dict() if want_stats else None
@@ -185,12 +190,12 @@ class Context:
         return pid, t
 
 
-def render_multi(contexts, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None):
+def render_multi(contexts, seed=0, glass_mode=0, samples_per_wave=0, out: np.ndarray | None = None, scheduler=0):
     """One frame on several devices of the box (nrcu_render_multi): contexts[g] must hold the same scene."""
     c0 = contexts[0]
     if out is None:
         out = np.empty((c0.height, c0.width, 4), np.float32)
     arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
-    p, st = Context._params(seed, 0, 0, glass_mode, samples_per_wave), NrcuStats()
+    p, st = Context._params(seed, 0, 0, glass_mode, samples_per_wave, 0, scheduler), NrcuStats()
     c0._check(c0._lib.nrcu_render_multi(arr, len(contexts), C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render_multi")
     return out, st.as_dict()

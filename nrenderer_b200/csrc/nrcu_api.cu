@@ -70,6 +70,9 @@ struct Sub { void* p = nullptr; template <typename T> T* as() const { return rei
 }  // namespace
 
 #define NRCU_MAX_WAVES 4
+#ifndef NRCU_SCHED_DEFAULT
+#define NRCU_SCHED_DEFAULT NRCU_SCHED_REGEN
+#endif
 struct nrcu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -91,6 +94,9 @@ struct nrcu_ctx {
     cudaStream_t extra_stream[NRCU_MAX_WAVES] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused: wave 0 runs on `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_acc = nullptr;
     DevBuf accum_own, rgba_dev, build_scratch;
+    DevBuf overflow;                       // DScene::overflow: [0] dropped traversal-stack pushes, [1] rays that did not fit the branching queue
+    uint32_t* h_flags = nullptr;           // pinned: alive flags of the regeneration scheduler's batches, [wave][ring slot][NRCU_REGEN_FLAGS * stride]
+    cudaEvent_t ev_batch[NRCU_MAX_WAVES][4] = {};
     // stats
     float ms_setup = 0.f;
     uint32_t bvh_nodes = 0, n_big = 0;
@@ -159,6 +165,9 @@ int nrcu_create(int device, nrcu_ctx** out) {
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return NRCU_ERR_CUDA; }
     ctx->own_stream = true;
     cudaEventCreate(&ctx->ev_begin); cudaEventCreate(&ctx->ev_end);
+    if (ctx->overflow.ensure(2 * sizeof(uint32_t)) != cudaSuccess || cudaMemset(ctx->overflow.p, 0, 2 * sizeof(uint32_t)) != cudaSuccess) {
+        g_create_error = "nrcu_create: device allocation failed"; cudaGetLastError(); nrcu_destroy(ctx); return NRCU_ERR_CUDA;
+    }
     *out = ctx;
     return NRCU_OK;
 }
@@ -174,6 +183,8 @@ int nrcu_destroy(nrcu_ctx* ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_acc) cudaEventDestroy(ctx->ev_acc);
     for (auto& xs : ctx->extra_stream) if (xs) { cudaStreamSynchronize(xs); cudaStreamDestroy(xs); }
+    for (auto& row : ctx->ev_batch) for (auto& e : row) if (e) cudaEventDestroy(e);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return NRCU_OK;
@@ -188,11 +199,25 @@ int nrcu_set_stream(nrcu_ctx* ctx, void* cuda_stream) {
     return NRCU_OK;
 }
 
+// Reads DScene::overflow after the stream has been synchronised; non-zero => the results of the calls since the last
+// check cannot be trusted.  The counters are cleared so that the context stays usable.
+static int check_overflow(nrcu_ctx* ctx) {
+    uint32_t h[2] = {0, 0};
+    CTX_CUDA(cudaMemcpy(h, ctx->overflow.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[0] == 0 && h[1] == 0) return NRCU_OK;
+    CTX_CUDA(cudaMemset(ctx->overflow.p, 0, sizeof(h)));
+    char buf[256];
+    if (h[0]) std::snprintf(buf, sizeof(buf), "BVH traversal stack overflow: %u entries did not fit %d-entry stacks; hits may have been missed", h[0], ctx->ds.stack_limit);
+    else std::snprintf(buf, sizeof(buf), "ray queue overflow in the branching glass mode: %u rays did not fit even at one sample per wave", h[1]);
+    ctx->error = buf;
+    return NRCU_ERR_OVERFLOW;
+}
+
 int nrcu_synchronize(nrcu_ctx* ctx) {
     if (!ctx) return NRCU_ERR_INVALID;
     CTX_CUDA(cudaSetDevice(ctx->device));
     CTX_CUDA(cudaStreamSynchronize(ctx->stream));
-    return NRCU_OK;
+    return check_overflow(ctx);   // asynchronous nrcu_render_accumulate calls report here
 }
 
 void nrcu_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
@@ -237,6 +262,11 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
 #undef UP
     DScene& ds = ctx->ds;
     fill_scene_scalars(ds, sc, mode, hp);
+    ds.overflow = ctx->overflow.as<uint32_t>();
+    {   // NRCU_DEBUG_STACK_LIMIT: only for the test of the overflow report (tests/test_gpu_parity.py)
+        int lim = (int)env_u32("NRCU_DEBUG_STACK_LIMIT", NRCU_LOCAL_STACK);
+        ds.stack_limit = std::min(std::max(lim, NRCU_T3_STACK), NRCU_LOCAL_STACK);
+    }
     if (sc->ambient_type == NRCU_AMBIENT_ENVIRONMENT_MAP && sc->ambient_environment_map >= 0 &&
         (uint32_t)sc->ambient_environment_map < sc->n_textures) {
         uint32_t ti = (uint32_t)sc->ambient_environment_map;
@@ -361,6 +391,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     bvh_padded_bounds(root_box, b.inflate, ds.bvh_lo, ds.bvh_hi);
 
     int begin = 0, end = 1;
+    bool converged = false;
     for (int level = 0; level < 128; level++) {
         b.level_begin = begin; b.level_end = end;
         CTX_CUDA(cudaMemsetAsync(counters.as<int>() + 3, 0, 2 * sizeof(int), st));
@@ -369,11 +400,15 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
         k_bvh_split<<<grid_for(end - begin, T), T, 0, st>>>(b, begin, end - begin); CTX_LAUNCH_CHECK("k_bvh_split");
         CTX_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
         CTX_CUDA(cudaStreamSynchronize(st));
-        if (h_counters[3] == 0) break;
+        if (h_counters[3] == 0) { converged = true; break; }
         k_bvh_partition<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_partition");
         begin = end; end = h_counters[0];
     }
     pt.mark("  bvh: level loop");
+    if (!converged) {   // unreachable with the depth cap of bvh_split (<= 24 + 32 levels); never emit a tree with OPEN nodes
+        ctx->error = "BVH build did not converge within 128 levels";
+        return NRCU_ERR_INVALID;
+    }
     const int n_nodes = h_counters[0];
     k_bvh_leaf_alloc<<<grid_for(n_nodes, T), T, 0, st>>>(b, 0, n_nodes); CTX_LAUNCH_CHECK("k_bvh_leaf_alloc");
     k_bvh_leaf_fill<<<grid_for(n, T), T, 0, st>>>(b, 0, (int)n); CTX_LAUNCH_CHECK("k_bvh_leaf_fill");
@@ -531,7 +566,7 @@ static cudaEvent_t pool_event(nrcu_ctx* ctx, size_t i) {
     return ctx->ev_pool[i];
 }
 
-static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats) {
+static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats) {
     const bool nee = params && (params->flags & NRCU_FLAG_NEE) && ctx->ds.n_area_lights > 0;
     ctx->ds.nee = nee ? 1 : 0;
     const DScene& ds = ctx->ds;
@@ -623,7 +658,8 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         pp.hb = w.hits.as<float2>(); pp.surv = w.surv.as<uint32_t>(); pp.L = w.L.as<f4>();
     }
 
-    for (uint32_t g0 = s0; g0 < s1; g0 += k * (uint32_t)NP) {
+    uint32_t wave_retries = 0, bounce_rounds = 0;
+    for (uint32_t g0 = s0; g0 < s1;) {
         // ---- camera rays (+ stage 1 of their closest hit) of the waves of this group ------------------------------
         for (int p = 0; p < NP; p++) {
             Pipe& pp = P[p];
@@ -649,8 +685,8 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                 if (d > 0) {
                     if (big_balanced()) {
-                        if (gate) k_big_balanced<true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
-                        else k_big_balanced<false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
+                        if (gate) k_big_balanced<true, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays, 0u);
+                        else k_big_balanced<false, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays, 0u);
                     }
                     else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
                     else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
@@ -670,9 +706,9 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
                 CTX_LAUNCH_CHECK("k_shade");
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 4; }
                 if (glass_branch) {   // only the branching mode can outgrow the queue
-                    k_clamp_count<<<1, 1, 0, st>>>(pp.d_qn + CS * (d + 1), capacity, cnt0 + CNT_HIGH_WATER);
+                    k_clamp_count<<<1, 1, 0, st>>>(pp.d_qn + CS * (d + 1), capacity, cnt0 + CNT_HIGH_WATER, ds.overflow + 1);
                     CTX_LAUNCH_CHECK("k_clamp_count");
-                    if (nee) { k_clamp_count<<<1, 1, 0, st>>>(pp.d_nshadow + CS * d, capacity, cnt0 + CNT_HIGH_WATER); CTX_LAUNCH_CHECK("k_clamp_count"); }
+                    if (nee) { k_clamp_count<<<1, 1, 0, st>>>(pp.d_nshadow + CS * d, capacity, cnt0 + CNT_HIGH_WATER, ds.overflow + 1); CTX_LAUNCH_CHECK("k_clamp_count"); }
                 }
                 if (nee && d + 1 < ds.depth) {   // the shadow rays of this bounce: same closest-hit kernels, then visibility + add
                     if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
@@ -688,15 +724,34 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
                 }
             }
         }
+        bounce_rounds += ds.depth;
+        if (glass_branch) {
+            // Only the branching mode can outgrow its queue (2^bounces rays per path inside glass).  A wave that dropped
+            // rays is NOT accumulated: it is rendered again with half the samples (the queue capacity stays, so the room
+            // per sample doubles); at one sample per wave the call fails with NRCU_ERR_OVERFLOW.
+            uint32_t h_over = 0;
+            CTX_CUDA(cudaMemcpyAsync(&h_over, ds.overflow + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, P[0].st));
+            CTX_CUDA(cudaStreamSynchronize(P[0].st));
+            if (h_over) {
+                if (k > 1) {
+                    CTX_CUDA(cudaMemsetAsync(ds.overflow + 1, 0, sizeof(uint32_t), P[0].st));
+                    k = std::max<uint32_t>(1, k / 2); wave_retries++;
+                    continue;
+                }
+                CTX_CUDA(cudaStreamSynchronize(S[0]));
+                return check_overflow(ctx);
+            }
+        }
         // ---- accum += the waves' samples, in sample order whatever stream a wave ran on -----------------------------
         for (int p = 0; p < NP; p++) {
             Pipe& pp = P[p];
             if (!pp.live) continue;
             if (NP > 1 && acc_recorded) CTX_CUDA(cudaStreamWaitEvent(pp.st, ctx->ev_acc, 0));
-            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw);
+            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw);
             CTX_LAUNCH_CHECK("k_accumulate");
             if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_acc, pp.st)); acc_recorded = true; }
         }
+        g0 += k * (uint32_t)NP;
     }
     for (int p = 1; p < NP; p++) { CTX_CUDA(cudaEventRecord(ctx->ev_join, S[p])); CTX_CUDA(cudaStreamWaitEvent(S[0], ctx->ev_join, 0)); }
     if (timing) {
@@ -719,8 +774,195 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
         stats->kernel_launches = ctx->launches - launches0;
         stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
         stats->max_queue = glass_branch ? h_cnt[CNT_HIGH_WATER] : std::min<uint32_t>(slots, npix * (s1 - s0));   // without branching the bounce-0 queue is the largest
+        stats->scheduler = NRCU_SCHED_WAVES; stats->iterations = bounce_rounds; stats->wave_retries = wave_retries;
+        return check_overflow(ctx);
     }
     return NRCU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Path-regeneration scheduler (kernels: k_regen_init, k_big_balanced<.., SLOTS>, k_trace2, k_shade_regen, k_accumulate_lanes)
+// ---------------------------------------------------------------------------------------------
+#define NRCU_REGEN_BATCH 8      // iterations enqueued between two looks at the alive flags
+#define NRCU_REGEN_RING 4       // batches whose counters / flags are live at any time
+static uint32_t regen_slots_target() { static uint32_t v = env_u32("NRCU_REGEN_MSLOTS", 64) << 20; return v; }
+
+static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats, uint32_t s0, uint32_t s1) {
+    ctx->ds.nee = 0;
+    const DScene& ds = ctx->ds;
+    const uint32_t npix = ds.width * ds.height, n_samples = s1 - s0;
+    const uint64_t seed = params ? params->seed : 0;
+    // K slots per pixel.  Automatic: as many as NRCU_REGEN_MSLOTS (default 64 Mi) slots allow; fewer slots per pixel mean
+    // more iterations per frame, i.e. a shorter drain phase relative to the frame.
+    uint32_t K = (params && params->scheduler == NRCU_SCHED_REGEN && params->samples_per_wave) ? params->samples_per_wave
+                                                                                              : std::max<uint32_t>(1, regen_slots_target() / npix);
+    K = std::min<uint32_t>(std::min<uint32_t>(K, n_samples), 32768u);
+    if ((uint64_t)K * npix > 0x7fffffffull) K = std::max<uint32_t>(1, (uint32_t)(0x7fffffffull / npix));
+    int NP = std::max(1, std::min<int>(concurrent_waves(), (int)K));
+    const size_t CS = counter_stride();
+    const size_t blk = 2 * CS + (size_t)NRCU_REGEN_FLAGS * NRCU_REGEN_FLAG_STRIDE;   // words per iteration: survivors, fetch cursor, alive flags
+    const size_t ring_iters = (size_t)NRCU_REGEN_BATCH * NRCU_REGEN_RING;
+    struct Part { uint32_t lane0, lanes, n_slots; PathQueue q; float2* hits; uint32_t* surv; f4* lacc; uint32_t* cnt; cudaStream_t st; bool done; uint32_t batches; } P[NRCU_MAX_WAVES];
+    int rc = NRCU_OK;
+    for (;;) {   // shrink K instead of failing when the device is smaller or fuller than a B200
+        rc = NRCU_OK;
+        for (int p = 0; p < NP && rc == NRCU_OK; p++) {
+            nrcu_ctx::WaveSet& w = ctx->ws[p];
+            P[p].lane0 = (uint32_t)((uint64_t)p * K / NP); P[p].lanes = (uint32_t)((uint64_t)(p + 1) * K / NP) - P[p].lane0;
+            P[p].n_slots = P[p].lanes * npix;
+            const size_t S = (size_t)wave_skew_kb() << 10;
+            DevBuf* bufs[] = {&w.qa[0], &w.qb[0], &w.qc[0], &w.hits, &w.surv, &w.L};
+            for (size_t j = 0; j < sizeof(bufs) / sizeof(bufs[0]); j++) bufs[j]->skew = (j + 1 + 9 * (size_t)p) * S;
+            auto need = [&](DevBuf& b, size_t bytes) { if (rc == NRCU_OK && b.ensure(bytes) != cudaSuccess) { ctx->error = "device allocation failed: out of memory"; rc = NRCU_ERR_CUDA; } };
+            need(w.qa[0], sizeof(f4) * (size_t)P[p].n_slots); need(w.qb[0], sizeof(float2) * (size_t)P[p].n_slots); need(w.qc[0], sizeof(f4) * (size_t)P[p].n_slots);
+            need(w.hits, sizeof(float2) * (size_t)P[p].n_slots); need(w.surv, sizeof(uint32_t) * (size_t)P[p].n_slots); need(w.L, sizeof(f4) * (size_t)P[p].n_slots);
+            need(w.counters, sizeof(uint32_t) * (CNT_QUEUE0 + blk * ring_iters));
+        }
+        if (rc == NRCU_OK) break;
+        cudaGetLastError();
+        if (K == 1) return rc;
+        for (int p = 0; p < NP; p++) { nrcu_ctx::WaveSet& w = ctx->ws[p]; for (DevBuf* b : {&w.qa[0], &w.qb[0], &w.qc[0], &w.hits, &w.surv, &w.L}) b->release(); }
+        K = std::max<uint32_t>(1, K / 2);
+        NP = std::max(1, std::min<int>(NP, (int)K));
+    }
+    const uint32_t samples_per_lane = (n_samples + K - 1) / K;
+    const uint64_t t_max = (uint64_t)samples_per_lane * ds.depth;   // a lane renders its samples one after the other, <= depth rays each
+    if (!ctx->h_flags) CTX_CUDA(cudaHostAlloc(&ctx->h_flags, sizeof(uint32_t) * NRCU_MAX_WAVES * NRCU_REGEN_RING * NRCU_REGEN_FLAGS * NRCU_REGEN_FLAG_STRIDE, cudaHostAllocDefault));
+    cudaStream_t S[NRCU_MAX_WAVES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
+    for (int p = 1; p < NP; p++) {
+        if (!ctx->extra_stream[p]) CTX_CUDA(cudaStreamCreateWithFlags(&ctx->extra_stream[p], cudaStreamNonBlocking));
+        S[p] = ctx->extra_stream[p];
+    }
+    if (NP > 1 && !ctx->ev_fork) {
+        CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_acc, cudaEventDisableTiming));
+    }
+    for (int p = 0; p < NP; p++) for (int r = 0; r < NRCU_REGEN_RING; r++)
+        if (!ctx->ev_batch[p][r]) CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_batch[p][r], cudaEventDisableTiming));
+    const int sms = sm_count(ctx->device);
+    const unsigned share = (unsigned)NP;
+    const unsigned big_grid = (unsigned)sms * (NP > 1 ? dual_big() : 8);
+    const bool timing = stats != nullptr, gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
+    size_t ev_i = 0;
+    struct Span { size_t a, b; int kind; };
+    std::vector<Span> spans;
+    CTX_CUDA(cudaMemsetAsync(ctx->ws[0].counters.p, 0, sizeof(uint32_t) * CNT_QUEUE0, S[0]));
+    if (timing) CTX_CUDA(cudaEventRecord(ctx->ev_begin, S[0]));
+    if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_fork, S[0])); for (int p = 1; p < NP; p++) CTX_CUDA(cudaStreamWaitEvent(S[p], ctx->ev_fork, 0)); }
+    const uint64_t launches0 = ctx->launches;
+    for (int p = 0; p < NP; p++) {
+        nrcu_ctx::WaveSet& w = ctx->ws[p];
+        P[p].q = PathQueue{w.qa[0].as<f4>(), w.qb[0].as<float2>(), w.qc[0].as<f4>(), nullptr};
+        P[p].hits = w.hits.as<float2>(); P[p].surv = w.surv.as<uint32_t>(); P[p].lacc = w.L.as<f4>(); P[p].cnt = w.counters.as<uint32_t>();
+        P[p].st = S[p]; P[p].done = false; P[p].batches = 0;
+    }
+    const size_t flag_words = (size_t)NRCU_REGEN_FLAGS * NRCU_REGEN_FLAG_STRIDE;
+    auto iter_block = [&](const Part& pp, uint64_t t) { return pp.cnt + CNT_QUEUE0 + blk * (size_t)(t % ring_iters); };
+    uint32_t iterations = 0;
+    const dim3 shade_block(256);
+    // Batches of NRCU_REGEN_BATCH iterations are enqueued two ahead of the last batch whose alive flags the host has seen:
+    // the GPU never waits for the host, and at most two batches of (immediately returning) kernels are launched in vain.
+    for (uint64_t b = 0;; b++) {
+        bool any = false;
+        for (int p = 0; p < NP; p++) {
+            Part& pp = P[p];
+            if (pp.done) continue;
+            if (b >= 2) {   // look at batch b-2
+                const int r = (int)((b - 2) % NRCU_REGEN_RING);
+                CTX_CUDA(cudaEventSynchronize(ctx->ev_batch[p][r]));
+                const uint32_t* hf = ctx->h_flags + ((size_t)p * NRCU_REGEN_RING + r) * flag_words;
+                uint32_t alive = 0;
+                for (int f = 0; f < NRCU_REGEN_FLAGS; f++) alive |= hf[(size_t)f * NRCU_REGEN_FLAG_STRIDE];
+                if (!alive) { pp.done = true; continue; }
+            }
+            const uint64_t t_first = b * NRCU_REGEN_BATCH;
+            if (t_first >= t_max) { pp.done = true; continue; }
+            any = true;
+            cudaStream_t st = pp.st;
+            CTX_CUDA(cudaMemsetAsync(iter_block(pp, t_first), 0, sizeof(uint32_t) * blk * NRCU_REGEN_BATCH, st));
+            const uint64_t t_last = std::min<uint64_t>(t_first + NRCU_REGEN_BATCH, t_max) - 1;
+            for (uint64_t t = t_first; t <= t_last; t++) {
+                uint32_t* ib = iter_block(pp, t);
+                uint32_t *n_surv = ib, *fetch = ib + CS, *flags = ib + 2 * CS;
+                const uint32_t* flags_prev = t ? iter_block(pp, t - 1) + 2 * CS : nullptr;
+                if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
+                if (t == 0) {
+                    const unsigned gen_grid = std::min<unsigned>(grid_for(pp.n_slots, 256), (unsigned)sms * 8);
+                    if (gate) k_regen_init<true><<<gen_grid, 256, 0, st>>>(ds, seed, s0, n_samples, pp.lane0, pp.n_slots, pp.q, pp.lacc, pp.hits, pp.surv, n_surv);
+                    else k_regen_init<false><<<gen_grid, 256, 0, st>>>(ds, seed, s0, n_samples, pp.lane0, pp.n_slots, pp.q, pp.lacc, pp.hits, pp.surv, n_surv);
+                    CTX_LAUNCH_CHECK("k_regen_init");
+                } else {
+                    if (gate) k_big_balanced<true, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots);
+                    else k_big_balanced<false, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots);
+                    CTX_LAUNCH_CHECK("k_big_balanced (slots)");
+                }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
+                if (bvh) {
+                    if (gate) launch_stage2<true>(ctx, st, share, ds, pp.q, pp.hits, pp.surv, n_surv, fetch, nullptr);
+                    else launch_stage2<false>(ctx, st, share, ds, pp.q, pp.hits, pp.surv, n_surv, fetch, nullptr);
+                    CTX_LAUNCH_CHECK("k_trace");
+                }
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 2}); }
+                k_shade_regen<<<dim3(grid_for(npix, 256), pp.lanes), shade_block, 0, st>>>(ds, seed, s0, n_samples, K, pp.lane0, pp.q, pp.hits, pp.lacc, flags_prev, flags);
+                CTX_LAUNCH_CHECK("k_shade_regen");
+                if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i + 2, ev_i + 3, 1}); ev_i += 4; }
+                if (p == 0) iterations++;
+            }
+            const int r = (int)(b % NRCU_REGEN_RING);
+            CTX_CUDA(cudaMemcpyAsync(ctx->h_flags + ((size_t)p * NRCU_REGEN_RING + r) * flag_words, iter_block(pp, t_last) + 2 * CS, sizeof(uint32_t) * flag_words, cudaMemcpyDeviceToHost, st));
+            CTX_CUDA(cudaEventRecord(ctx->ev_batch[p][r], st));
+        }
+        if (!any) break;
+    }
+    for (int p = 1; p < NP; p++) { CTX_CUDA(cudaEventRecord(ctx->ev_join, S[p])); CTX_CUDA(cudaStreamWaitEvent(S[0], ctx->ev_join, 0)); }
+    unsigned long long* d_rays = reinterpret_cast<unsigned long long*>(ctx->ws[0].counters.as<uint32_t>() + CNT_RAYS);
+    for (int p = 0; p < NP; p++) {   // lane order = partition order: the summation tree does not depend on NRCU_WAVES
+        k_accumulate_lanes<<<grid_for(npix, 256), 256, 0, S[0]>>>(P[p].lacc, d_accum, npix, P[p].lanes, p == 0 ? n_samples : 0u, d_rays);
+        CTX_LAUNCH_CHECK("k_accumulate_lanes");
+    }
+    if (timing) {
+        cudaStream_t st = S[0];
+        CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
+        unsigned long long rays = 0;
+        CTX_CUDA(cudaMemcpyAsync(&rays, d_rays, sizeof(rays), cudaMemcpyDeviceToHost, st));
+        CTX_CUDA(cudaStreamSynchronize(st));
+        std::memset(stats, 0, sizeof(*stats));
+        CTX_CUDA(cudaEventElapsedTime(&stats->ms_total, ctx->ev_begin, ctx->ev_end));
+        for (auto& sp : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]);
+            if (sp.kind == 0) stats->ms_trace += ms; else if (sp.kind == 2) { stats->ms_trace += ms; stats->ms_stage2 += ms; } else stats->ms_shade += ms;
+        }
+        stats->rays = rays; stats->paths = (uint64_t)npix * n_samples;
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
+        stats->max_queue = K * npix; stats->scheduler = NRCU_SCHED_REGEN; stats->iterations = iterations;
+        return check_overflow(ctx);
+    }
+    return NRCU_OK;
+}
+
+static int default_scheduler() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("NRCU_SCHED"); v = (e && std::string(e) == "waves") ? NRCU_SCHED_WAVES : ((e && std::string(e) == "regen") ? NRCU_SCHED_REGEN : NRCU_SCHED_DEFAULT); }
+    return v;
+}
+
+static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats) {
+    uint32_t s0 = params ? params->sample_begin : 0, s1 = params ? params->sample_end : 0;
+    if (s0 == 0 && s1 == 0) s1 = ctx->spp;
+    if (s1 < s0) { ctx->error = "sample_end < sample_begin"; return NRCU_ERR_INVALID; }
+    int sched = params ? (int)params->scheduler : NRCU_SCHED_AUTO;
+    if (sched != NRCU_SCHED_WAVES && sched != NRCU_SCHED_REGEN) sched = (params && params->samples_per_wave) ? NRCU_SCHED_WAVES : default_scheduler();
+    const bool nee = params && (params->flags & NRCU_FLAG_NEE) && ctx->ds.n_area_lights > 0;
+    const bool branch = params && params->glass_mode == NRCU_GLASS_BRANCH;
+    const uint32_t depth = ctx->ds.depth;
+    // the regeneration scheduler carries one ray per slot: no shadow rays, no path splitting; its state packs the bounce
+    // into 12 bits and counts a slot's rays in an fp32 (exact up to 2^24)
+    const bool can_regen = !nee && !branch && depth >= 1 && depth < (1u << NRCU_SLOT_BOUNCE_BITS) && s1 > s0 &&
+                           (uint64_t)(s1 - s0) * depth < (1ull << 24);
+    if (sched == NRCU_SCHED_REGEN && can_regen) return render_regen(ctx, params, d_accum, stats, s0, s1);
+    return render_waves(ctx, params, d_accum, stats);
 }
 
 int nrcu_render_accumulate(nrcu_ctx* ctx, const nrcu_render_params* params, float* d_accum, nrcu_stats* stats) {
@@ -770,7 +1012,7 @@ int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out
             stats->ms_trace = stats->ms_total; stats->rays = rays; stats->paths = npix;
             stats->kernel_launches = ctx->launches - launches0; stats->ms_setup = ctx->ms_setup; stats->n_primitives = ds.n_prims;
         }
-        return NRCU_OK;
+        return NRCU_OK;   // brute force: no traversal stack, nothing that can overflow
     }
     CTX_CUDA(ctx->accum_own.ensure(sizeof(f4) * (size_t)npix));
     CTX_CUDA(cudaMemsetAsync(ctx->accum_own.p, 0, sizeof(f4) * (size_t)npix, st));
@@ -784,7 +1026,7 @@ int nrcu_render(nrcu_ctx* ctx, const nrcu_render_params* params, float* rgba_out
     if (stats) stats->kernel_launches++;
     CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
     CTX_CUDA(cudaStreamSynchronize(st));
-    return NRCU_OK;
+    return check_overflow(ctx);
 }
 
 int nrcu_render_progressive(nrcu_ctx* ctx, const nrcu_render_params* params, uint32_t samples_per_update,
@@ -879,7 +1121,12 @@ int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params
         if (can) pf.part[g] = ctxs[g]->accum_own.as<f4>();
         else {   // no peer mapping: stage the partial frame through a copy
             CTX_CUDA(staged[g].ensure(sizeof(f4) * (size_t)npix));
-            CTX_CUDA(cudaMemcpyPeerAsync(staged[g].p, ctx->device, ctxs[g]->accum_own.p, ctxs[g]->device, sizeof(f4) * (size_t)npix, s0));
+            cudaError_t e = cudaMemcpyPeerAsync(staged[g].p, ctx->device, ctxs[g]->accum_own.p, ctxs[g]->device, sizeof(f4) * (size_t)npix, s0);
+            if (e != cudaSuccess) {
+                ctx->error = "device " + std::to_string(ctxs[g]->device) + ": partial frame neither peer-mapped nor copied: " + cudaGetErrorString(e);
+                cudaGetLastError();
+                return NRCU_ERR_PEER;
+            }
             pf.part[g] = staged[g].as<f4>();
         }
     }
@@ -928,6 +1175,7 @@ int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim
     std::vector<float2> h(n);
     CTX_CUDA(cudaMemcpyAsync(h.data(), hits.p, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CTX_CUDA(cudaStreamSynchronize(st));
+    if (int orc = check_overflow(ctx)) return orc;
     for (uint32_t i = 0; i < n; i++) {
         int id; std::memcpy(&id, &h[i].y, 4);
         if (prim_id) prim_id[i] = id;

@@ -21,6 +21,7 @@
 namespace nrcu {
 
 #define NRCU_NBINS 16
+#define NRCU_SAH_MAX_DEPTH 24
 #define NRCU_BIN_WORDS 7   // 6 encoded bounds + count
 
 // order-preserving float <-> int key (so that integer atomicMin/Max order floats)
@@ -246,7 +247,11 @@ NR_HD void bvh_split(const BvhBuild& b, int n) {
     int slot = b.nbin_slot[n];
     int best_axis = -1, best_k = 0;
     float best_cost = NRCU_INF;
-    if (slot >= 0 && slot < b.bin_nodes) {
+    // Depth cap: SAH planes may peel off one primitive per level on adversarial inputs.  From NRCU_SAH_MAX_DEPTH on, nodes
+    // are split at the median of their primitive-id range, which at least halves that range per level: the binary tree
+    // is at most NRCU_SAH_MAX_DEPTH + 32 levels deep, i.e. <= (24 + 32) / 2 = 28 BVH4 levels x 3 pushes = 84 stack
+    // entries < NRCU_LOCAL_STACK (96), whatever the scene.
+    if (slot >= 0 && slot < b.bin_nodes && b.ndepth[n] < NRCU_SAH_MAX_DEPTH) {
         const int* bn = b.bins + (size_t)slot * 3 * NRCU_NBINS * NRCU_BIN_WORDS;
         for (int a = 0; a < 3; a++) {
             float clo = fkey_inv(b.cbox[n * 6 + a]), chi = fkey_inv(b.cbox[n * 6 + 3 + a]);

@@ -11,7 +11,11 @@
 // closest_hit_bvh() is the replacement for closestHitObject (SimplePathTracer.cpp:104-129,
 // AccPathTracer.cpp:87-99 -> BVHTree::getIntersect BVH.hpp:93-164): inner nodes are culled with a
 // conservative slab test, the exact reference tests run only at the leaves, and equal-t ties go to
-// the lowest primitive id, which is what the reference's in-order loops produce.
+// the lowest primitive id.  That is what the in-order loops of RayCast and SimplePathTracer produce.  For
+// AccPathTracer it matches the reference EXCEPT in two corner cases the parity tests exclude: exact-t ties (the
+// reference's tree returns `hit1->t < hit2->t ? hit1 : hit2`, BVH.hpp:153, i.e. the RIGHT subtree wins a tie, which
+// depends on its unstable std::sort) and rays that pass a leaf's box but fail Bounds3::IntersectP of one of its
+// ancestors' boxes through rounding (the reference gates every inner node, this code and the oracle gate the leaf only).
 #pragma once
 #include "nrcu_scene.cuh"
 
@@ -141,9 +145,9 @@ NR_HD bool bounds_intersectp(f4 lo, f4 hi, const Ray& ray) {
 // the shared-memory stack in the device kernels.
 #define NRCU_LOCAL_STACK 96
 struct LocalStack {
-    float t[NRCU_LOCAL_STACK]; int ref[NRCU_LOCAL_STACK]; int sp;
-    NR_HD LocalStack() : sp(0) {}
-    NR_HD void push(float tt, int r) { if (sp < NRCU_LOCAL_STACK) { t[sp] = tt; ref[sp] = r; sp++; } }
+    float t[NRCU_LOCAL_STACK]; int ref[NRCU_LOCAL_STACK]; int sp; int dropped;   // dropped: entries that did not fit (the answer may be wrong)
+    NR_HD LocalStack() : sp(0), dropped(0) {}
+    NR_HD void push(float tt, int r) { if (sp < NRCU_LOCAL_STACK) { t[sp] = tt; ref[sp] = r; sp++; } else dropped++; }
     NR_HD bool pop(float& tt, int& r) { if (sp == 0) return false; sp--; tt = t[sp]; r = ref[sp]; return true; }
 };
 

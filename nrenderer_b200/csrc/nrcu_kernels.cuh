@@ -184,15 +184,27 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
 // per-candidate fallback stay with the owning lane.
 #define NRCU_BIGB_WARPS 8
 #define NRCU_BEST_NONE 0x7f800000ffffffffull
-template <bool GATE>
+// SLOTS (path-regeneration scheduler): the queue is the slot array of a partition - n_fixed entries, never compacted; a
+// slot whose lane has run out of samples holds a NaN origin and is skipped; rays are counted by the shading kernel;
+// `n_ptr` then points at the previous iteration's "somebody is still alive" flags (null in the first iteration).
+#define NRCU_REGEN_FLAGS 16        // alive flags per iteration, each on a 128-byte line of its own
+#define NRCU_REGEN_FLAG_STRIDE 32
+__device__ __forceinline__ bool regen_anyone_alive(const uint32_t* flags) {
+    if (!flags) return true;
+    uint32_t v = 0;
+    if (threadIdx.x < NRCU_REGEN_FLAGS) v = flags[threadIdx.x * NRCU_REGEN_FLAG_STRIDE];
+    return __syncthreads_or((int)v) != 0;
+}
+template <bool GATE, bool SLOTS>
 __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
-                                                                       uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
+                                                                       uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter, uint32_t n_fixed) {
     __shared__ BigList bl;
     __shared__ unsigned short pairs[NRCU_BIGB_WARPS][32 * NRCU_MAX_BIG];
     __shared__ float rays[NRCU_BIGB_WARPS][6][32];
     __shared__ unsigned long long best[NRCU_BIGB_WARPS][32];
+    if (SLOTS && !regen_anyone_alive(n_ptr)) return;
     bl.load(s);
-    const uint32_t n = *n_ptr;
+    const uint32_t n = SLOTS ? n_fixed : *n_ptr;
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, lt = (1u << lane) - 1u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -201,6 +213,11 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
     { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
         const uint32_t i = base + lane;
+        const bool live = SLOTS ? (i < n && a.x == a.x) : i < n;
+        if (SLOTS && !__any_sync(0xffffffffu, live)) {   // a warp of finished slots (end of the frame): only keep the pipeline going
+            const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; }
+            continue;
+        }
         Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
         const RayPrep rp = prep_ray(r);
         rays[wib][0][lane] = r.o.x; rays[wib][1][lane] = r.o.y; rays[wib][2][lane] = r.o.z;
@@ -211,7 +228,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
         // Lanes past the end of the queue: an x offset of -inf puts near and far at -inf, so tf = -inf < 0 <= tn and the
         // lane never becomes a candidate (prep_ray clamps 1/d to +-1e18, the products stay finite: no NaN) - one
         // predicate less per primitive than testing i < n inside the loop.
-        const float nox = i < n ? -rp.oinv.x : -NRCU_INF;
+        const float nox = live ? -rp.oinv.x : -NRCU_INF;
         const vec3 ainv = mk3(fabsf(rp.inv.x), fabsf(rp.inv.y), fabsf(rp.inv.z));
         for (uint32_t k = 0; k < s.n_big; k++) {
             float tn, tf;
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
         }
         __syncwarp();
         bool more = false;
-        if (i < n) {
+        if (live) {
             const unsigned long long key = best[wib][lane];
             float best_t = NRCU_INF; int best_id = -1;
             if (key != NRCU_BEST_NONE) {
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
             more = bvh_reachable(s, rp, best_t);
         }
         __syncwarp();   // the shared lists are rewritten by the next iteration
-        if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        if (!SLOTS && lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
         append_survivors(more, i, surv, n_surv);
     }
 }
@@ -275,10 +292,10 @@ struct Stack3 {
     float ot[NRCU_LOCAL_STACK - NRCU_T3_STACK];
     int oref[NRCU_LOCAL_STACK - NRCU_T3_STACK];
 };
-__device__ __forceinline__ void push3(Stack3& st, int& sp, float t, int r) {
+__device__ __forceinline__ void push3(const DScene& s, Stack3& st, int& sp, float t, int r) {
     if (sp < NRCU_T3_STACK) st.smem[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t), (unsigned)r);
-    else if (sp < NRCU_LOCAL_STACK) { st.ot[sp - NRCU_T3_STACK] = t; st.oref[sp - NRCU_T3_STACK] = r; }
-    else return;
+    else if (sp < s.stack_limit) { st.ot[sp - NRCU_T3_STACK] = t; st.oref[sp - NRCU_T3_STACK] = r; }
+    else { atomicAdd(s.overflow, 1u); return; }   // cannot happen with trees from nrcu_bvh.cuh (depth cap); counted, never silent
     sp++;
 }
 __device__ __forceinline__ int pop3(Stack3& st, int& sp, float best_t) {
@@ -316,9 +333,9 @@ __device__ __forceinline__ int node_step3(const DScene& s, const RayPrep& rp, in
         if (t2 < NRCU_INF) { st.smem[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t2), (unsigned)r2); sp++; }
         if (t1 < NRCU_INF) { st.smem[sp * NRCU_TRACE_THREADS] = make_uint2(__float_as_uint(t1), (unsigned)r1); sp++; }
     } else {
-        if (t3 < NRCU_INF) push3(st, sp, t3, r3);
-        if (t2 < NRCU_INF) push3(st, sp, t2, r2);
-        if (t1 < NRCU_INF) push3(st, sp, t1, r1);
+        if (t3 < NRCU_INF) push3(s, st, sp, t3, r3);
+        if (t2 < NRCU_INF) push3(s, st, sp, t2, r2);
+        if (t1 < NRCU_INF) push3(s, st, sp, t1, r1);
     }
     return (t0 < NRCU_INF) ? r0 : pop3(st, sp, best_t);
 }
@@ -572,6 +589,124 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Path-regeneration scheduler (the default for the reference's estimator; NEE and the branching glass mode keep the
+// per-bounce wavefront above)
+// ---------------------------------------------------------------------------------------------
+// A SLOT is bound to (pixel, lane): slot = lane * n_pixels + pixel, lane < K.  It carries ONE path at a time, in place
+// (ray a/b, throughput + state c, hit), and renders the samples  sample0 + lane + j*K,  j = 0, 1, ...  of its pixel one
+// after the other: when a path ends, the same thread adds its radiance to the slot's accumulator and starts the lane's
+// next sample in the same slot.  Nothing is compacted, so there is no output-queue allocation (the atomicAdd the
+// wavefront's k_shade spends 54 % of its stall samples on), every launch is full until the last samples of the frame
+// drain, and one iteration = stage 1 + stage 2 + shade over all slots whatever bounce each path is at.
+//   state (c.w bits) = j << 12 | bounce, or NRCU_SLOT_DEAD once the lane has no samples left (a.x = NaN then, which is
+//   what stage 1 looks at).  lacc[slot] = (sum of the lane's radiances in sample order, rays traced for them).
+// Per-pixel result = sum over lanes, in lane order, of the lane sums: a fixed fp32 summation tree for a given K.
+#define NRCU_SLOT_DEAD 0xffffffffu
+#define NRCU_SLOT_BOUNCE_BITS 12
+
+// First iteration: the lanes' first samples (+ fused stage 1: these camera rays are still coherent).
+template <bool GATE>
+__global__ void __launch_bounds__(256) k_regen_init(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_samples, uint32_t lane0, uint32_t n_slots,
+                                                   PathQueue q, f4* lacc, float2* hits, uint32_t* surv, uint32_t* n_surv) {
+    __shared__ BigList bl;
+    bl.load(s);
+    const uint32_t npix = s.width * s.height;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_slots; base += stride) {   // warp-uniform trip count
+        const uint32_t slot = base + threadIdx.x;
+        bool more = false;
+        if (slot < n_slots) {
+            const uint32_t pixel = slot % npix, lane = lane0 + slot / npix;
+            lacc[slot] = mk4(0.f, 0.f, 0.f, 0.f);
+            if (lane < n_samples) {
+                Ray r = pt_camera_ray(s, seed, pixel, sample0 + lane);
+                q.a[slot] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
+                q.b[slot] = make_float2(r.d.y, r.d.z);
+                q.c[slot] = mk4(1.f, 1.f, 1.f, i2f(0));
+                if (r.o.x == r.o.x) more = stage1<GATE>(s, bl, r, slot, hits);
+                else hits[slot] = make_float2(NRCU_INF, __int_as_float(-1));   // a NaN origin hits nothing (and stage 1 of later iterations skips it)
+            } else {
+                q.a[slot] = mk4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+                q.c[slot] = mk4(0.f, 0.f, 0.f, __int_as_float((int)NRCU_SLOT_DEAD));
+            }
+        }
+        append_survivors(more, slot, surv, n_surv);
+    }
+}
+
+// One path vertex per live slot: shade, then either continue in place or finish the sample and start the lane's next one.
+// Grid: x over pixels (256 per CTA), y over the lanes of this partition.  No atomics.
+__global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_regen(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_samples, uint32_t K, uint32_t lane0,
+                                                                      PathQueue q, float2* hits, f4* lacc, const uint32_t* flags_prev, uint32_t* flags_out) {
+    if (!regen_anyone_alive(flags_prev)) return;
+    const uint32_t npix = s.width * s.height;
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive_after = false;
+    if (pixel < npix) {
+        const size_t i = (size_t)blockIdx.y * npix + pixel;
+        const f4 c = q.c[i];
+        const uint32_t state = (uint32_t)f2i(c.w);
+        if (state != NRCU_SLOT_DEAD) {
+            const f4 a = q.a[i]; const float2 b = q.b[i]; float2 h = hits[i];
+            if (!(a.x == a.x)) h = make_float2(NRCU_INF, __int_as_float(-1));   // stage 1 skipped it: its hit record is stale
+            const uint32_t lane = lane0 + blockIdx.y, bounce = state & ((1u << NRCU_SLOT_BOUNCE_BITS) - 1u);
+            uint32_t j = state >> NRCU_SLOT_BOUNCE_BITS;
+            Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
+            const PathStep ps = path_vertex<false>(s, seed, pixel, sample0 + lane + j * K, bounce, 0u, r, mk3(c.x, c.y, c.z), h.x, __float_as_int(h.y), 0, false);
+            if (ps.action == PATH_CONTINUE) {
+                q.a[i] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
+                q.b[i] = make_float2(ps.next.d.y, ps.next.d.z);
+                q.c[i] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)(state + 1u)));
+                alive_after = true;
+            } else {
+                f4 v = lacc[i];
+                lacc[i] = mk4(v.x + ps.radiance.x, v.y + ps.radiance.y, v.z + ps.radiance.z, v.w + (float)(bounce + 1u));   // w: rays of the finished path
+                j++;
+                const uint32_t next_lane_sample = lane + j * K;
+                if (next_lane_sample < n_samples) {
+                    Ray nr = pt_camera_ray(s, seed, pixel, sample0 + next_lane_sample);
+                    q.a[i] = mk4(nr.o.x, nr.o.y, nr.o.z, nr.d.x);
+                    q.b[i] = make_float2(nr.d.y, nr.d.z);
+                    q.c[i] = mk4(1.f, 1.f, 1.f, i2f((int)(j << NRCU_SLOT_BOUNCE_BITS)));
+                    alive_after = true;
+                } else {
+                    q.a[i] = mk4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+                    q.c[i] = mk4(0.f, 0.f, 0.f, __int_as_float((int)NRCU_SLOT_DEAD));
+                }
+            }
+        }
+    }
+    if (__syncthreads_or((int)alive_after) && threadIdx.x == 0)
+        flags_out[((blockIdx.x + blockIdx.y) % NRCU_REGEN_FLAGS) * NRCU_REGEN_FLAG_STRIDE] = 1u;
+}
+
+// End of the frame (or slice): accum[p].rgb += the lanes' sums in lane order, accum[p].a += n_samples (passed for the
+// first partition only); the rays the lanes counted go to the context's ray counter, one atomic per CTA.
+__global__ void __launch_bounds__(256) k_accumulate_lanes(const f4* lacc, f4* accum, uint32_t npix, uint32_t lanes, uint32_t n_samples, unsigned long long* ray_counter) {
+    __shared__ unsigned long long warp_rays[8];
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long rays = 0;
+    if (p < npix) {
+        f4 acc = accum[p];
+        for (uint32_t k = 0; k < lanes; k++) {
+            f4 v = lacc[(size_t)k * npix + p];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z;
+            rays += (unsigned long long)v.w;
+        }
+        acc.w += (float)n_samples;
+        accum[p] = acc;
+    }
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, o);
+    if ((threadIdx.x & 31) == 0) warp_rays[threadIdx.x >> 5] = rays;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; w++) t += warp_rays[w];
+        if (t) atomicAdd(ray_counter, t);
+    }
+}
+
 // NEE: the shadow rays of one bounce after their closest-hit query - an unoccluded ray adds its contribution to
 // the radiance slot of its path (one shadow ray per path and bounce: plain read-modify-write; atomics when the glass
 // branches of a path share the slot).
@@ -589,15 +724,15 @@ __global__ void __launch_bounds__(256) k_shadow_resolve(DScene s, PathQueue qs, 
 }
 
 // The shade kernel may have tried to allocate past the queue capacity (glass branch mode only).
-__global__ void k_clamp_count(uint32_t* n_ptr, uint32_t capacity, uint32_t* high_water) {
+__global__ void k_clamp_count(uint32_t* n_ptr, uint32_t capacity, uint32_t* high_water, uint32_t* dropped) {
     uint32_t n = *n_ptr;
-    if (n > capacity) { n = capacity; *n_ptr = n; }
-    if (n > *high_water) *high_water = n;
+    if (n > *high_water) *high_water = n;   // the unclamped demand: a full queue and an overflow are told apart
+    if (n > capacity) { atomicAdd(dropped, n - capacity); *n_ptr = capacity; }
 }
 
 // End of wave: accum[p].rgb += L[s*npix + p] for the k samples of the wave in sample order (fp32,
 // the reference's `color += trace(...)`, AccPathTracer.cpp:30), accum[p].a += k.
-__global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k) {
+__global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k, uint32_t n_samples) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npix) return;
     f4 acc = accum[p];
@@ -605,7 +740,7 @@ __global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k) 
         f4 v = L[(size_t)s * npix + p];
         acc.x += v.x; acc.y += v.y; acc.z += v.z;
     }
-    acc.w += (float)k;
+    acc.w += (float)n_samples;
     accum[p] = acc;
 }
 

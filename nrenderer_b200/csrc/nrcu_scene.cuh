@@ -124,6 +124,11 @@ struct DScene {
     // minstd_rand with 6 on every call (Microfacet.cpp:65-76); computed on the host with libm.
     float mf_u1, mf_u2, mf_cos_phi, mf_sin_phi;
     int nee;                      // next-event estimation at Lambertian vertices (extension, NRCU_FLAG_NEE; off = reference estimator)
+    // Loud failure instead of a silently wrong frame: [0] traversal-stack entries that did not fit (a hit may have been
+    // missed), [1] rays that did not fit the branching-glass queue.  Read back by the host at every synchronisation
+    // point; non-zero => NRCU_ERR_OVERFLOW.
+    uint32_t* overflow;
+    int stack_limit;              // entries per traversal stack (NRCU_LOCAL_STACK; lowered only by the overflow test)
 };
 
 }  // namespace nrcu

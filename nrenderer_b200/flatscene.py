@@ -209,6 +209,20 @@ class FlatScene:
         self.material_params = np.concatenate([self.material_params.reshape(-1, MATERIAL_PARAM_FLOATS), params[None]])
         return self.n_materials - 1
 
+    def set_triangles(self, tris: np.ndarray, material: int, translation=(0, 0, 0)) -> None:
+        """Replace the geometry by one model of explicit triangles (n x 3 x 3, model-local); normals from the winding."""
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 3, 3)
+        n = len(tris)
+        nrm = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])
+        nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+        self.model_translation = np.array([translation], np.float32)
+        self.node_type = np.full(n, NODE_TRIANGLE, np.uint32)
+        self.node_entity = np.arange(n, dtype=np.uint32)
+        self.node_model = np.zeros(n, np.uint32)
+        self.triangle_vertices = tris.reshape(n, 9)
+        self.triangle_normal = nrm.astype(np.float32)
+        self.triangle_material = np.full(n, material, np.int32)
+
     def add_texture(self, rgba: np.ndarray) -> int:
         rgba = np.ascontiguousarray(rgba, np.float32)
         h, w, c = rgba.shape

@@ -35,6 +35,7 @@
 #include "utilities/ImageLoader.hpp"
 
 #include "../plugin/scene_bridge.hpp"
+#include "ComponentManager.hpp"
 
 // The importers call these after a successful parse to build OpenGL preview buffers
 // (code/app/src/importer/ScnImporter.cpp:508-514, ObjImporter.cpp:396-398); headless: no-ops.
@@ -93,15 +94,19 @@ static void usage() {
         "         [--mesh-material K] [--texture IMG] [--env-map TEXIDX]\n"
         "         [--w W --h H --depth D --spp S --aspect A --ambient R G B]\n"
         "         [--dump-flat OUT.nrsc]\n"
-        "         [--plugin LIB.so]... [--component NAME --out FRAME.f32|.ppm|.png|.pfm] [--repeat N] [--list]\n");
+        "         [--plugin LIB.so]... [--plugin-dir DIR] [--manager]\n"
+        "         [--component NAME --out FRAME.f32|.ppm|.png|.pfm] [--warmup W] [--repeat N] [--list]\n"
+        "  --plugin-dir DIR  load every *.so of DIR like the GUI's ComponentManager::init (ComponentManager.cpp:15-30)\n"
+        "  --manager         run the component the way the GUI does: ComponentManager::exec on a detached thread,\n"
+        "                    polling getState() and Screen::isUpdated() (ComponentProgressView.cpp, ScreenView.cpp:168-173)\n");
 }
 
 int main(int argc, char** argv) {
     std::vector<std::pair<std::string, std::string>> imports;
-    std::vector<std::string> plugins, textures;
+    std::vector<std::string> plugins, textures, plugin_dirs;
     std::string flat_in, flat_out, component, out;
-    int mesh_material = -1, env_map = -1, repeat = 1;
-    bool list = false;
+    int mesh_material = -1, env_map = -1, repeat = 1, warmup = 0;
+    bool list = false, via_manager = false;
     long w = -1, h = -1, depth = -1, spp = -1;
     float aspect = -1.f;
     bool have_ambient = false;
@@ -117,6 +122,9 @@ int main(int argc, char** argv) {
         else if (a == "--flat") flat_in = next();
         else if (a == "--dump-flat") flat_out = next();
         else if (a == "--plugin") plugins.push_back(next());
+        else if (a == "--plugin-dir") plugin_dirs.push_back(next());
+        else if (a == "--manager") via_manager = true;
+        else if (a == "--warmup") warmup = std::atoi(next().c_str());
         else if (a == "--component") component = next();
         else if (a == "--out") out = next();
         else if (a == "--mesh-material") mesh_material = std::atoi(next().c_str());
@@ -189,6 +197,11 @@ int main(int argc, char** argv) {
         // plugins depend on the one libNRServer.so.
         if (!dlopen(p.c_str(), RTLD_NOW | RTLD_LOCAL)) { std::fprintf(stderr, "dlopen %s: %s\n", p.c_str(), dlerror()); return 1; }
     }
+    ComponentManager manager;
+    for (auto& d : plugin_dirs) {
+        manager.init(d + "/*.so");
+        for (auto& e : manager.getLoadErrors()) std::fprintf(stderr, "plugin-dir %s: %s\n", d.c_str(), e.c_str());
+    }
     if (list) {
         for (auto& ci : getServer().componentFactory.getComponentsInfo("Render"))
             std::printf("%s\n", ci.name.c_str());
@@ -197,15 +210,33 @@ int main(int argc, char** argv) {
     if (!scene) { std::fprintf(stderr, "no scene\n"); return 2; }
 
     double best = 1e300, total = 0;
-    for (int r = 0; r < repeat; r++) {
+    unsigned screen_updates = 0;
+    ComponentInfo info;
+    for (auto& ci : getServer().componentFactory.getComponentsInfo("Render")) if (ci.name == component) info = ci;
+    for (int r = -warmup; r < repeat; r++) {
         // The reference components mutate the Scene in place, so every run gets a fresh copy
         // (the GUI builds a new Scene per click, SceneView.cpp:100-101).
         SharedScene run_scene = std::make_shared<Scene>(*scene);
-        auto comp = getServer().componentFactory.createComponent<RenderComponent>("Render", component);
-        if (!comp) { std::fprintf(stderr, "component %s is not registered\n", component.c_str()); return 1; }
-        auto t0 = std::chrono::steady_clock::now();
-        comp->exec([] {}, [] {}, run_scene);
-        double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        double s;
+        if (via_manager) {
+            auto t0 = std::chrono::steady_clock::now();
+            if (!manager.exec<RenderComponent>(info, run_scene)) { std::fprintf(stderr, "component %s is not registered\n", component.c_str()); return 1; }
+            // what the GUI's frame loop does while the worker runs: look at the state, re-read the screen when it changed
+            while (manager.getState() != ComponentManager::State::FINISH) {
+                if (getServer().screen.isUpdated()) { (void)getServer().screen.getPixels(); if (r >= 0) screen_updates++; }
+                std::this_thread::sleep_for(std::chrono::microseconds(200));
+            }
+            s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (getServer().screen.isUpdated()) { (void)getServer().screen.getPixels(); if (r >= 0) screen_updates++; }
+            manager.finish();
+        } else {
+            auto comp = getServer().componentFactory.createComponent<RenderComponent>("Render", component);
+            if (!comp) { std::fprintf(stderr, "component %s is not registered\n", component.c_str()); return 1; }
+            auto t0 = std::chrono::steady_clock::now();
+            comp->exec([] {}, [] {}, run_scene);
+            s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (r < 0) continue;   // warm-up runs are not timed
         best = std::min(best, s); total += s;
     }
     auto& screen = getServer().screen;
@@ -237,15 +268,23 @@ int main(int argc, char** argv) {
             o.write((const char*)px, sizeof(float) * 4 * (size_t)sw * sh);
         }
     }
-    std::string last_log;
+    std::string last_log, last_error;
+    unsigned n_errors = 0, n_warnings = 0;
     {
         auto logs = getServer().logger.get();
-        for (unsigned i = 0; i < logs.nums; i++) last_log = logs.msgs[i].message;
+        for (unsigned i = 0; i < logs.nums; i++) {
+            last_log = logs.msgs[i].message;
+            if (logs.msgs[i].type == Logger::LogType::ERROR) { n_errors++; last_error = logs.msgs[i].message; }
+            if (logs.msgs[i].type == Logger::LogType::WARNING) n_warnings++;
+        }
     }
-    for (auto& c : last_log) if (c == '"' || c == '\n' || c == '\\') c = ' ';
+    for (auto* str : {&last_log, &last_error}) for (auto& c : *str) if (c == '"' || c == '\n' || c == '\\') c = ' ';
     std::printf("{\"component\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %u, \"depth\": %u, "
-                "\"seconds\": %.6f, \"seconds_mean\": %.6f, \"repeat\": %d, \"host_threads\": %u, \"last_log\": \"%s\"}\n",
+                "\"seconds\": %.6f, \"seconds_mean\": %.6f, \"repeat\": %d, \"warmup\": %d, \"host_threads\": %u, \"via\": \"%s\", "
+                "\"screen_updates\": %u, \"errors\": %u, \"warnings\": %u, \"last_error\": \"%s\", \"last_log\": \"%s\"}\n",
                 component.c_str(), sw, sh, scene->renderOption.samplesPerPixel, scene->renderOption.depth,
-                best, total / repeat, repeat, std::thread::hardware_concurrency(), last_log.c_str());
+                best, total / repeat, repeat, warmup, std::thread::hardware_concurrency(),
+                via_manager ? "ComponentManager::exec (detached thread)" : "RenderComponent::exec",
+                screen_updates, n_errors, n_warnings, last_error.c_str(), last_log.c_str());
     return 0;
 }

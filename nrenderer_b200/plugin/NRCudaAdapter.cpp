@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -36,9 +37,10 @@ namespace NRCuda
     // (the GUI runs render() on a fresh detached thread per click, ComponentManager.hpp:41-64).
     struct SharedContext {
         std::mutex mtx;
-        nrcu_ctx* ctx = nullptr;               // device NRCU_DEVICE (default 0)
-        std::vector<nrcu_ctx*> extra;          // further devices when NRCU_DEVICES > 1 (sample slices, nrcu_render_multi)
-        ~SharedContext() { for (auto* c : extra) nrcu_destroy(c); if (ctx) nrcu_destroy(ctx); }
+        nrcu_ctx* ctx = nullptr;               // primary device: NRCU_DEVICE (default 0)
+        int ctx_device = -1;
+        std::map<int, nrcu_ctx*> extra;        // further devices when NRCU_DEVICES > 1, keyed by DEVICE INDEX (sample slices, nrcu_render_multi)
+        ~SharedContext() { for (auto& kv : extra) nrcu_destroy(kv.second); if (ctx) nrcu_destroy(ctx); }
     };
     static SharedContext& shared() { static SharedContext s; return s; }
 
@@ -62,39 +64,49 @@ namespace NRCuda
 
                 auto& sh = shared();
                 std::lock_guard<std::mutex> lock(sh.mtx);
+                int dev = 0;
+                if (const char* e = std::getenv("NRCU_DEVICE")) dev = std::atoi(e);
+                if (sh.ctx && sh.ctx_device != dev) {   // NRCU_DEVICE changed between two renders: rebind, do not keep a stale device
+                    nrcu_destroy(sh.ctx); sh.ctx = nullptr;
+                    auto it = sh.extra.find(dev);
+                    if (it != sh.extra.end()) { nrcu_destroy(it->second); sh.extra.erase(it); }
+                }
                 if (!sh.ctx) {
-                    int dev = 0;
-                    if (const char* e = std::getenv("NRCU_DEVICE")) dev = std::atoi(e);
                     if (nrcu_create(dev, &sh.ctx) != NRCU_OK) {
                         logger.error(std::string("NRCuda: ") + nrcu_last_error(nullptr));
                         publishBlack(w, h);
                         return;
                     }
+                    sh.ctx_device = dev;
                 }
                 if (nrcu_upload_scene(sh.ctx, &view, NRCU_PLUGIN_MODE) != NRCU_OK) {
                     logger.error(std::string("NRCuda: ") + nrcu_last_error(sh.ctx));
                     publishBlack(w, h);
                     return;
                 }
-                // NRCU_DEVICES=N (or "all"): split the samples of the frame over N GPUs of this box
+                // NRCU_DEVICES=N (or "all"): split the samples of the frame over N GPUs of this box.  A device that
+                // cannot be opened or refuses the scene is skipped (and said so); the next device index is tried instead.
                 std::vector<nrcu_ctx*> devs{sh.ctx};
+                std::vector<int> dev_ids{dev};
                 if (const char* e = std::getenv("NRCU_DEVICES")) {
-                    int want = std::string(e) == "all" ? nrcu_device_count() : std::atoi(e);
-                    want = std::min(want, nrcu_device_count());
-                    for (int d = 0, have = 1; d < nrcu_device_count() && have < want; d++) {
-                        bool used = false;   // the primary context may sit on any device
-                        if (const char* pd = std::getenv("NRCU_DEVICE")) used = std::atoi(pd) == d; else used = d == 0;
-                        if (used) continue;
-                        size_t slot = (size_t)have - 1;
-                        if (sh.extra.size() <= slot) {
+                    const int n_dev = nrcu_device_count();
+                    const int want = std::min(std::string(e) == "all" ? n_dev : std::atoi(e), n_dev);
+                    for (int d = 0; d < n_dev && (int)devs.size() < want; d++) {
+                        if (d == dev) continue;
+                        auto it = sh.extra.find(d);
+                        if (it == sh.extra.end()) {
                             nrcu_ctx* c = nullptr;
-                            if (nrcu_create(d, &c) != NRCU_OK) { logger.warning(std::string("NRCuda: device skipped: ") + nrcu_last_error(nullptr)); continue; }
-                            sh.extra.push_back(c);
+                            if (nrcu_create(d, &c) != NRCU_OK) {
+                                logger.warning("NRCuda: device " + std::to_string(d) + " skipped: " + nrcu_last_error(nullptr));
+                                continue;
+                            }
+                            it = sh.extra.emplace(d, c).first;
                         }
-                        if (nrcu_upload_scene(sh.extra[slot], &view, NRCU_PLUGIN_MODE) != NRCU_OK) {
-                            logger.warning(std::string("NRCuda: device skipped: ") + nrcu_last_error(sh.extra[slot])); continue;
+                        if (nrcu_upload_scene(it->second, &view, NRCU_PLUGIN_MODE) != NRCU_OK) {
+                            logger.warning("NRCuda: device " + std::to_string(d) + " skipped: " + nrcu_last_error(it->second));
+                            continue;
                         }
-                        devs.push_back(sh.extra[slot]); have++;
+                        devs.push_back(it->second); dev_ids.push_back(d);
                     }
                 }
                 nrcu_render_params params{};
@@ -116,7 +128,12 @@ namespace NRCuda
                                                  }, &pub, &st);
                 } else rc = nrcu_render_multi(devs.data(), (int)devs.size(), &params, reinterpret_cast<float*>(pixels), &st);
                 if (rc != NRCU_OK) {
-                    logger.error(std::string("NRCuda: ") + nrcu_last_error(sh.ctx));
+                    std::string why = nrcu_last_error(sh.ctx);   // the root context carries "device N: ..." for a failed peer
+                    for (size_t g = 1; g < devs.size(); g++) {
+                        const char* pe = nrcu_last_error(devs[g]);
+                        if (pe && *pe && why.find(pe) == std::string::npos) why += " | device " + std::to_string(dev_ids[g]) + ": " + pe;
+                    }
+                    logger.error("NRCuda: " + why);
                     delete[] pixels;
                     publishBlack(w, h);
                     return;

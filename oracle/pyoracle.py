@@ -145,8 +145,10 @@ def ref_available() -> bool:
     return os.path.exists(os.path.join(REF_DIR, "nr_headless")) and os.path.exists(os.path.join(REF_DIR, "libNRServer.so"))
 
 
-def run_reference(flat, component: str, *, repeat: int = 1, extra_plugins=(), timeout=3600):
-    """Run a registered render component through the reference's plugin API on a flat scene.
+def run_reference(flat, component: str, *, repeat: int = 1, warmup: int = 0, extra_plugins=(), plugin_dirs=(), manager=False, env=None, timeout=3600):
+    """Run a registered render component through the reference's plugin API on a flat scene
+    (nr_headless: SceneBuilder-equivalent Scene -> ComponentFactory::createComponent -> RenderComponent::exec -> Screen).
+    `manager`: go through ComponentManager::exec on a detached thread like the GUI.  `env`: extra environment (NRCU_*).
     Returns (rgba[h,w,4], info dict with wall seconds)."""
     if not ref_available():
         raise RuntimeError("oracle/_ref is not built (run oracle/build_ref.py where /root/reference is mounted)")
@@ -159,10 +161,15 @@ def run_reference(flat, component: str, *, repeat: int = 1, extra_plugins=(), ti
             plugins.append(os.path.join(REF_DIR, REF_PLUGINS[component]))
         for p in plugins:
             cmd += ["--plugin", p]
-        cmd += ["--component", component, "--out", out_path, "--repeat", str(repeat)]
-        env = dict(os.environ)
-        env["LD_LIBRARY_PATH"] = REF_DIR + os.pathsep + env.get("LD_LIBRARY_PATH", "")
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        for d in plugin_dirs:
+            cmd += ["--plugin-dir", d]
+        if manager:
+            cmd += ["--manager"]
+        cmd += ["--component", component, "--out", out_path, "--repeat", str(repeat), "--warmup", str(warmup)]
+        full_env = dict(os.environ)
+        full_env.update(env or {})
+        full_env["LD_LIBRARY_PATH"] = REF_DIR + os.pathsep + full_env.get("LD_LIBRARY_PATH", "")
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=full_env)
         if r.returncode != 0:
             raise RuntimeError(f"nr_headless failed: {r.stderr[-2000:]}")
         info = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])

@@ -28,14 +28,14 @@ def test_library_builds_and_exports_every_symbol():
     lib = C.CDLL(so)
     for sym in declared_symbols():
         assert hasattr(lib, sym), sym
-    assert api.load_library().nrcu_abi_version() == 1
+    assert api.load_library().nrcu_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
     from nrenderer_b200 import api, flatscene
     assert C.sizeof(flatscene.NrcuMaterial) == 24 * 4
     assert C.sizeof(api.NrcuRenderParams) == 32
-    assert C.sizeof(api.NrcuStats) == 56
+    assert C.sizeof(api.NrcuStats) == 72
     # compile a tiny C program printing sizeof/offsetof and compare
     import subprocess, tempfile
     src = r'''
@@ -49,7 +49,7 @@ def test_struct_layouts_match_the_header():
         subprocess.run(["gcc", f"-I{REPO}/include", os.path.join(td, "t.c"), "-o", os.path.join(td, "t")], check=True)
         out = subprocess.run([os.path.join(td, "t")], capture_output=True, text=True, check=True).stdout.split()
     S = flatscene.NrcuScene
-    assert [int(x) for x in out] == [C.sizeof(S), S.materials.offset, S.texture_rgba.offset, 96, 32, 56]
+    assert [int(x) for x in out] == [C.sizeof(S), S.materials.offset, S.texture_rgba.offset, 96, 32, 72]
 
 
 def test_philox_known_answers():

@@ -91,3 +91,45 @@ def test_harness_image_writers(tmp_path):
     assert struct.unpack(">IIBBBBB", chunks[0][1]) == (40, 30, 8, 2, 0, 0, 0)
     rows = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(30, 1 + 3 * 40)
     assert not rows[:, 0].any() and np.array_equal(rows[:, 1:].reshape(30, 40, 3), want)
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
+def test_component_manager_hosts_plugins_like_the_gui(tmp_path):
+    """harness/ComponentManager.hpp (Linux stand-in for app/include/manager/ComponentManager.hpp): directory scan + dlopen,
+    exec on a detached thread, IDLING -> READY -> RUNNING -> FINISH; the frame equals the direct exec() frame."""
+    fs = load_scene("ray_cast_cornel", width=60, height=40)
+    direct, d_info = po.run_reference(fs, "RayCast")
+    managed, info = po.run_reference(fs, "RayCast", plugin_dirs=[po.REF_DIR], manager=True, repeat=2, warmup=1)
+    assert "ComponentManager" in info["via"] and "RenderComponent::exec" in d_info["via"]
+    assert info["repeat"] == 2 and info["warmup"] == 1 and info["screen_updates"] == 2 and info["errors"] == 0
+    assert np.array_equal(direct, managed)
+    # an unknown component is refused before a thread is started
+    env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
+    r = subprocess.run([os.path.join(po.REF_DIR, "nr_headless"), "--flat", os.path.join(GOLDEN, "ray_cast_cornel.nrsc"), "--plugin-dir", po.REF_DIR,
+                        "--manager", "--component", "NoSuchRenderer"], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "not registered" in r.stderr
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
+def test_texture_files_go_through_the_reference_image_loader(tmp_path):
+    """--texture decodes with the reference's ImageLoader (stb, channel / 255.f, 4 channels: ImageLoader.cpp:8-19) and
+    --env-map sets Ambient::Type::ENVIROMENT_MAP + the texture handle like SceneBuilder.cpp:89-98."""
+    import struct, zlib
+    rng = np.random.default_rng(7)
+    w, h = 20, 10
+    tex8 = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    raw = b"".join(b"\x00" + tex8[y].tobytes() for y in range(h))
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body))
+    png = tmp_path / "env.png"
+    png.write_bytes(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+    out = tmp_path / "t.nrsc"
+    env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
+    subprocess.run([os.path.join(po.REF_DIR, "nr_headless"), "--flat", os.path.join(GOLDEN, "env_map_spheres.nrsc"), "--texture", str(png), "--env-map", "0",
+                    "--dump-flat", str(out)], check=True, env=env)
+    fs = FlatScene.load(out)
+    assert fs.ambient_type == 1 and fs.ambient_environment_map == 0
+    assert (int(fs.texture_width[0]), int(fs.texture_height[0])) == (w, h)
+    tex = fs.texture_rgba.reshape(h, w, 4)
+    assert np.array_equal(tex[..., :3], tex8.astype(np.float32) / np.float32(255.0)) and (tex[..., 3] == 1).all()
