@@ -13,12 +13,16 @@ partial linear frames are combined with one NCCL reduce, rank 0 resolves (÷spp,
 
 One JSON line on rank 0:
   value      Mpath-samples/s, whole job, scene resident in HBM, device-timed (CUDA events, max over ranks)
-  e2e        the same metric through the reference-facing call sequence with HOST buffers: upload of
-             the Scene arrays (H2D), render, D2H of the RGBA frame that Screen::set would receive
-  roofline   the closest-hit kernels (k_raygen incl. fused stage 1, k_big, k_trace2): algorithmic bytes/ray x rays /
-             CUDA-event time of their launches inside the timed region
+  e2e        the same metric THROUGH THE DROP-IN: wall time around RenderComponent::exec of the registered plugin
+             (nr_headless -> ComponentFactory::createComponent -> exec -> NRCuda::Adapter::render -> nrcu_* -> Screen::set),
+             i.e. Scene flattening, H2D, BVH build, render, D2H into the adapter's pageable RGBA buffer and the
+             Screen::set copy, every step; with N GPUs the plugin runs with NRCU_DEVICES=N (nrcu_render_multi)
+  roofline   the binding roofline of the step: SM issue slots.  achieved = warp instructions per path sample (ncu launch
+             list of this very code, profiles/) x paths of the timed region / its CUDA-event time; peak = SMs x 4 x the SM
+             clock sampled during the run.  roofline_hbm: the same step against HBM with this implementation's own bytes
   cpu_baseline  the reference's own AccPathTracer (oracle/_ref, unmodified sources) on the host cores,
-             on a bounded sample (same frame, few spp)
+             on a bounded sample (same frame, few spp, two spp values to show the rate is spp-independent)
+  other_workloads  BASELINE.json's other configs (cfg1, cfg2, cfg4-i/ii/iii; cfg5 at every N), one or two steps each
 """
 import argparse
 import json
@@ -33,26 +37,43 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 WORKLOADS = {
-    # name: (scene fixture, mode, width, height, spp, depth, aspect, reference component, algorithmic bytes per ray)
-    "cfg2_simple_cornell_1024x1024_2048spp": ("path_tracing_cornel", 1, 1024, 1024, 2048, 20, 1.0, "SimplePathTracer", 866.0),
-    "cfg3_acc_bunny5k_1920x1080_1024spp": ("bunny5k_cornel", 2, 1920, 1080, 1024, 20, 16.0 / 9.0, "AccPathTracer", 2039.0),
-    "cfg4_acc_gold_1920x1080_4096spp": ("pt_glass", 2, 1920, 1080, 4096, 20, 16.0 / 9.0, "AccPathTracer", 866.0),
-    # cfg5: no reference semantics; synthetic 64x32 lat-long map; meant for --gpus 8 (weak point: 34 G paths)
-    "cfg5_acc_envmap_3840x2160_4096spp": ("env_map_spheres", 2, 3840, 2160, 4096, 20, 16.0 / 9.0, "AccPathTracer", 866.0),
+    # name: (scene fixture, mode, width, height, spp, depth, aspect, reference component, edit applied to the fixture)
+    "cfg1_raycast_cornell_500x500_1spp": ("ray_cast_cornel", 0, 500, 500, 1, 20, 1.0, "RayCast", None),
+    "cfg2_simple_cornell_1024x1024_2048spp": ("path_tracing_cornel", 1, 1024, 1024, 2048, 20, 1.0, "SimplePathTracer", None),
+    "cfg3_acc_bunny5k_1920x1080_1024spp": ("bunny5k_cornel", 2, 1920, 1080, 1024, 20, 16.0 / 9.0, "AccPathTracer", None),
+    "cfg4_acc_gold_1920x1080_4096spp": ("pt_glass", 2, 1920, 1080, 4096, 20, 16.0 / 9.0, "AccPathTracer", None),
+    # cfg4-ii / cfg4-iii are harness-defined: the sphere as Glass{ior 1.5}; Box/Pyramid as type-3 (microfacet) materials
+    "cfg4ii_acc_glass_1920x1080_4096spp": ("pt_glass", 2, 1920, 1080, 4096, 20, 16.0 / 9.0, "AccPathTracer", "glass"),
+    "cfg4iii_acc_microfacet_1920x1080_4096spp": ("pt_glass_conductors", 2, 1920, 1080, 4096, 20, 16.0 / 9.0, "AccPathTracer", "microfacet"),
+    # cfg5: no reference semantics; synthetic 64x32 lat-long map
+    "cfg5_acc_envmap_3840x2160_4096spp": ("env_map_spheres", 2, 3840, 2160, 4096, 20, 16.0 / 9.0, "AccPathTracer", "envmap"),
 }
 DEFAULT_WORKLOAD = "cfg3_acc_bunny5k_1920x1080_1024spp"
+OTHER_WORKLOADS = ["cfg1_raycast_cornell_500x500_1spp", "cfg2_simple_cornell_1024x1024_2048spp", "cfg4_acc_gold_1920x1080_4096spp",
+                   "cfg4ii_acc_glass_1920x1080_4096spp", "cfg4iii_acc_microfacet_1920x1080_4096spp"]
+CFG5 = "cfg5_acc_envmap_3840x2160_4096spp"
+# This implementation's own algorithmic HBM bytes: per ray 24 B read by stage 1 + 8 B hit written, 40 + 8 B read and
+# 40 B written by the shading kernel; per path 32 B of radiance accumulation.  The scene itself is L1/L2 resident.
+ALGO_BYTES_PER_RAY, ALGO_BYTES_PER_PATH = 120.0, 32.0
+# SURVEY 8(d)'s figure for the REFERENCE's never-pruned binary tree (53.5 box tests/ray on the bunny): kept as a side key only
+REFERENCE_TRAVERSAL_BYTES_PER_RAY = {"bunny5k_cornel": 2039.0}
 
 
 def load_workload(name, spp_override=None):
+    import numpy as np
     from nrenderer_b200.flatscene import FlatScene
-    scene, mode, w, h, spp, depth, aspect, comp, bpr = WORKLOADS[name]
+    scene, mode, w, h, spp, depth, aspect, comp, edit = WORKLOADS[name]
     fs = FlatScene.load(os.path.join(REPO, "tests", "golden", scene + ".nrsc"))
     fs.width, fs.height, fs.samples_per_pixel, fs.depth, fs.cam_aspect = w, h, spp_override or spp, depth, aspect
-    if name.startswith("cfg5"):   # ambient = environment map (extension); deterministic synthetic texture
-        import numpy as np
+    if edit == "glass":
+        fs.sphere_material[:] = fs.add_material(2, ior=1.5, absorbed=[1, 1, 1])
+    elif edit == "microfacet":        # conductors.scn's type-3 materials on the pyramid triangles and the box quads
+        fs.triangle_material[:] = 4 + 6
+        fs.plane_material[5:] = 4 + 0
+    elif edit == "envmap":            # ambient = environment map (extension); deterministic synthetic texture
         g = np.random.default_rng(1)
         fs.ambient_type, fs.ambient_environment_map = 1, fs.add_texture(g.uniform(0.0, 2.0, (32, 64, 4)).astype(np.float32))
-    return fs, mode, comp, bpr
+    return fs, mode, comp
 
 
 def peaks():
@@ -63,26 +84,71 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def csrc_hash():
+    """Hash of the kernel sources: profiles/*_summary.json records it, so that instruction counts taken from an ncu capture
+    of OTHER code are flagged (`profile_stale`)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(REPO, "nrenderer_b200", "csrc")
+    for f in sorted(os.listdir(d)) + ["../../include/nrcu.h"]:
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode()); h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def profile_summary():
-    """Numbers derived from the committed ncu captures (profiles/r1_summary.json); not measured live."""
-    p = os.path.join(REPO, "profiles", "r1_summary.json")
-    try:
-        return json.load(open(p))
-    except Exception:
-        return {}
+    """Numbers derived from the committed ncu launch list of the bench workload (profiles/r2_summary.json, written by
+    tools/make_profile_summary.py): warp instructions and DRAM bytes per path sample.  Not measured live - ncu serialises
+    and slows the kernels - which is why the summary carries the hash of the code it was taken from."""
+    for name in ("r2_summary.json", "r1_summary.json"):
+        try:
+            d = json.load(open(os.path.join(REPO, "profiles", name)))
+            d["_file"] = "profiles/" + name
+            return d
+        except Exception:
+            continue
+    return {}
 
 
-def issue_roofline(workload, paths, ms, clocks, world=1):
-    """The binding roofline: warp instructions per path sample (committed ncu launch list of this workload) x the paths of
-    the timed region / its live CUDA-event time, against 148 SMs x 4 schedulers x the SM clock sampled during the run."""
-    d = dict(profile_summary().get("issue") or {})
-    wipp = d.get("warp_inst_per_path_sample")
-    if wipp and workload == DEFAULT_WORKLOAD and ms > 0:
-        mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        peak = 148 * 4 * mhz * world              # warp instructions per microsecond, all GPUs
-        d["step"] = {"bound": "issue", "achieved": wipp * paths / (ms * 1e3), "peak": peak, "unit": "warp-inst/us", "frac": wipp * paths / (ms * 1e3) / peak,
-                     "sm_mhz": mhz, "note": "whole step, all kernels, both concurrent waves"}
-    return d
+def sm_count():
+    import torch
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+def rooflines(workload, paths, rays, ms, clocks, world, scheduler):
+    """roofline (issue slots, the binding one) and roofline_hbm for the timed region of the default workload."""
+    prof = profile_summary()
+    issue = prof.get("issue") or {}
+    per_sched = (prof.get("per_scheduler") or {}).get(scheduler) or {}
+    wipp = per_sched.get("warp_inst_per_path_sample") or issue.get("warp_inst_per_path_sample")
+    dram_pp = per_sched.get("dram_bytes_per_path_sample") or issue.get("dram_bytes_per_path_sample")
+    stale = prof.get("csrc_sha") != csrc_hash()
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    sms = sm_count()
+    hbm_peak, peak_src = peaks()
+    secs = ms * 1e-3
+    roof = {"bound": "issue", "achieved": None, "peak": sms * 4 * mhz * world, "unit": "warp-inst/us", "frac": None, "traffic": None,
+            "kernel": "whole step (stage 1 + BVH traversal + shading; all concurrent streams)",
+            "peak_source": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz sampled during the timed region x {world} GPU(s)",
+            "warp_inst_per_path_sample": wipp, "threads_per_inst": per_sched.get("threads_per_inst") or issue.get("threads_per_inst_step"),
+            "profile": prof.get("_file"), "profile_csrc_sha": prof.get("csrc_sha"), "csrc_sha": csrc_hash(), "profile_stale": stale,
+            "note": "achieved = warp instructions per path sample (ncu launch list of the same command, committed under profiles/) x the path samples of "
+                    "the timed region / its CUDA-event time; the scene is L1/L2 resident, so issue slots, not HBM, bound the step (roofline_hbm)"}
+    hbm = {"bound": "hbm", "peak": hbm_peak * world, "unit": "GB/s", "peak_source": peak_src,
+           "algorithmic_bytes_per_path_sample": None, "measured_dram_bytes_per_path_sample": dram_pp, "achieved": None, "frac": None, "achieved_measured_traffic": None}
+    if workload == DEFAULT_WORKLOAD and secs > 0 and paths > 0:
+        if wipp:
+            roof["achieved"] = wipp * paths / (ms * 1e3)
+            roof["frac"] = roof["achieved"] / roof["peak"]
+        algo = ALGO_BYTES_PER_RAY * rays / paths + ALGO_BYTES_PER_PATH
+        hbm["algorithmic_bytes_per_path_sample"] = algo
+        hbm["achieved"] = algo * paths / secs * 1e-9
+        hbm["frac"] = hbm["achieved"] / hbm["peak"]
+        if dram_pp:
+            roof["traffic"] = dram_pp * paths / max(1, 1)      # DRAM bytes of the timed region (ncu bytes per path sample x paths)
+            hbm["achieved_measured_traffic"] = dram_pp * paths / secs * 1e-9
+            hbm["traffic_over_algorithmic"] = dram_pp / algo
+    return roof, hbm
 
 
 class ClockSampler(threading.Thread):
@@ -133,12 +199,22 @@ def calibrated_reference_spp(fs, component, target_seconds):
     return spp, paths / sec * 1e-6
 
 
+def reference_linearity(fs, component, spp):
+    """the CPU rate is quoted from a few-spp sample of the frame, so show that it does not depend on spp."""
+    a = max(1, spp // 2)
+    sa, pa = run_reference_sample(fs, component, a)
+    sb, pb = run_reference_sample(fs, component, 2 * a)
+    return {"spp_a": a, "value_a": pa / sa * 1e-6, "spp_b": 2 * a, "value_b": pb / sb * 1e-6, "unit": "Mpath-samples/s",
+            "note": "same frame at two sample counts: the rate is spp-independent, so the few-spp sample stands for the full-spp render"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import pyoracle as po
-    fs, mode, comp, _ = load_workload(args.workload)
+    fs, mode, comp = load_workload(args.workload)
+    linearity = None
     if not po.ref_available():   # the oracle port is the other CPU implementation of the path
         kind, cores = "port", os.cpu_count()
         osc = po.OracleScene(fs, mode)
@@ -158,6 +234,7 @@ def reference_arm(args):
         def sample():
             return run_reference_sample(fs, comp, spp)
         desc = f"{comp} (oracle/_ref, unmodified reference sources, 16 render threads) on the full {fs.width}x{fs.height} frame at {spp} spp, depth {fs.depth}"
+        linearity = reference_linearity(fs, comp, spp)
     for _ in range(args.warmup):
         sample()
     secs, paths = 0.0, 0
@@ -169,7 +246,7 @@ def reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "sample": desc},
-            "cpu_baseline": {"value": value, "unit": "Mpath-samples/s", "cores": cores, "kind": kind, "sample": desc},
+            "cpu_baseline": {"value": value, "unit": "Mpath-samples/s", "cores": cores, "kind": kind, "sample": desc, "linearity": linearity},
             "e2e": {"value": value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -179,6 +256,79 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 def scene_bytes(fs):
     return int(sum(getattr(fs, n).nbytes for n in fs._ARRAYS))
+
+
+PLUGIN_COMPONENT = {0: "CudaRayCast", 1: "CudaSimplePathTracer", 2: "CudaAccPathTracer"}
+
+
+def plugin_e2e(fs, mode, seed, steps, n_devices, device0, want_frame=False):
+    """Wall time around RenderComponent::exec of the registered CUDA plugin, hosted by nr_headless (the reference's own
+    ComponentFactory / Screen from libNRServer.so).  One warm-up exec (context creation, buffer allocation), then `steps` timed ones.
+    Returns (seconds per exec, info, frame or None); raises when the harness or the plugin is not built."""
+    import numpy as np
+    import tempfile
+    from nrenderer_b200 import build
+    ref_dir = os.path.join(REPO, "oracle", "_ref")
+    exe, so = os.path.join(ref_dir, "nr_headless"), build.plugin_path(mode)
+    if not (os.path.exists(exe) and os.path.exists(so)):
+        raise RuntimeError("nr_headless / plugin adapter not built (python __graft_entry__.py where /root/reference is mounted)")
+    with tempfile.TemporaryDirectory() as td:
+        sp, out = os.path.join(td, "scene.nrsc"), os.path.join(td, "frame.f32")
+        fs.save(sp)
+        env = dict(os.environ, NRCU_SEED=str(seed), NRCU_DEVICE=str(device0))
+        env["LD_LIBRARY_PATH"] = ref_dir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+        if n_devices > 1:
+            env["NRCU_DEVICES"] = str(n_devices)
+        cmd = [exe, "--flat", sp, "--plugin", so, "--component", PLUGIN_COMPONENT[mode], "--warmup", "1", "--repeat", str(steps)]
+        if want_frame:
+            cmd += ["--out", out]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1800)
+        if r.returncode != 0:
+            raise RuntimeError("nr_headless failed: " + r.stderr[-800:])
+        info = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        if info.get("errors"):
+            raise RuntimeError("plugin reported: " + info.get("last_error", ""))
+        frame = np.fromfile(out, np.float32).reshape(info["height"], info["width"], 4) if want_frame else None
+    return info["seconds_mean"], info, frame
+
+
+def measure_workload(ctx, name, steps, seed, flush, spp_override=None):
+    """One of the other BASELINE configs on this GPU: device-timed (CUDA events), scene resident, L2 flushed between steps."""
+    import torch
+    fs, mode, comp = load_workload(name, spp_override)
+    w, h, spp = fs.width, fs.height, fs.samples_per_pixel
+    ctx.upload(fs, mode)
+    out = {"mode": ["RayCast", "SimplePathTracer", "AccPathTracer"][mode], "width": w, "height": h, "spp": spp, "depth": fs.depth, "steps": steps}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if mode == 0:    # RayCast: one deterministic pass; nrcu_render includes the D2H of the frame, the kernel time is in the stats
+        import numpy as np
+        host = np.empty((h, w, 4), np.float32)
+        ctx.render(out=host)
+        ms, rays = 0.0, 0
+        for _ in range(steps):
+            flush.fill_(1)
+            _, st = ctx.render(out=host)
+            ms += st["ms_total"]; rays += st["rays"]
+        out.update({"ms_per_step": ms / steps, "value": w * h * steps / (ms * 1e-3) * 1e-6, "unit": "Mpath-samples/s (1 path = 1 pixel: primary + shadow ray)",
+                    "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / (w * h * steps), "timed": "k_raycast (CUDA events inside nrcu_render)"})
+        return out
+    accum = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    ctx.render_accumulate(accum.data_ptr(), s0=0, s1=min(spp, 64), seed=seed, want_stats=False)   # warm-up: allocations
+    torch.cuda.synchronize()
+    rays = paths = 0
+    ev0.record()
+    for _ in range(steps):
+        flush.fill_(1)
+        accum.zero_()
+        st = ctx.render_accumulate(accum.data_ptr(), seed=seed, want_stats=True)
+        rays += st["rays"]; paths += st["paths"]
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    out.update({"ms_per_step": ms / steps, "value": paths / (ms * 1e-3) * 1e-6, "unit": "Mpath-samples/s", "mrays_per_s": rays / (ms * 1e-3) * 1e-6,
+                "rays_per_path": rays / max(paths, 1), "scheduler": {1: "waves", 2: "regen"}.get(st["scheduler"], "?")})
+    del accum
+    return out
 
 
 def cuda_arm(args):
@@ -200,7 +350,7 @@ def cuda_arm(args):
     else:
         torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    fs, mode, comp, bytes_per_ray = load_workload(args.workload, args.spp)
+    fs, mode, comp = load_workload(args.workload, args.spp)
     w, h, spp = fs.width, fs.height, fs.samples_per_pixel
 
     ctx = Context(local)
@@ -208,7 +358,6 @@ def cuda_arm(args):
     ctx.upload(fs, mode)
     accum = torch.zeros(h, w, 4, dtype=torch.float32, device=dev)
     rgba = torch.empty(h, w, 4, dtype=torch.float32, device=dev)
-    host_rgba = torch.empty(h, w, 4, dtype=torch.float32, pin_memory=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -221,11 +370,13 @@ def cuda_arm(args):
     def resolve(acc, out):
         ctx.resolve(acc.data_ptr(), out.data_ptr())
 
+    coll_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
     def step(want_stats):
         flush.fill_(1)
         return multigpu.render_frame(
             lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=want_stats),
-            resolve, accum, rgba, spp, rank, world)
+            resolve, accum, rgba, spp, rank, world, collective_events=coll_ev if want_stats else None)
 
     for _ in range(args.warmup):
         step(False)
@@ -234,134 +385,173 @@ def cuda_arm(args):
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"rays": 0, "paths": 0, "kernel_launches": 0, "ms_trace": 0.0, "ms_shade": 0.0, "ms_stage2": 0.0}
+    agg = {"rays": 0, "paths": 0, "kernel_launches": 0, "ms_trace": 0.0, "ms_shade": 0.0, "ms_stage2": 0.0, "iterations": 0}
+    sched, coll_ms = 0, 0.0
     ev0.record()
     for _ in range(args.steps):
         st = step(True)
         for k in agg:
             agg[k] += st[k] if st else 0
+        sched = st["scheduler"] if st else sched
+        if world > 1:
+            coll_ev[1].synchronize()
+            coll_ms += coll_ev[0].elapsed_time(coll_ev[1])
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_stage2"]], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_stage2"], coll_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([agg["rays"], agg["paths"], agg["kernel_launches"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, ms_trace, ms_shade, ms_stage2 = t.tolist()
-    ms_closest = ms_trace               # k_raygen (fused stage 1) + k_big_balanced + k_trace2; ms_stage2 = the k_trace2 part
+    ms, ms_trace, ms_shade, ms_stage2, coll_ms = t.tolist()
     rays, paths, launches = sums.tolist()
     launches += args.steps * (1 if rank == 0 else 0)   # resolve
     value = paths / (ms * 1e-3) * 1e-6
+    scheduler = {1: "waves", 2: "regen"}.get(sched, "?")
 
-    # ---- end to end: Scene arrays from host memory in, RGBA frame in host memory out ------------------
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h2d, d2h = scene_bytes(fs), w * h * 16
+    # ---- cfg5 (4K, 4096 spp: the configuration the north star's scaling claim is quoted on), 3 steps at every N --------------------
+    cfg5 = None
+    if args.workload == DEFAULT_WORKLOAD and not args.no_other_workloads:
+        f5, m5, _ = load_workload(CFG5)
+        ctx.upload(f5, m5)
+        acc5 = torch.zeros(f5.height, f5.width, 4, dtype=torch.float32, device=dev)
+        rgba5 = torch.empty_like(acc5)
 
-    host_np = host_rgba.numpy()
+        def step5(stats):
+            flush.fill_(1)
+            return multigpu.render_frame(lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=stats),
+                                         resolve, acc5, rgba5, f5.samples_per_pixel, rank, world)
+        step5(False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r5 = p5 = 0
+        e0.record()
+        for _ in range(3):
+            st = step5(True)
+            r5 += st["rays"] if st else 0; p5 += st["paths"] if st else 0
+        e1.record()
+        barrier()
+        t5 = torch.tensor([e0.elapsed_time(e1), r5, p5], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = t5.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t5, op=dist.ReduceOp.SUM)
+            t5[0] = mx[0]
+        ms5, r5, p5 = t5.tolist()
+        cfg5 = {"workload": CFG5, "width": f5.width, "height": f5.height, "spp": f5.samples_per_pixel, "depth": f5.depth, "steps": 3, "n_gpus": world,
+                "ms_per_step": ms5 / 3, "value": p5 / (ms5 * 1e-3) * 1e-6, "unit": "Mpath-samples/s", "mrays_per_s": r5 / (ms5 * 1e-3) * 1e-6,
+                "rays_per_path": r5 / max(p5, 1), "partition": f"sample slices x{world}, NCCL reduce of the 133 MB linear frame" if world > 1 else "single GPU",
+                "note": "environment-map lighting is an extension (the reference renders this scene black, SURVEY A18); synthetic 64x32 lat-long map"}
+        del acc5, rgba5
+        ctx.upload(fs, mode)
 
-    def e2e_step():
-        ctx.upload(fs, mode)                                    # H2D of the scene + device-side flattening + BVH build
-        if world == 1:                                          # exactly the plugin adapter's call sequence (NRCudaAdapter.cpp):
-            ctx.render(seed=args.seed, out=host_np)             # nrcu_upload_scene + nrcu_render into HOST memory (pinned)
-            return
-        multigpu.render_frame(
-            lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=False),
-            resolve, accum, rgba, spp, rank, world)
-        if rank == 0:
-            host_rgba.copy_(rgba, non_blocking=True)            # D2H of what Screen::set receives
-        torch.cuda.synchronize()
-
-    e2e_step()
-    barrier()
-    sampler2 = ClockSampler(local) if rank == 0 else None
-    if sampler2:
-        sampler2.start()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_clocks = sampler2.stop() if sampler2 else None
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = (w * h * spp * e2e_steps) / te.item() * 1e-6
-
-    waves = -(-spp // max(1, (64 << 20) // (w * h))) if world == 1 else None   # 2 concurrent waves of 64 Mi path slots
-    closest_hit_launches = args.steps * waves * (1 + (fs.depth - 1) + fs.depth) if waves else 0
-    if rank == 0:
-        peak, peak_src = peaks()
-        achieved = rays * bytes_per_ray / (ms_closest * 1e-3) * 1e-9 if ms_closest > 0 else None
-        line = {
-            "metric": "Mpath-samples/s", "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "scene": "bunny_5k_faces.obj + path_tracing_cornel.scn (reference importers)" if "bunny" in args.workload else args.workload,
-                       "width": w, "height": h, "spp": spp, "depth": fs.depth, "partition": f"sample slices x{world}, NCCL reduce" if world > 1 else "single GPU",
-                       "l2": "256 MB flush buffer written between steps; per-wave ray/path state (~7 GB) exceeds the 126 MB L2",
-                       "glass_mode": "stochastic", "seed": args.seed},
-            "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / max(paths, 1),
-            "kernel_ms": {"closest_hit": ms_closest / args.steps, "of_which_bvh_traversal": ms_stage2 / args.steps, "shade": ms_shade / args.steps},
-            "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "clocks": e2e_clocks},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                         "traffic": profile_summary().get("closest_hit", {}).get("dram_bytes_per_launch"),
-                         "algorithmic_bytes_per_launch": (rays * bytes_per_ray / max(closest_hit_launches, 1)) if closest_hit_launches else None,
-                         "kernel": "closest hit = k_raygen (camera rays + fused stage 1) + k_big_balanced + k_trace2", "algorithmic_bytes_per_ray": bytes_per_ray,
-                         "peak_source": peak_src, "share_of_step": ms_closest / ms if ms else None, "concurrent_waves": 2,
-                         "note": "two waves run side by side on two streams, so kernel times (summed per launch) overlap and their share of the step can exceed 1; "
-                                 "algorithmic bytes are those of the REFERENCE's traversal (SURVEY 8d); the scene is L1/L2 resident, so the "
-                                 "fraction can exceed 1 and the binding limit is issue slots x warp efficiency: see 'issue' (from the committed "
-                                 "ncu launch list, profiles/) and DESIGN.md section 5",
-                         "issue": issue_roofline(args.workload, paths, ms, clocks, world)},
-            # the same kernels against the HBM roofline with THIS implementation's algorithmic bytes per ray
-            "roofline_kernels": [
-                {"kernel": "k_shade", "bound": "hbm", "algorithmic_bytes_per_ray": 88.0, "achieved": rays * 88.0 / (ms_shade * 1e-3) * 1e-9 if ms_shade > 0 else None,
-                 "peak": peak, "unit": "GB/s", "frac": rays * 88.0 / (ms_shade * 1e-3) * 1e-9 / peak if ms_shade > 0 else None,
-                 "traffic": profile_summary().get("kernels", {}).get("k_shade<1, 0>", {}).get("dram_bytes_per_launch")},
-                {"kernel": "k_raygen + k_big_balanced (stage 1)", "bound": "issue", "algorithmic_bytes_per_ray": 36.0,
-                 "achieved": rays * 36.0 / ((ms_trace - ms_stage2) * 1e-3) * 1e-9 if ms_trace > ms_stage2 else None, "peak": peak, "unit": "GB/s",
-                 "frac": rays * 36.0 / ((ms_trace - ms_stage2) * 1e-3) * 1e-9 / peak if ms_trace > ms_stage2 else None,
-                 "traffic": profile_summary().get("kernels", {}).get("k_big_balanced<1>", {}).get("dram_bytes_per_launch"),
-                 "issue_active_pct": profile_summary().get("kernels", {}).get("k_big_balanced<1>", {}).get("issue_active_pct")},
-            ],
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
+    # ---- the other BASELINE configs on one GPU ----------------------------------------------------------------------------------
+    others = None
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_other_workloads:
+        others = {}
+        for name in OTHER_WORKLOADS:
             try:
-                from oracle import pyoracle as po
-                if po.ref_available():
-                    spp_ref, _ = calibrated_reference_spp(fs, comp, args.cpu_baseline_seconds)
-                    sec, p = run_reference_sample(fs, comp, spp_ref)
-                    line["cpu_baseline"] = {"value": p / sec * 1e-6, "unit": "Mpath-samples/s", "cores": min(16, os.cpu_count() or 1), "kind": "reference",
-                                            "sample": f"{comp} from oracle/_ref (unmodified reference sources, 16 render threads hard-coded, host has {os.cpu_count()} cpus) "
-                                                      f"on the full {w}x{h} frame at {spp_ref} spp, depth {fs.depth}: {sec:.2f} s"}
-                else:
-                    line["cpu_baseline"] = {"value": None, "unit": "Mpath-samples/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
-            except Exception as ex:   # the GPU number stands on its own
-                line["cpu_baseline"] = {"value": None, "unit": "Mpath-samples/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        print(json.dumps(line), flush=True)
-        os.dup2(2, 1)
+                others[name] = measure_workload(ctx, name, 1 if "4096" in name else 2, args.seed, flush)
+            except Exception as ex:
+                others[name] = {"failed": str(ex)[:300]}
+        ctx.upload(fs, mode)
+
+    frame_nccl = rgba.cpu().numpy() if rank == 0 else None   # the frame of the last timed step (NCCL path at N > 1)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        ctx.close()
+        return        # rank 0 goes on alone: the plugin opens its own contexts on all N devices
+
+    # ---- end to end through the drop-in: RenderComponent::exec of the registered plugin, NRCU_DEVICES = N ----------------------------
+    del accum, rgba
+    ctx.close()
+    torch.cuda.empty_cache()
+    e2e_steps = max(5, min(args.steps, args.e2e_steps))
+    h2d, d2h = scene_bytes(fs) * world, w * h * 16
+    sampler2 = ClockSampler(local)
+    sampler2.start()
+    e2e = {"value": None, "unit": "Mpath-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps}
+    try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
+        sec, info, frame = plugin_e2e(fs, mode, args.seed, e2e_steps, world, local, want_frame=True)
+        e2e.update({"value": w * h * spp / sec * 1e-6, "seconds_per_exec": sec, "seconds_best": info["seconds"],
+                    "path": "nr_headless -> ComponentFactory::createComponent<RenderComponent> -> exec() -> NRCuda::Adapter::render (flatten, nrcu_upload_scene, "
+                            + ("nrcu_render_multi over %d devices: peer-read reduce fused with the resolve" % world if world > 1 else "nrcu_render")
+                            + ", pageable RGBA buffer) -> Screen::set; wall clock around exec(), through RenderComponent::exec",
+                    "plugin_log": info.get("last_log"),
+                    "max_abs_diff_vs_device_timed_frame": float(np.abs(np.clip(frame_nccl, 0, 1) - frame).max())})
+    except Exception as ex:
+        e2e["unavailable"] = str(ex)[:400]
+    e2e["clocks"] = sampler2.stop()
+
+    roof, roof_hbm = rooflines(args.workload, paths, rays, ms, clocks, world, scheduler)
+    line = {
+        "metric": "Mpath-samples/s", "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "scene": "bunny_5k_faces.obj + path_tracing_cornel.scn (reference importers)" if "bunny" in args.workload else args.workload,
+                   "width": w, "height": h, "spp": spp, "depth": fs.depth, "partition": f"sample slices x{world}, NCCL reduce" if world > 1 else "single GPU",
+                   "l2": "256 MB flush buffer written between steps; the path state of a step (~5 GB) exceeds the 126 MB L2",
+                   "glass_mode": "stochastic", "seed": args.seed, "scheduler": scheduler},
+        "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / max(paths, 1),
+        "kernel_ms": {"closest_hit": ms_trace / args.steps, "of_which_bvh_traversal": ms_stage2 / args.steps, "shade": ms_shade / args.steps,
+                      "note": "per-kernel CUDA-event spans summed over the concurrent streams: they overlap, so they add up to more than ms_per_step"},
+        "iterations_per_step": agg["iterations"] / args.steps,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "roofline_hbm": roof_hbm,
+        "clocks": clocks,
+    }
+    if world > 1:
+        line["collective"] = {"what": "zero-copy NCCL reduce(sum, fp32) of the linear frame to rank 0 + k_resolve", "ms_per_step": coll_ms / args.steps,
+                              "bytes": w * h * 16}
+    ref_bpr = REFERENCE_TRAVERSAL_BYTES_PER_RAY.get(WORKLOADS[args.workload][0])
+    if ref_bpr and ms_trace > 0:
+        line["reference_traversal_equivalent"] = {"gbytes_per_s": rays * ref_bpr / (ms * 1e-3) * 1e-9, "bytes_per_ray": ref_bpr,
+                                                  "note": "NOT a roofline: what the reference's never-pruned binary tree would have read per second (SURVEY 8d)"}
+    if cfg5:
+        line["cfg5"] = cfg5
+    if others is not None:
+        line["other_workloads"] = others
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import pyoracle as po
+            if po.ref_available():
+                spp_ref, _ = calibrated_reference_spp(fs, comp, args.cpu_baseline_seconds)
+                sec, p = run_reference_sample(fs, comp, spp_ref)
+                line["cpu_baseline"] = {"value": p / sec * 1e-6, "unit": "Mpath-samples/s", "cores": min(16, os.cpu_count() or 1), "kind": "reference",
+                                        "sample": f"{comp} from oracle/_ref (unmodified reference sources, 16 render threads hard-coded, host has {os.cpu_count()} cpus) "
+                                                  f"on the full {w}x{h} frame at {spp_ref} spp, depth {fs.depth}: {sec:.2f} s",
+                                        "linearity": reference_linearity(fs, comp, max(2, spp_ref // 2))}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "Mpath-samples/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        except Exception as ex:   # the GPU number stands on its own
+            line["cpu_baseline"] = {"value": None, "unit": "Mpath-samples/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=None, help="override samples per pixel (parity/debug only; the headline uses the workload's)")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the plugin end-to-end leg (tuning / profiling runs)")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip cfg1/cfg2/cfg4/cfg5 (tuning runs)")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-seconds", type=float, default=8.0)
     args = ap.parse_args()
     if args.impl == "reference":

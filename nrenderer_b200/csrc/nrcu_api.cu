@@ -71,7 +71,7 @@ struct Sub { void* p = nullptr; template <typename T> T* as() const { return rei
 
 #define NRCU_MAX_WAVES 4
 #ifndef NRCU_SCHED_DEFAULT
-#define NRCU_SCHED_DEFAULT NRCU_SCHED_REGEN
+#define NRCU_SCHED_DEFAULT NRCU_SCHED_WAVES
 #endif
 struct nrcu_ctx {
     int device = 0;
@@ -592,7 +592,9 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     NP = std::max(1, std::min<int>(NP, (int)((s1 - s0 + k - 1) / k)));   // also with no samples at all: one (idle) wave set
     const unsigned share = (unsigned)NP;
     uint32_t slots = k * npix;
-    uint32_t capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
+    // branching glass mode: room for 4 rays per path slot, and never less than 4 Mi entries (small frames at many bounces)
+    auto branch_capacity = [](uint32_t sl) { return (uint32_t)std::min<uint64_t>(0x7fffffffull, std::max<uint64_t>((uint64_t)sl * 4, 4ull << 20)); };
+    uint32_t capacity = glass_branch ? branch_capacity(slots) : slots;
     int rc;
     for (;;) {   // the default wave size assumes a B200's 180 GB; on a fuller or smaller device shrink the waves instead of failing
         rc = NRCU_OK;
@@ -608,7 +610,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         }
         k = std::max<uint32_t>(1, k / 2);
         slots = k * npix;
-        capacity = glass_branch ? (uint32_t)std::min<uint64_t>(0x7fffffffull, (uint64_t)slots * 4) : slots;
+        capacity = glass_branch ? branch_capacity(slots) : slots;
     }
     cudaStream_t S[NRCU_MAX_WAVES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
     if (NP > 1) {
@@ -826,7 +828,8 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         NP = std::max(1, std::min<int>(NP, (int)K));
     }
     const uint32_t samples_per_lane = (n_samples + K - 1) / K;
-    const uint64_t t_max = (uint64_t)samples_per_lane * ds.depth;   // a lane renders its samples one after the other, <= depth rays each
+    uint64_t t_max = (uint64_t)samples_per_lane * ds.depth;   // a lane renders its samples one after the other, <= depth rays each
+    { static uint32_t dbg = env_u32("NRCU_REGEN_MAX_ITERS", 0); if (dbg) t_max = std::min<uint64_t>(t_max, dbg); }   // steady-state measurements only: truncates the frame
     if (!ctx->h_flags) CTX_CUDA(cudaHostAlloc(&ctx->h_flags, sizeof(uint32_t) * NRCU_MAX_WAVES * NRCU_REGEN_RING * NRCU_REGEN_FLAGS * NRCU_REGEN_FLAG_STRIDE, cudaHostAllocDefault));
     cudaStream_t S[NRCU_MAX_WAVES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
     for (int p = 1; p < NP; p++) {

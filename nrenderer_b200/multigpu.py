@@ -33,18 +33,30 @@ def all_slices(spp: int, world: int):
 def render_frame(render_slice: Callable[[torch.Tensor, int, int], Optional[dict]],
                  resolve: Callable[[torch.Tensor, torch.Tensor], None],
                  accum: torch.Tensor, rgba: Optional[torch.Tensor], spp: int,
-                 rank: int = 0, world: int = 1, group=None, root: int = 0) -> Optional[dict]:
+                 rank: int = 0, world: int = 1, group=None, root: int = 0, collective_events=None) -> Optional[dict]:
     """Render this rank's sample slice into `accum` (zeroed here), reduce to `root`, resolve there.
 
     render_slice(accum, s0, s1) adds the linear sums of samples [s0, s1) to accum[..., :3] and the
     sample count to accum[..., 3]; an empty slice (more ranks than samples) must add nothing.
     resolve(accum, rgba) writes sqrt(accum.rgb / accum.a), alpha 1.  Returns render_slice's stats.
+
+    STREAM CONTRACT: `accum.zero_()` and the reduce are issued on torch's CURRENT stream, so render_slice and resolve
+    must run on that stream too - on a GPU: `ctx.set_stream(torch.cuda.current_stream().cuda_stream)` before the
+    first frame (bench.py does) - or synchronise themselves (`ctx.synchronize()`) before returning.  A context left
+    on its own non-blocking stream would race with the zeroing and with the collective.
+
+    collective_events: optional (start, end) torch.cuda.Event pair recorded around the exchange step (reduce + resolve),
+    so that the caller can report the collective's own device time.
     """
     s0, s1 = sample_slice(spp, rank, world)
     accum.zero_()
     stats = render_slice(accum, s0, s1) if s1 > s0 else None
+    if collective_events is not None:
+        collective_events[0].record()
     if world > 1:
         dist.reduce(accum, dst=root, op=dist.ReduceOp.SUM, group=group)
     if rank == root and rgba is not None:
         resolve(accum, rgba)
+    if collective_events is not None:
+        collective_events[1].record()
     return stats

@@ -567,15 +567,54 @@ void nro_render_raycast(const nro_scene* s, float* rgba) {
 #define PT_PI 3.1415926535898f /* acc_path_tracing/include/shaders/Shader.hpp:17 */
 
 /* closestHitLight, AccPathTracer.cpp:101-112 == SimplePathTracer.cpp:131-142 */
-static float closest_light(const nro_scene* s, ray_t r, v3* radiance) {
+static float closest_light_which(const nro_scene* s, ray_t r, v3* radiance, int* which) {
     float closest = INFINITY;
     *radiance = V(0, 0, 0);
+    if (which) *which = -1;
     for (uint32_t i = 0; i < s->n_area; i++) {
         v3 u = ld3(s->area_u + 3 * i), v = ld3(s->area_v + 3 * i);
         hit_t h = x_quad(r, vcross(u, v), ld3(s->area_position + 3 * i), u, v, -1, (float)0.000001, closest, 0);
-        if (h.hit && closest > h.t) { closest = h.t; *radiance = ld3(s->area_radiance + 3 * i); }
+        if (h.hit && closest > h.t) { closest = h.t; *radiance = ld3(s->area_radiance + 3 * i); if (which) *which = (int)i; }
     }
     return closest;
+}
+static float closest_light(const nro_scene* s, ray_t r, v3* radiance) { return closest_light_which(s, r, radiance, NULL); }
+
+/* ---- next-event estimation: an EXTENSION of this backend (NRCU_FLAG_NEE), not in the reference, whose area lights are
+ * only hit by chance (SimplePathTracer.cpp:144-177 has no light sampling).  Restated here independently of the CUDA
+ * sources so that the kernels are checked against something other than themselves: at a Lambertian vertex one point of
+ * one area light is sampled uniformly (light by e1, position by (frac(e1 * n), e2)); the shadow ray carries
+ * f * Le / (p_light + p_hemisphere) (balance heuristic, solid-angle pdfs), and a hemisphere sample that then finds a
+ * light is weighted by p_hemisphere / (p_hemisphere + p_light).  Visibility uses the same closest-hit / closest-light
+ * queries as any other ray. */
+#define PDF_HEMISPHERE (1.0f / (2.0f * PT_PI))
+static int nee_sample(const nro_scene* s, v3 albedo, v3 hit_point, v3 normal, v3 thr, float e1, float e2, ray_t* shadow, v3* contrib, int* light) {
+    if (s->n_area == 0) return 0;
+    float fl = e1 * (float)s->n_area;
+    int li = (int)fl; if (li > (int)s->n_area - 1) li = (int)s->n_area - 1;
+    float a = fl - (float)li;
+    v3 u = ld3(s->area_u + 3 * li), v = ld3(s->area_v + 3 * li), nl = vcross(u, v);
+    v3 y = vadd(vadd(ld3(s->area_position + 3 * li), vscale(u, a)), vscale(v, e2));
+    v3 wv = vsub(y, hit_point);
+    float r2 = vdot(wv, wv);
+    if (!(r2 > 0.f)) return 0;
+    v3 w = vscale(wv, 1.0f / sqrtf(r2));
+    float cos_s = vdot(normal, w);
+    float cl = fabsf(vdot(nl, w));
+    if (!(cos_s > 0.f) || !(cl > 0.f)) return 0;
+    float p_l = r2 / (cl * (float)s->n_area);
+    v3 f = vscale(vdivs(albedo, PT_PI), cos_s);
+    *contrib = vscale(vmul(vmul(thr, f), ld3(s->area_radiance + 3 * li)), 1.0f / (p_l + PDF_HEMISPHERE));
+    if (contrib->x == 0.f && contrib->y == 0.f && contrib->z == 0.f) return 0;
+    shadow->o = hit_point; shadow->d = w; *light = li;
+    return 1;
+}
+static float mis_light_weight(const nro_scene* s, ray_t ray, int which, float tl) {
+    v3 nl = vcross(ld3(s->area_u + 3 * which), ld3(s->area_v + 3 * which));
+    float cl = fabsf(vdot(nl, ray.d));
+    if (!(cl > 0.f)) return 1.f;
+    float p_l = tl * tl * vdot(ray.d, ray.d) / (cl * (float)s->n_area);
+    return PDF_HEMISPHERE / (PDF_HEMISPHERE + p_l);
 }
 
 /* Camera::shoot, acc_path_tracing/include/Camera.hpp:51-63, with UniformInSquare jitter
@@ -788,20 +827,25 @@ static v3 env_lookup(const nro_scene* s, v3 d) {
  * for the glass two-branch case.  branch_bits identifies the branch for the RNG. */
 typedef struct { ray_t ray; v3 thr; uint32_t depth; uint32_t branch; } work_t;
 
-static v3 pt_trace(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t sample, ray_t ray0, int glass_mode, uint64_t* rays) {
+static v3 pt_trace(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t sample, ray_t ray0, int glass_mode, int nee, uint64_t* rays) {
     v3 L = V(0, 0, 0);
     work_t stack[256];
     int sp = 0;
+    if (s->n_area == 0) nee = 0;
     stack[sp].ray = ray0; stack[sp].thr = V(1, 1, 1); stack[sp].depth = 0; stack[sp].branch = 0; sp++;
     while (sp > 0) {
         work_t wk = stack[--sp];
         ray_t ray = wk.ray; v3 thr = wk.thr; uint32_t branch = wk.branch;
+        int mis = 0;   /* the previous vertex also sampled the lights directly: a light found now gets the balance-heuristic weight */
         for (uint32_t d = wk.depth;; d++) {
             if (d == s->depth) { L = vadd(L, vmul(thr, s->ambient)); break; }
             (*rays)++;
             hit_t h = closest_hit(s, ray, NULL, NULL);
             v3 radiance;
-            float tl = closest_light(s, ray, &radiance);
+            int which = -1;
+            float tl = closest_light_which(s, ray, &radiance, &which);
+            const int weigh_light = mis;
+            mis = 0;
             if (h.hit && h.t < tl) {
                 const nrcu_material* m = &s->materials[h.material];
                 uint32_t type = s->mode == NRCU_MODE_ACC ? m->type : 0;
@@ -836,10 +880,23 @@ static v3 pt_trace(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t s
                 } else {
                     /* type 0; any other type falls off the end of the reference's trace() (UB) - treated as Lambertian */
                     v3 albedo = ld3(m->diffuse_color);
+                    if (nee && d + 1 < s->depth) {   /* only where the continuation is really traced (AccPathTracer.cpp:122) */
+                        ray_t shadow; v3 contrib; int li;
+                        if (nee_sample(s, albedo, h.p, h.n, thr, u01(rn[2]), u01(rn[3]), &shadow, &contrib, &li)) {
+                            (*rays)++;
+                            hit_t sh = closest_hit(s, shadow, NULL, NULL);
+                            v3 srad; int swhich;
+                            float stl = closest_light_which(s, shadow, &srad, &swhich);
+                            if (swhich == li && !(sh.hit && sh.t < stl)) L = vadd(L, contrib);
+                        }
+                        mis = 1;
+                    }
                     v3 f; ray = shade_lambertian(albedo, h.p, h.n, u01(rn[0]), u01(rn[1]), &f); thr = vmul(thr, f);
                 }
             } else if (tl != INFINITY) {
-                L = vadd(L, vmul(thr, radiance)); break;
+                v3 add = vmul(thr, radiance);
+                if (nee && weigh_light) add = vscale(add, mis_light_weight(s, ray, which, tl));
+                L = vadd(L, add); break;
             } else {
                 if (s->env_rgba && s->mode == NRCU_MODE_ACC) L = vadd(L, vmul(thr, env_lookup(s, ray.d)));
                 break;
@@ -849,7 +906,7 @@ static v3 pt_trace(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t s
     return L;
 }
 
-typedef struct { const nro_scene* s; uint64_t seed; uint32_t s0, s1; int glass_mode; const uint32_t* pixels; float* accum4;
+typedef struct { const nro_scene* s; uint64_t seed; uint32_t s0, s1; int glass_mode; int nee; const uint32_t* pixels; float* accum4;
                  uint64_t rays[PF_MAX_THREADS]; } pt_ctx;
 static void pt_body(int64_t b, int64_t e, void* c_, int tid) {
     pt_ctx* c = (pt_ctx*)c_;
@@ -860,18 +917,26 @@ static void pt_body(int64_t b, int64_t e, void* c_, int tid) {
         v3 sum = V(0, 0, 0);
         for (uint32_t k = c->s0; k < c->s1; k++) {
             ray_t r = camera_ray(s, c->seed, p, k);
-            sum = vadd(sum, pt_trace(s, c->seed, p, k, r, c->glass_mode, &rays));
+            sum = vadd(sum, pt_trace(s, c->seed, p, k, r, c->glass_mode, c->nee, &rays));
         }
         float* a = c->accum4 + 4 * q;
         a[0] += sum.x; a[1] += sum.y; a[2] += sum.z; a[3] += (float)(c->s1 - c->s0);
     }
     c->rays[tid] += rays;
 }
+void nro_render_pt_pixels_flags(const nro_scene* s, uint64_t seed, uint32_t s0, uint32_t s1, int glass_mode, uint32_t flags,
+                                const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out);
 void nro_render_pt_pixels(const nro_scene* s, uint64_t seed, uint32_t s0, uint32_t s1, int glass_mode,
                           const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out) {
+    nro_render_pt_pixels_flags(s, seed, s0, s1, glass_mode, 0u, pixels, n_pixels, accum4, rays_out);
+}
+/* flags: nrcu_render_flags (NRCU_FLAG_NEE = the next-event-estimation extension; 0 = the reference's estimator) */
+void nro_render_pt_pixels_flags(const nro_scene* s, uint64_t seed, uint32_t s0, uint32_t s1, int glass_mode, uint32_t flags,
+                                const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out) {
     if (s1 == 0 && s0 == 0) s1 = s->spp;
     pt_ctx* c = (pt_ctx*)calloc(1, sizeof(pt_ctx));
-    c->s = s; c->seed = seed; c->s0 = s0; c->s1 = s1; c->glass_mode = glass_mode; c->pixels = pixels; c->accum4 = accum4;
+    c->s = s; c->seed = seed; c->s0 = s0; c->s1 = s1; c->glass_mode = glass_mode; c->nee = (flags & NRCU_FLAG_NEE) != 0; c->pixels = pixels; c->accum4 = accum4;
+    if (!pixels) n_pixels = s->width * s->height;
     parallel_for(n_pixels, 64, pt_body, c);
     uint64_t total = 0;
     for (int i = 0; i < PF_MAX_THREADS; i++) total += c->rays[i];

@@ -55,6 +55,10 @@ void nro_render_pt(const nro_scene* s, uint64_t seed, uint32_t s0, uint32_t s1, 
 /* Same for a list of pixels only (pixel index = row_from_top*w + col), for sparse checks at full size. */
 void nro_render_pt_pixels(const nro_scene* s, uint64_t seed, uint32_t s0, uint32_t s1, int glass_mode,
                           const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays);
+/* The same with nrcu_render_flags (NRCU_FLAG_NEE: next-event estimation, an extension of this backend restated here
+ * independently of the CUDA sources); pixels == NULL renders the whole frame. */
+void nro_render_pt_pixels_flags(const nro_scene* s, uint64_t seed, uint32_t s0, uint32_t s1, int glass_mode, uint32_t flags,
+                                const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out);
 /* rgba = (sqrt(sum/count), 1)  (AccPathTracer.cpp:14-16, 32-34) */
 void nro_resolve(const float* accum, uint64_t n_pixels, float* rgba);
 

@@ -44,6 +44,7 @@ def lib():
         L.nro_render_raycast.argtypes = [C.c_void_p, C.c_void_p]
         L.nro_render_pt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         L.nro_render_pt_pixels.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.nro_render_pt_pixels_flags.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.nro_resolve.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.nro_camera_ray.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
         L.nro_philox4x32.argtypes = [C.c_void_p] * 3
@@ -99,16 +100,16 @@ class OracleScene:
         lib().nro_render_raycast(self._h, out.ctypes.data)
         return out
 
-    def render_pt_accum(self, seed=0, s0=0, s1=0, glass_mode=0, pixels=None):
-        """Linear sums (rgb) + sample count (a). Returns (accum, rays)."""
+    def render_pt_accum(self, seed=0, s0=0, s1=0, glass_mode=0, pixels=None, flags=0):
+        """Linear sums (rgb) + sample count (a). Returns (accum, rays).  flags: nrcu_render_flags (1 = NEE extension)."""
         rays = C.c_uint64(0)
         if pixels is None:
             acc = np.zeros((self.height, self.width, 4), np.float32)
-            lib().nro_render_pt(self._h, seed, s0, s1, glass_mode, acc.ctypes.data, C.addressof(rays))
+            lib().nro_render_pt_pixels_flags(self._h, seed, s0, s1, glass_mode, flags, None, 0, acc.ctypes.data, C.addressof(rays))
         else:
             pixels = np.ascontiguousarray(pixels, np.uint32)
             acc = np.zeros((len(pixels), 4), np.float32)
-            lib().nro_render_pt_pixels(self._h, seed, s0, s1, glass_mode, pixels.ctypes.data, len(pixels), acc.ctypes.data, C.addressof(rays))
+            lib().nro_render_pt_pixels_flags(self._h, seed, s0, s1, glass_mode, flags, pixels.ctypes.data, len(pixels), acc.ctypes.data, C.addressof(rays))
         return acc, rays.value
 
     def camera_ray(self, seed, pixel, sample):

@@ -62,3 +62,12 @@ def env_texture(fs, w=64, h=32, seed=1):
     fs.add_texture(tex)
     fs.ambient_type = 1
     fs.ambient_environment_map = 0
+
+
+def lens_small(fs):
+    fs.cam_aperture = 0.02            # lens radius 0.01 at the default focus distance 0.1
+
+
+def lens_wide(fs):
+    fs.cam_aperture = 6.0             # a visibly defocused view: lens radius 3, focused on the back of the box
+    fs.cam_focus_distance = 900.0

@@ -17,12 +17,26 @@ def test_workloads_cover_the_baseline_configs():
     import bench
     base = json.load(open(os.path.join(REPO, "BASELINE.json")))
     assert bench.DEFAULT_WORKLOAD.startswith("cfg3") and "1920x1080_1024spp" in bench.DEFAULT_WORKLOAD   # the config the target is quoted on
-    for tag in ("cfg2", "cfg3", "cfg4", "cfg5"):
+    for tag in ("cfg1", "cfg2", "cfg3", "cfg4_", "cfg4ii", "cfg4iii", "cfg5"):
         assert any(w.startswith(tag) for w in bench.WORKLOADS), tag
     assert len(base["configs"]) == 5
+    assert set(bench.OTHER_WORKLOADS) | {bench.DEFAULT_WORKLOAD, bench.CFG5} == set(bench.WORKLOADS)   # every config is measured somewhere in the default line
     for name in bench.WORKLOADS:
-        fs, mode, comp, bytes_per_ray = bench.load_workload(name, spp_override=1)
-        assert fs.width * fs.height > 0 and mode in (1, 2) and comp in po.REF_PLUGINS and bytes_per_ray > 0
+        fs, mode, comp = bench.load_workload(name, spp_override=1)
+        assert fs.width * fs.height > 0 and mode in (0, 1, 2) and comp in po.REF_PLUGINS
+    glass, _, _ = bench.load_workload("cfg4ii_acc_glass_1920x1080_4096spp")
+    assert int(glass.material_type_present[int(glass.sphere_material[0]), 0]) == 2            # the sphere is the Glass of env_map_spheres.scn
+    mf, _, _ = bench.load_workload("cfg4iii_acc_microfacet_1920x1080_4096spp")
+    assert int(mf.material_type_present[int(mf.triangle_material[0]), 0]) == 3                # conductors.scn's type 3 -> Microfacet
+
+
+def test_profile_summary_carries_the_hash_of_the_code_it_was_taken_from():
+    sys.path.insert(0, REPO)
+    import bench
+    prof = bench.profile_summary()
+    assert len(bench.csrc_hash()) == 16
+    if prof.get("_file", "").endswith("r2_summary.json"):
+        assert "csrc_sha" in prof and prof["issue"]["warp_inst_per_path_sample"] > 0
 
 
 @pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
@@ -38,6 +52,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("cfg3")
+    lin = d["cpu_baseline"]["linearity"]                    # the CPU rate at two spp values
+    assert lin["spp_b"] == 2 * lin["spp_a"] and lin["value_a"] > 0 and lin["value_b"] > 0
 
 
 def test_cuda_arm_fails_loudly_without_a_device():

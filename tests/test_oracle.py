@@ -29,10 +29,10 @@ def test_raycast_frame_is_bit_identical_to_the_live_reference():
         assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
 
 
-def linear_stats(name, seed):
+def linear_stats(name, seed, spp_slice=128, flags=0):
     ref = np.load(os.path.join(GOLDEN, f"pt_ref_{name}.npz"))
     w, h, depth, mode = int(ref["width"]), int(ref["height"]), int(ref["depth"]), int(ref["mode"])
-    fs = load_scene(str(ref["scene"]), width=w, height=h, samples_per_pixel=1024, depth=depth)
+    fs = load_scene(str(ref["scene"]), width=w, height=h, samples_per_pixel=8 * spp_slice, depth=depth)
     if name == "acc_glass_d6":
         glassify(fs)
     if name == "acc_microfacet_d8":
@@ -40,29 +40,34 @@ def linear_stats(name, seed):
     osc = po.OracleScene(fs, mode)
     slices = []
     for k in range(8):
-        acc, _ = osc.render_pt_accum(seed=seed, s0=128 * k, s1=128 * (k + 1))
+        acc, _ = osc.render_pt_accum(seed=seed, s0=spp_slice * k, s1=spp_slice * (k + 1), flags=flags)
         slices.append(acc[..., :3].astype(np.float64) / acc[..., 3:4])
     slices = np.stack(slices)
     return ref, slices.mean(0), slices.std(0, ddof=1) / np.sqrt(8.0)
 
 
-@pytest.mark.parametrize("name", ["simple_cornell_d4", "acc_cornell_d20", "acc_gold_d20", "acc_glass_d6", "acc_microfacet_d8"])
-def test_path_tracer_statistics_match_the_reference_golden(name):
+# (golden, samples per slice, flags): the bunny is brute force over 4984 primitives in the oracle, so it gets fewer samples
+# (the bound scales with its own standard error); flags = 1 pins the oracle's next-event-estimation port - an estimator
+# with the same expectation - to the reference's frames as well
+@pytest.mark.parametrize("name,spp_slice,flags", [("simple_cornell_d4", 128, 0), ("acc_cornell_d20", 128, 0), ("acc_gold_d20", 128, 0), ("acc_glass_d6", 128, 0),
+                                                  ("acc_microfacet_d8", 128, 0), ("acc_bunny5k_d20", 16, 0), ("simple_cornell_d4", 32, 1), ("acc_gold_d20", 16, 1)])
+def test_path_tracer_statistics_match_the_reference_golden(name, spp_slice, flags):
     """Linear-space mean and RMSE of the oracle (counter-based RNG) against the reference's own
     high-spp frames (time-seeded libstdc++ RNG): Monte-Carlo bound k = 5 sigma (+1%: the estimator is
     heavy tailed — lights are only hit by chance — so the sample sigma itself is noisy) on the image
     mean, RMSE within 1.5x the combined per-pixel standard error."""
-    ref, mine, sem = linear_stats(name, seed=123)
+    ref, mine, sem = linear_stats(name, seed=123, spp_slice=spp_slice, flags=flags)
     valid = ref["valid"]
     rmean, rsem = ref["mean"].astype(np.float64), ref["sem"].astype(np.float64)
     gm, gr = mine[valid].mean(), rmean[valid].mean()
     sigma = np.sqrt((sem[valid] ** 2).sum() + (rsem[valid] ** 2).sum()) / valid.sum() / 3
     z = (mine - rmean)[valid] / np.sqrt(sem[valid] ** 2 + rsem[valid] ** 2 + 1e-12)
     rmse, noise = np.sqrt(((mine - rmean)[valid] ** 2).mean()), np.sqrt((sem[valid] ** 2 + rsem[valid] ** 2).mean())
-    print(f"{name}: mean {gm:.5f} vs {gr:.5f}, 5 sigma {5 * sigma:.5f}, rmse {rmse:.5f} noise {noise:.5f}, median|z| {np.median(np.abs(z)):.3f}")
+    print(f"{name} flags {flags}: mean {gm:.5f} vs {gr:.5f}, 5 sigma {5 * sigma:.5f}, rmse {rmse:.5f} noise {noise:.5f}, median|z| {np.median(np.abs(z)):.3f}")
     assert abs(gm - gr) <= 5 * sigma + 0.01 * gr
     assert rmse <= 1.5 * noise
-    assert np.median(np.abs(z)) < 1.0
+    if spp_slice >= 128:   # per-pixel z scores need a usable standard error: at a few samples per slice most pixels never saw the light
+        assert np.median(np.abs(z)) < 1.0
 
 
 def test_rays_per_path_match_the_survey_probe():
@@ -108,3 +113,22 @@ def test_parser_quirk_preserved_in_fixtures():
     assert np.allclose(fs.material_params[1, 0:3], [0.63, 0.065, 0.0])
     fs = load_scene("bunny5k_cornel")
     assert fs.mesh_indices.size == 4968 * 3 and fs.mesh_positions.shape == (2503, 3)
+
+
+@pytest.mark.parametrize("name,mode,depth,glass,edit", [("path_tracing_cornel", 1, 5, 0, None), ("pt_glass", 2, 6, 1, glassify), ("bunny200_cornel", 2, 8, 0, None)])
+def test_nee_port_equals_the_host_build_of_the_device_code(name, mode, depth, glass, edit):
+    """oracle/nr_oracle.c restates the NEE extension in plain C; tests/host_emu compiles the CUDA headers for the host.
+    Two independent statements of the estimator, same counter-based RNG: same frames, same ray counts."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+    import pyemu
+    fs = load_scene(name, width=32, height=24, samples_per_pixel=6, depth=depth)
+    if edit:
+        edit(fs)
+    o, orays = po.OracleScene(fs, mode).render_pt_accum(seed=17, glass_mode=glass, flags=1)
+    e, erays = pyemu.EmuScene(fs, mode).render_pt_accum(seed=17, glass_mode=glass, flags=1)
+    assert orays == erays
+    rel = np.abs(o[..., :3] - e[..., :3]) / np.maximum(np.abs(e[..., :3]), 1e-3)
+    assert (rel < 1e-3).all(-1).mean() >= 0.99
+    plain, prays = po.OracleScene(fs, mode).render_pt_accum(seed=17, glass_mode=glass)
+    assert orays > prays and not np.array_equal(plain, o)

@@ -31,7 +31,7 @@ def main():
     for st in settings:
         env = dict(os.environ, **st)
         r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "2", "--warmup", "1", "--spp", spp,
-                            "--no-cpu-baseline", "--e2e-steps", "1"] + extra, capture_output=True, text=True, env=env)
+                            "--no-cpu-baseline", "--no-e2e", "--no-other-workloads"] + extra, capture_output=True, text=True, env=env)
         try:
             d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
             print(f"{st}: {d['value']:.1f} Mpath/s  {d['mrays_per_s']:.1f} Mrays/s  closest-hit {d['kernel_ms']['closest_hit']:.2f} ms  shade {d['kernel_ms']['shade']:.2f} ms  step {d['ms_per_step']:.2f} ms", flush=True)
