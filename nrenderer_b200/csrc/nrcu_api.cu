@@ -70,6 +70,9 @@ struct Sub { void* p = nullptr; template <typename T> T* as() const { return rei
 }  // namespace
 
 #define NRCU_MAX_WAVES 4
+#ifndef NRCU_OPT_RAYCOUNT
+#define NRCU_OPT_RAYCOUNT 1
+#endif
 #ifndef NRCU_SCHED_DEFAULT
 #define NRCU_SCHED_DEFAULT NRCU_SCHED_WAVES
 #endif
@@ -566,6 +569,13 @@ static cudaEvent_t pool_event(nrcu_ctx* ctx, size_t i) {
     return ctx->ev_pool[i];
 }
 
+#if NRCU_OPT_RAYCOUNT
+#define NRCU_RC_K nullptr      /* closest-hit kernels: no per-warp ray-counter atomics ... */
+#define NRCU_RC_A pp.d_rays    /* ... the wave's rays are summed from its queue sizes by k_accumulate */
+#else
+#define NRCU_RC_K pp.d_rays
+#define NRCU_RC_A nullptr
+#endif
 static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats) {
     const bool nee = params && (params->flags & NRCU_FLAG_NEE) && ctx->ds.n_area_lights > 0;
     ctx->ds.nee = nee ? 1 : 0;
@@ -672,8 +682,9 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             CTX_CUDA(cudaMemsetAsync(pp.cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
             const unsigned gen_grid = std::min<unsigned>(grid_for(pp.n_slots, 256), (unsigned)sms * 8);
             if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
-            if (gate) k_raygen<true, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, pp.d_rays);
-            else k_raygen<false, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, pp.d_rays);
+            // rays are counted from the queue sizes at the end of the wave (k_accumulate): no ray counter for the kernels
+            if (gate) k_raygen<true, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, NRCU_RC_K);
+            else k_raygen<false, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, NRCU_RC_K);
             CTX_LAUNCH_CHECK("k_raygen");
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); ev_i += 2; }   // booked as closest-hit time: stage 1 of bounce 0 is most of this kernel
         }
@@ -687,11 +698,11 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                 if (d > 0) {
                     if (big_balanced()) {
-                        if (gate) k_big_balanced<true, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays, 0u);
-                        else k_big_balanced<false, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays, 0u);
+                        if (gate) k_big_balanced<true, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u);
+                        else k_big_balanced<false, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u);
                     }
-                    else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
-                    else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, pp.d_rays);
+                    else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
+                    else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
                     CTX_LAUNCH_CHECK("k_big");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i, ev_i + 3, 0}); }
@@ -701,9 +712,13 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                     CTX_LAUNCH_CHECK("k_trace");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i + 3, ev_i + 1, 2}); }
-#define NRCU_SHADE(G, N) k_shade<G, N><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, pp.d_qn + CS * d, pp.hb, qo, pp.d_qn + CS * (d + 1), capacity, pp.L, pp.qs, pp.d_nshadow + CS * d)
-                if (gate) { if (nee) NRCU_SHADE(true, true); else NRCU_SHADE(true, false); }
-                else { if (nee) NRCU_SHADE(false, true); else NRCU_SHADE(false, false); }
+#define NRCU_SHADE(N, B) k_shade<N, B><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, pp.d_qn + CS * d, pp.hb, qo, pp.d_qn + CS * (d + 1), capacity, pp.L, pp.qs, pp.d_nshadow + CS * d)
+#if NRCU_OPT_BRANCH_TEMPLATE
+                if (glass_branch) { if (nee) NRCU_SHADE(true, true); else NRCU_SHADE(false, true); }
+                else { if (nee) NRCU_SHADE(true, false); else NRCU_SHADE(false, false); }
+#else
+                if (nee) NRCU_SHADE(true, false); else NRCU_SHADE(false, false);
+#endif
 #undef NRCU_SHADE
                 CTX_LAUNCH_CHECK("k_shade");
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 1}); ev_i += 4; }
@@ -715,8 +730,8 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                 if (nee && d + 1 < ds.depth) {   // the shadow rays of this bounce: same closest-hit kernels, then visibility + add
                     if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                     int nl = 0;
-                    if (gate) launch_closest_hit<true>(ctx, st, share, ds, pp.qs, pp.d_nshadow + CS * d, pp.hb, pp.surv, pp.d_snsurv + CS * d, pp.d_sfetch + CS * d, pp.d_rays, &nl);
-                    else launch_closest_hit<false>(ctx, st, share, ds, pp.qs, pp.d_nshadow + CS * d, pp.hb, pp.surv, pp.d_snsurv + CS * d, pp.d_sfetch + CS * d, pp.d_rays, &nl);
+                    if (gate) launch_closest_hit<true>(ctx, st, share, ds, pp.qs, pp.d_nshadow + CS * d, pp.hb, pp.surv, pp.d_snsurv + CS * d, pp.d_sfetch + CS * d, NRCU_RC_K, &nl);
+                    else launch_closest_hit<false>(ctx, st, share, ds, pp.qs, pp.d_nshadow + CS * d, pp.hb, pp.surv, pp.d_snsurv + CS * d, pp.d_sfetch + CS * d, NRCU_RC_K, &nl);
                     ctx->launches += nl - 1;
                     CTX_LAUNCH_CHECK("k_big/k_trace (shadow)");
                     if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }
@@ -749,7 +764,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             Pipe& pp = P[p];
             if (!pp.live) continue;
             if (NP > 1 && acc_recorded) CTX_CUDA(cudaStreamWaitEvent(pp.st, ctx->ev_acc, 0));
-            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw);
+            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw, pp.d_qn, nee ? pp.d_nshadow : nullptr, (uint32_t)CS, ds.depth, NRCU_RC_A);
             CTX_LAUNCH_CHECK("k_accumulate");
             if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_acc, pp.st)); acc_recorded = true; }
         }

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_
     const uint32_t stride = gridDim.x * blockDim.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *n_queue = s.depth == 0 ? 0u : n_slots;   // every slot starts one path: the bounce-0 queue is dense
-        if (STAGE1 && s.depth != 0) atomicAdd(ray_counter, (unsigned long long)n_slots);
+        if (STAGE1 && s.depth != 0 && ray_counter) atomicAdd(ray_counter, (unsigned long long)n_slots);
     }
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_slots; base += stride) {   // warp-uniform trip count
         const uint32_t slot = base + threadIdx.x;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             more = stage1<GATE>(s, bl, r, i, hits);
         }
-        if (lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        if (lane == 0 && ray_counter) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
         const uint32_t m = __ballot_sync(0xffffffffu, more);
         uint32_t start = 0;
         if (lane == 0 && m) start = atomicAdd(n_surv, (uint32_t)__popc(m));
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
             more = bvh_reachable(s, rp, best_t);
         }
         __syncwarp();   // the shared lists are rewritten by the next iteration
-        if (!SLOTS && lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        if (!SLOTS && ray_counter && lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
         append_survivors(more, i, surv, n_surv);
     }
 }
@@ -504,11 +504,23 @@ __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hit
 #ifndef NRCU_SHADE_MINB
 #define NRCU_SHADE_MINB 4
 #endif
-template <bool GATE, bool NEE>
-__global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch, uint32_t sample0,
+// NRCU_OPT_BRANCH_TEMPLATE=1 makes BRANCH (the reference's two-branch glass recursion) a template parameter, so that the
+// stochastic default carries none of the second-branch bookkeeping (split ballots, branch-bit loads and stores, shared-slot
+// float atomics): 280 fewer SASS instructions - and 1.5 % SLOWER in the same-call A/B (3015-3027 vs 3067 Mpath-samples/s,
+// profiles/r2_history.md), like every other "leaner" form of this latency-bound kernel.  Off: the mode is a kernel argument.
+#ifndef NRCU_OPT_BRANCH_TEMPLATE
+#define NRCU_OPT_BRANCH_TEMPLATE 0
+#endif
+template <bool NEE, bool BRANCH_T>
+__global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch_rt, uint32_t sample0,
                                               PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
                                               PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L,
                                               PathQueue qs, uint32_t* n_shadow_ptr) {
+#if NRCU_OPT_BRANCH_TEMPLATE
+    constexpr bool BRANCH = BRANCH_T;
+#else
+    const bool BRANCH = glass_branch_rt != 0;   // A/B only: the round-1 form with the mode as a kernel argument
+#endif
     const uint32_t n = *n_in_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -518,7 +530,7 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
     auto load_entry = [&](uint32_t j) {
         if (j >= n) return;
         a = qi.a[j]; b = qi.b[j]; c = qi.c[j]; h = hits[j];
-        if (glass_branch) br = qi.d[j];
+        if (BRANCH) br = qi.d[j];
     };
     load_entry(warp_global * 32u + lane);
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
@@ -532,14 +544,14 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
             slot = (uint32_t)f2i(c.w) & 0x7fffffffu; branch = br;
             const bool skip_light = ((uint32_t)f2i(c.w) >> 31) != 0u;   // the previous vertex sent a shadow ray (NEE)
             uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
-            ps = path_vertex<NEE>(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), glass_branch, skip_light);
+            ps = path_vertex<NEE>(s, seed, pixel, sample, d, branch, r, thr, h.x, __float_as_int(h.y), BRANCH ? 1 : 0, skip_light);
             if (ps.action == PATH_TERMINATE) {
                 if (NEE) {            // shadow rays of earlier bounces add to the same slot (k_shadow_resolve)
                     if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) {
-                        if (glass_branch) { atomicAdd(&L[slot].x, ps.radiance.x); atomicAdd(&L[slot].y, ps.radiance.y); atomicAdd(&L[slot].z, ps.radiance.z); }
+                        if (BRANCH) { atomicAdd(&L[slot].x, ps.radiance.x); atomicAdd(&L[slot].y, ps.radiance.y); atomicAdd(&L[slot].z, ps.radiance.z); }
                         else { f4 v = L[slot]; L[slot] = mk4(v.x + ps.radiance.x, v.y + ps.radiance.y, v.z + ps.radiance.z, 0.f); }
                     }
-                } else if (glass_branch) {   // several branches of one path share the slot
+                } else if (BRANCH) {   // several branches of one path share the slot
                     if (ps.radiance.x != 0.f) atomicAdd(&L[slot].x, ps.radiance.x);
                     if (ps.radiance.y != 0.f) atomicAdd(&L[slot].y, ps.radiance.y);
                     if (ps.radiance.z != 0.f) atomicAdd(&L[slot].z, ps.radiance.z);
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
             } else n_out = ps.action == PATH_SPLIT ? 2 : 1;
         }
         // warp-aggregated allocation in the output queue
-        const uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = __ballot_sync(0xffffffffu, n_out == 2);
+        const uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = BRANCH ? __ballot_sync(0xffffffffu, n_out == 2) : 0u;
         const uint32_t total = __popc(m1) + __popc(m2);
         uint32_t start = 0;
         if (lane == 0 && total) start = atomicAdd(n_out_ptr, total);
@@ -578,9 +590,9 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
             qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
             qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
             qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)(slot | ((NEE && ps.next_skips_light) ? 0x80000000u : 0u))));
-            if (glass_branch) qo.d[pos1] = branch;
+            if (BRANCH) qo.d[pos1] = branch;
         }
-        if (n_out == 2 && pos2 < out_capacity) {   // glass branch mode only
+        if (BRANCH && n_out == 2 && pos2 < out_capacity) {   // glass branch mode only
             qo.a[pos2] = mk4(ps.next2.o.x, ps.next2.o.y, ps.next2.o.z, ps.next2.d.x);
             qo.b[pos2] = make_float2(ps.next2.d.y, ps.next2.d.z);
             qo.c[pos2] = mk4(ps.thr2.x, ps.thr2.y, ps.thr2.z, i2f((int)slot));
@@ -732,8 +744,20 @@ __global__ void k_clamp_count(uint32_t* n_ptr, uint32_t capacity, uint32_t* high
 
 // End of wave: accum[p].rgb += L[s*npix + p] for the k samples of the wave in sample order (fp32,
 // the reference's `color += trace(...)`, AccPathTracer.cpp:30), accum[p].a += k.
-__global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k, uint32_t n_samples) {
+// The rays of the wave are the sizes of its queues - every entry of every bounce's queue (and of every shadow queue) went
+// through one closest-hit query - so thread 0 adds those counters up here instead of every warp of the closest-hit kernels
+// sending an atomic per 32 rays.
+__global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k, uint32_t n_samples,
+                             const uint32_t* qn, const uint32_t* nshadow, uint32_t counter_stride, uint32_t depth, unsigned long long* ray_counter) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0 && ray_counter) {
+        unsigned long long rays = 0;
+        for (uint32_t d = 0; d < depth; d++) {
+            rays += qn[(size_t)counter_stride * d];
+            if (nshadow && d + 1 < depth) rays += nshadow[(size_t)counter_stride * d];
+        }
+        *ray_counter += rays;   // one wave accumulates at a time on this counter (its own block of counters)
+    }
     if (p >= npix) return;
     f4 acc = accum[p];
     for (uint32_t s = 0; s < k; s++) {

@@ -171,12 +171,23 @@ NR_HD Ray shade_lambertian(vec3 albedo, vec3 hit_point, vec3 normal, float e1, f
     float y = sn * r;
     float z = e1;
     vec3 w = normal;
+    // Onb.hpp:20 compares in double: (double)|w.x| > 0.9.  0.9f = 0.89999997... < 0.9 < its fp32 successor, so for a float
+    // operand that is the same predicate as |w.x| > 0.9f - without the conversion and the FP64 compare.
+#ifndef NRCU_OPT_ONB_FLOAT
+#define NRCU_OPT_ONB_FLOAT 1
+#endif
+#if NRCU_OPT_ONB_FLOAT
+    vec3 a = (fabsf(w.x) > 0.9f) ? mk3(0, 1, 0) : mk3(1, 0, 0);
+#else
     vec3 a = ((double)fabsf(w.x) > 0.9) ? mk3(0, 1, 0) : mk3(1, 0, 0);
+#endif
     vec3 v = normalize(cross(w, a));
     vec3 u = cross(w, v);
     vec3 local = x * u + y * v + z * w;
     Ray out; out.o = hit_point; out.d = normalize(local);
     float pdf = 1 / (2 * NRCU_PT_PI);
+    // (albedo / PI precomputed per material was measured twice - at the end of the record and inside its first 32-byte
+    // sector - and lost 0.5 % both times although it removes three IEEE divisions: profiles/r2_history.md)
     vec3 attenuation = albedo / NRCU_PT_PI;
     float n_dot_in = dot(normal, out.d);
     factor = attenuation * n_dot_in / pdf;
@@ -409,7 +420,7 @@ NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint3
         } else {
             // type 0 (any other type falls off the end of the reference's trace(): treated as Lambertian)
             u32x4 rn = rng_block(seed, pixel, sample, d, branch);
-            vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(rn.y), f);
+vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(rn.y), f);
             ps.thr = thr * f; ps.action = PATH_CONTINUE;
             // NEE only where the continuation will really be traced: at the depth limit the reference returns the
             // ambient colour without looking for the light (AccPathTracer.cpp:122)
