@@ -186,10 +186,16 @@ enum nrcu_glass_mode {
 
 /* nrcu_render_params.flags */
 enum nrcu_render_flags {
-    NRCU_FLAG_NEE = 1u << 0    /* EXTENSION (not in the reference, whose area lights are only hit by chance): next-event
+    NRCU_FLAG_NEE = 1u << 0,   /* EXTENSION (not in the reference, whose area lights are only hit by chance): next-event
                                   estimation at Lambertian vertices - one shadow ray per diffuse bounce towards a uniformly
                                   sampled point of an area light; same expectation as the reference's estimator, far
                                   lower variance.  Ignored in RayCast mode. */
+    NRCU_FLAG_ENV_IS = 1u << 1 /* EXTENSION to the environment-map extension: at Lambertian vertices one direction is
+                                  drawn from the map's luminance x sin(theta) distribution (marginal/conditional CDF tables built at
+                                  upload) and its shadow ray is combined with the hemisphere sample by the balance heuristic.  Same
+                                  expectation as the plain miss lookup, far lower variance for maps with small bright regions.  Takes
+                                  effect only when the scene's ambient is an environment map; it then replaces NRCU_FLAG_NEE's light
+                                  sampling at those vertices (one shadow ray per vertex). */
 };
 
 /* How the (pixel, sample) paths are scheduled onto the GPU.  Both schedulers trace exactly the same paths (the RNG is

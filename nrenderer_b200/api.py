@@ -14,6 +14,7 @@ import numpy as np
 from .flatscene import FlatScene, MODE_ACC, MODE_RAYCAST, MODE_SIMPLE  # noqa: F401
 
 FLAG_NEE = 1   # nrcu_render_flags.NRCU_FLAG_NEE
+FLAG_ENV_IS = 2   # nrcu_render_flags.NRCU_FLAG_ENV_IS
 SCHED_AUTO, SCHED_WAVES, SCHED_REGEN = 0, 1, 2   # nrcu_scheduler
 ERR_OVERFLOW = 6
 

@@ -86,7 +86,7 @@ struct nrcu_ctx {
     uint32_t spp = 0;
     DScene ds{};
     // scene buffers
-    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, materials, area_lights, env;
+    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, materials, area_lights, env, env_tab;
     // scene-prep sources kept for nrcu_download_primitives
     DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
@@ -277,6 +277,17 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
         if (cnt) {
             if ((rc = upload(ctx, ctx->env, reinterpret_cast<const f4*>(sc->texture_rgba + sc->texture_offset[ti]), cnt)) != NRCU_OK) return rc;
             ds.env_rgba = ctx->env.as<f4>(); ds.env_w = (int)sc->texture_width[ti]; ds.env_h = (int)sc->texture_height[ti];
+            // importance-sampling tables (NRCU_FLAG_ENV_IS): sin per row, marginal CDF, conditional CDFs + the total weight
+            const size_t tab_floats = 2 * (size_t)ds.env_h + cnt;
+            CTX_CUDA(ctx->env_tab.ensure(sizeof(float) * (tab_floats + 1)));
+            float* tab = ctx->env_tab.as<float>();
+            k_env_rows<<<grid_for((size_t)ds.env_h, 64), 64, 0, ctx->stream>>>(ds.env_rgba, ds.env_w, ds.env_h, tab);
+            CTX_LAUNCH_CHECK("k_env_rows");
+            k_env_marginal<<<1, 1, 0, ctx->stream>>>(ds.env_h, tab, tab + tab_floats);
+            CTX_LAUNCH_CHECK("k_env_marginal");
+            CTX_CUDA(cudaMemcpyAsync(&ds.env_total, tab + tab_floats, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CTX_CUDA(cudaStreamSynchronize(ctx->stream));
+            ds.env_tab = tab;
         }
     }
     // ---- mesh world transform on the device, once per MESH node, in node order --------------------------
@@ -564,6 +575,13 @@ static void launch_closest_hit(nrcu_ctx* ctx, cudaStream_t st, unsigned share, c
 
 extern "C" {
 
+static int direct_sampling_mode(const nrcu_ctx* ctx, const nrcu_render_params* params) {
+    if (!params) return 0;
+    if ((params->flags & NRCU_FLAG_ENV_IS) && ctx->mode == NRCU_MODE_ACC && ctx->ds.env_rgba && ctx->ds.env_tab && ctx->ds.env_total > 0.f) return 2;
+    if ((params->flags & NRCU_FLAG_NEE) && ctx->ds.n_area_lights > 0) return 1;
+    return 0;
+}
+
 static cudaEvent_t pool_event(nrcu_ctx* ctx, size_t i) {
     while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
     return ctx->ev_pool[i];
@@ -577,8 +595,10 @@ static cudaEvent_t pool_event(nrcu_ctx* ctx, size_t i) {
 #define NRCU_RC_A nullptr
 #endif
 static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats) {
-    const bool nee = params && (params->flags & NRCU_FLAG_NEE) && ctx->ds.n_area_lights > 0;
-    ctx->ds.nee = nee ? 1 : 0;
+    // direct sampling at Lambertian vertices (extensions): the environment map when the scene has one and NRCU_FLAG_ENV_IS is
+    // set, else the area lights under NRCU_FLAG_NEE; one shadow ray per vertex either way
+    ctx->ds.nee = direct_sampling_mode(ctx, params);
+    const bool nee = ctx->ds.nee != 0;
     const DScene& ds = ctx->ds;
     const uint32_t npix = ds.width * ds.height;
     uint32_t s0 = params ? params->sample_begin : 0, s1 = params ? params->sample_end : 0;
@@ -972,7 +992,7 @@ static int render_pt(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accu
     if (s1 < s0) { ctx->error = "sample_end < sample_begin"; return NRCU_ERR_INVALID; }
     int sched = params ? (int)params->scheduler : NRCU_SCHED_AUTO;
     if (sched != NRCU_SCHED_WAVES && sched != NRCU_SCHED_REGEN) sched = (params && params->samples_per_wave) ? NRCU_SCHED_WAVES : default_scheduler();
-    const bool nee = params && (params->flags & NRCU_FLAG_NEE) && ctx->ds.n_area_lights > 0;
+    const bool nee = direct_sampling_mode(ctx, params) != 0;
     const bool branch = params && params->glass_mode == NRCU_GLASS_BRANCH;
     const uint32_t depth = ctx->ds.depth;
     // the regeneration scheduler carries one ray per slot: no shadow rays, no path splitting; its state packs the bounce

@@ -21,6 +21,13 @@ __global__ void k_build_prims(PrimSources ps, uint32_t n, int raycast, f4* geom,
     if (i < n) build_prim(ps, i, raycast, geom, shade, box, bound, meta, export16);
 }
 
+// environment-map importance-sampling tables (bodies in nrcu_shade.cuh): one thread per row, then one thread
+__global__ void k_env_rows(const f4* rgba, int w, int h, float* tab) {
+    int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y < h) env_table_row(rgba, w, h, y, tab);
+}
+__global__ void k_env_marginal(int h, float* tab, float* total_out) { *total_out = env_table_marginal(h, tab); }
+
 // ---------------------------------------------------------------------------------------------
 // BVH build: one kernel per step body
 // ---------------------------------------------------------------------------------------------

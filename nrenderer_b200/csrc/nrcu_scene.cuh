@@ -120,10 +120,13 @@ struct DScene {
     DCamera cam;
     vec3 ambient;
     const f4* env_rgba; int env_w, env_h;   // ambient environment map (extension) or null
+    // importance-sampling tables of the map (NRCU_FLAG_ENV_IS): [0,h) sin(theta) at the row centres, [h,2h) marginal CDF over
+    // the rows (weight = sin x row luminance), [2h, 2h + w*h) conditional CDF inside each row; env_total = sum of the row weights
+    const float* env_tab; float env_total;
     // Microfacet: the half-vector in the local frame is a constant because the reference reseeds
     // minstd_rand with 6 on every call (Microfacet.cpp:65-76); computed on the host with libm.
     float mf_u1, mf_u2, mf_cos_phi, mf_sin_phi;
-    int nee;                      // next-event estimation at Lambertian vertices (extension, NRCU_FLAG_NEE; off = reference estimator)
+    int nee;                      // direct sampling at Lambertian vertices (extensions): 0 off = the reference's estimator, 1 area lights (NRCU_FLAG_NEE), 2 environment map (NRCU_FLAG_ENV_IS)
     // Loud failure instead of a silently wrong frame: [0] traversal-stack entries that did not fit (a hit may have been
     // missed), [1] rays that did not fit the branching-glass queue.  Read back by the host at every synchronisation
     // point; non-zero => NRCU_ERR_OVERFLOW.

@@ -16,6 +16,7 @@
 namespace nrcu {
 
 #define NRCU_PT_PI 3.1415926535898f   // acc_path_tracing/include/shaders/Shader.hpp:17
+#define NRCU_PDF_HEMISPHERE (1.0f / (2.0f * NRCU_PT_PI))   // HemiSphere sampler: uniform over the hemisphere
 
 // RayCast: pixel corner, no jitter (RayCastRenderer.cpp:27-35).  p = output pixel index (row 0 = top).
 NR_HD Ray raycast_camera_ray(const DScene& s, uint32_t p) {
@@ -316,6 +317,89 @@ NR_HD vec3 env_lookup(const DScene& s, vec3 d) {
     return mk3(px.x, px.y, px.z);
 }
 
+// ---- environment-map importance sampling (extension, NRCU_FLAG_ENV_IS) ---------------------------------------------------
+// The map is piecewise constant (nearest-texel lookup above), so a texel is drawn with probability proportional to
+// luminance x sin(theta_row) and the direction uniformly inside the texel: marginal CDF over rows, conditional CDF per row.
+NR_HD float env_luminance(f4 px) { return (px.x + px.y) + px.z; }
+// table layout: DScene::env_tab.  Row pass: one work item per row (sequential fp32 prefix sums: the same on every machine).
+NR_HD void env_table_row(const f4* rgba, int w, int h, int y, float* tab) {
+    const float C_PI = 3.14159265358979323846264338327950288f;
+    float sn, cs;
+    sincos_det(C_PI * ((float)y + 0.5f) / (float)h, sn, cs);
+    tab[y] = sn;
+    float* cdf = tab + 2 * (size_t)h + (size_t)y * w;
+    float sum = 0.f;
+    for (int x = 0; x < w; x++) { sum += env_luminance(rgba[(size_t)y * w + x]); cdf[x] = sum; }
+    for (int x = 0; x < w; x++) cdf[x] = sum > 0.f ? cdf[x] / sum : (float)(x + 1) / (float)w;
+    cdf[w - 1] = 1.f;
+    tab[h + y] = sn * sum;   // row weight; turned into the marginal CDF by env_table_marginal
+}
+NR_HD float env_table_marginal(int h, float* tab) {   // ONE work item, after every row; returns the total weight
+    float total = 0.f;
+    for (int y = 0; y < h; y++) { total += tab[h + y]; tab[h + y] = total; }
+    for (int y = 0; y < h; y++) tab[h + y] = total > 0.f ? tab[h + y] / total : (float)(y + 1) / (float)h;
+    tab[2 * h - 1] = 1.f;
+    return total;
+}
+// smallest i in [0, n) with e < cdf[i] (cdf[n-1] = 1 > e), and e remapped to [0,1) inside that step
+NR_HD int cdf_pick(const float* cdf, int n, float e, float& frac) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (e < cdf[mid]) hi = mid; else lo = mid + 1; }
+    float c0 = lo ? cdf[lo - 1] : 0.f, c1 = cdf[lo];
+    frac = c1 > c0 ? (e - c0) / (c1 - c0) : 0.5f;
+    if (!(frac >= 0.f)) frac = 0.f;
+    if (frac > 0.99999994f) frac = 0.99999994f;
+    return lo;
+}
+// solid-angle pdf of drawing direction n (unit) through texel (x, y): sin_row lum w h / (total 2 pi^2 sin(theta_n))
+NR_HD float env_pdf(const DScene& s, int x, int y, vec3 n) {
+    float st = sqrtf(fmaxf(0.f, 1.f - n.y * n.y));
+    if (!(st > 0.f) || !(s.env_total > 0.f)) return 0.f;
+    float lum = env_luminance(ldg4(s.env_rgba + (size_t)y * s.env_w + x));
+    return s.env_tab[y] * lum * (float)s.env_w * (float)s.env_h / (s.env_total * (2.f * NRCU_PT_PI * NRCU_PT_PI) * st);
+}
+// texel that env_lookup reads for direction d (d non-zero, finite)
+NR_HD void env_texel(const DScene& s, vec3 n, int& x, int& y) {
+    float u = 0.5f + atan2f(n.x, n.z) * (0.5f / NRCU_PT_PI);
+    float cy = fminf(1.f, fmaxf(-1.f, n.y));
+    float v = acosf(cy) * (1.0f / NRCU_PT_PI);
+    x = (int)(u * (float)s.env_w); y = (int)(v * (float)s.env_h);
+    x = x < 0 ? 0 : (x > s.env_w - 1 ? s.env_w - 1 : x);
+    y = y < 0 ? 0 : (y > s.env_h - 1 ? s.env_h - 1 : y);
+}
+// One direct sample of the map at a Lambertian vertex: shadow ray + what it adds if it leaves the scene unoccluded
+// (f Le / (p_env + p_hemisphere), balance heuristic with the hemisphere sample that follows).
+NR_HD bool env_sample(const DScene& s, vec3 albedo, vec3 hit_point, vec3 normal, vec3 thr, float e1, float e2, Ray& shadow, vec3& contrib) {
+    const float C_PI = 3.14159265358979323846264338327950288f;
+    const int w = s.env_w, h = s.env_h;
+    float jy, jx;
+    const int y = cdf_pick(s.env_tab + h, h, e1, jy);
+    const int x = cdf_pick(s.env_tab + 2 * (size_t)h + (size_t)y * w, w, e2, jx);
+    const float u = ((float)x + jx) / (float)w, v = ((float)y + jy) / (float)h;
+    float sp, cp, st, ct;
+    sincos_det(2.f * C_PI * u, sp, cp);          // phi = 2 pi u - pi: sin(phi) = -sin(2 pi u), cos(phi) = -cos(2 pi u)
+    sincos_det(C_PI * v, st, ct);
+    vec3 d = mk3(st * -sp, ct, st * -cp);
+    float cos_s = dot(normal, d);
+    if (!(cos_s > 0.f)) return false;
+    float p_env = env_pdf(s, x, y, d);
+    if (!(p_env > 0.f)) return false;
+    f4 px = ldg4(s.env_rgba + (size_t)y * w + x);
+    vec3 f = (albedo / NRCU_PT_PI) * cos_s;
+    contrib = thr * f * mk3(px.x, px.y, px.z) * (1.0f / (p_env + NRCU_PDF_HEMISPHERE));
+    if (is_zero(contrib)) return false;
+    shadow.o = hit_point; shadow.d = d;
+    return true;
+}
+// Balance-heuristic weight of a hemisphere sample that left the scene in direction d (the previous vertex also sampled the map).
+NR_HD float mis_env_weight(const DScene& s, vec3 d) {
+    if (!(dot(d, d) > 0.f) || !(dot(d, d) < NRCU_INF)) return 1.f;
+    vec3 n = normalize(d);
+    int x, y; env_texel(s, n, x, y);
+    return NRCU_PDF_HEMISPHERE / (NRCU_PDF_HEMISPHERE + env_pdf(s, x, y, n));
+}
+#define NRCU_NEE_LIGHT_ENV (-2)   // PathStep::nee_light of a shadow ray aimed at the environment map
+
 // Result of processing one path vertex.
 enum { PATH_CONTINUE = 0, PATH_TERMINATE = 1, PATH_SPLIT = 2 };
 struct PathStep {
@@ -338,7 +422,6 @@ struct PathStep {
 // light of path_tracing_cornel.scn, 3 units under the ceiling, makes the 1/r^2 term explode.  V is evaluated by the
 // caller with the same closest-hit and closest-light queries the reference applies to any ray (so self-intersection
 // "acne" blocks the light exactly where it would have turned a hemisphere sample into a surface hit).
-#define NRCU_PDF_HEMISPHERE (1.0f / (2.0f * NRCU_PT_PI))
 NR_HD bool nee_sample(const DScene& s, vec3 albedo, vec3 hit_point, vec3 normal, vec3 thr, float e1, float e2, Ray& shadow, vec3& contrib, int& light) {
     if (s.n_area_lights == 0) return false;
     float fl = e1 * (float)s.n_area_lights;
@@ -375,6 +458,7 @@ NR_HD float mis_light_weight(const DScene& s, const Ray& ray, int which, float t
 NR_HD bool nee_visible(const DScene& s, const Ray& shadow, int light, float t_obj, int id_obj) {
     vec3 rad; int which;
     float tl = closest_light(s, shadow, rad, &which);
+    if (light == NRCU_NEE_LIGHT_ENV) return id_obj < 0 && which < 0;   // the map is seen iff the ray leaves the scene: no object, no light quad
     if (which != light) return false;
     return !(id_obj >= 0 && t_obj < tl);
 }
@@ -425,8 +509,9 @@ vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(r
             // NEE only where the continuation will really be traced: at the depth limit the reference returns the
             // ambient colour without looking for the light (AccPathTracer.cpp:122)
             if (NEE && d + 1 < s.depth) {
-                ps.nee = nee_sample(s, ld3(m.diffuse_color), hp, n, thr, u01(rn.z), u01(rn.w), ps.shadow, ps.nee_contrib, ps.nee_light);
-                ps.next_skips_light = true;
+                if (s.nee == 2) { ps.nee = env_sample(s, ld3(m.diffuse_color), hp, n, thr, u01(rn.z), u01(rn.w), ps.shadow, ps.nee_contrib); ps.nee_light = NRCU_NEE_LIGHT_ENV; }
+                else ps.nee = nee_sample(s, ld3(m.diffuse_color), hp, n, thr, u01(rn.z), u01(rn.w), ps.shadow, ps.nee_contrib, ps.nee_light);
+                ps.next_skips_light = true;   // "the vertex before this ray also sampled its light source (area lights / the map) directly"
             }
         }
         // the continuation would return ambient at the depth limit (AccPathTracer.cpp:122)
@@ -437,9 +522,10 @@ vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(r
         }
     } else if (tl != NRCU_INF) {
         ps.radiance = thr * radiance;
-        if (NEE && skip_light) ps.radiance = ps.radiance * mis_light_weight(s, ray, which_light, tl);
+        if (NEE && skip_light && s.nee == 1) ps.radiance = ps.radiance * mis_light_weight(s, ray, which_light, tl);
     } else if (s.env_rgba && s.mode == MODE_ACC) {
         ps.radiance = thr * env_lookup(s, ray.d);
+        if (NEE && skip_light && s.nee == 2) ps.radiance = ps.radiance * mis_env_weight(s, ray.d);
     }
     return ps;
 }

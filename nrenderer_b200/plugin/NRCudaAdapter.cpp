@@ -112,6 +112,7 @@ namespace NRCuda
                 nrcu_render_params params{};
                 if (const char* e = std::getenv("NRCU_SEED")) params.seed = std::strtoull(e, nullptr, 10);
                 if (const char* e = std::getenv("NRCU_NEE")) if (std::atoi(e)) params.flags |= NRCU_FLAG_NEE;   // extension: same expectation, less noise
+                if (const char* e = std::getenv("NRCU_ENV_IS")) if (std::atoi(e)) params.flags |= NRCU_FLAG_ENV_IS;   // extension: importance-sample the environment map
                 if (const char* e = std::getenv("NRCU_GLASS_BRANCH")) params.glass_mode = std::atoi(e) ? NRCU_GLASS_BRANCH : NRCU_GLASS_STOCHASTIC;
                 nrcu_stats st{};
                 RGBA* pixels = new RGBA[(size_t)w * h];   // plugin owns the buffer, Screen::set copies it (RayCastRenderer.cpp:7-10)

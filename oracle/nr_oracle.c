@@ -72,6 +72,7 @@ struct nro_scene {
     camera_t cam;
     v3 ambient;
     int env_w, env_h; float* env_rgba; /* ambient environment map (our extension, A18) */
+    float *env_sin, *env_row_cdf, *env_col_cdf; float env_total; /* importance-sampling tables (NRCU_FLAG_ENV_IS), built lazily */
     /* Microfacet Sampler(6) constants (acc_path_tracing/src/shaders/Microfacet.cpp:71-76) */
     float mf_u1, mf_u2;
 };
@@ -319,6 +320,7 @@ void nro_free(nro_scene* s) {
     if (!s) return;
     free(s->prims); free(s->materials); free(s->point_intensity); free(s->point_position);
     free(s->area_radiance); free(s->area_position); free(s->area_u); free(s->area_v); free(s->env_rgba);
+    free(s->env_sin); free(s->env_row_cdf); free(s->env_col_cdf);
     free(s);
 }
 uint32_t nro_primitive_count(const nro_scene* s) { return s->n_prims; }
@@ -822,6 +824,83 @@ static v3 env_lookup(const nro_scene* s, v3 d) {
     return V(px[0], px[1], px[2]);
 }
 
+/* ---- environment-map importance sampling: an EXTENSION of the environment-map extension (NRCU_FLAG_ENV_IS), restated here
+ * independently of the CUDA sources.  The map is piecewise constant, so a texel is drawn with probability proportional to
+ * (r+g+b) * sin(theta at the row centre) - marginal CDF over the rows, conditional CDF inside the row - and the direction
+ * uniformly inside the texel; solid-angle pdf = sin_row * lum * w * h / (total * 2 pi^2 * sin(theta of the direction)).
+ * All sums are sequential fp32, sin via the shared sincos_det, so the tables equal the device's bit for bit. */
+static void sincos_det(float a, float* s, float* c);
+static void env_build_tables(nro_scene* s) {
+    const float C_PI = 3.14159265358979323846264338327950288f;
+    int w = s->env_w, h = s->env_h;
+    s->env_sin = (float*)malloc(sizeof(float) * h); s->env_row_cdf = (float*)malloc(sizeof(float) * h);
+    s->env_col_cdf = (float*)malloc(sizeof(float) * (size_t)w * h);
+    for (int y = 0; y < h; y++) {
+        float sn, cs; sincos_det(C_PI * ((float)y + 0.5f) / (float)h, &sn, &cs);
+        s->env_sin[y] = sn;
+        float* cdf = s->env_col_cdf + (size_t)y * w;
+        float sum = 0.f;
+        for (int x = 0; x < w; x++) { const float* px = s->env_rgba + 4 * ((size_t)y * w + x); sum += (px[0] + px[1]) + px[2]; cdf[x] = sum; }
+        for (int x = 0; x < w; x++) cdf[x] = sum > 0.f ? cdf[x] / sum : (float)(x + 1) / (float)w;
+        cdf[w - 1] = 1.f;
+        s->env_row_cdf[y] = sn * sum;
+    }
+    float total = 0.f;
+    for (int y = 0; y < h; y++) { total += s->env_row_cdf[y]; s->env_row_cdf[y] = total; }
+    for (int y = 0; y < h; y++) s->env_row_cdf[y] = total > 0.f ? s->env_row_cdf[y] / total : (float)(y + 1) / (float)h;
+    s->env_row_cdf[h - 1] = 1.f;
+    s->env_total = total;
+}
+static int cdf_pick(const float* cdf, int n, float e, float* frac) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (e < cdf[mid]) hi = mid; else lo = mid + 1; }
+    float c0 = lo ? cdf[lo - 1] : 0.f, c1 = cdf[lo];
+    *frac = c1 > c0 ? (e - c0) / (c1 - c0) : 0.5f;
+    if (!(*frac >= 0.f)) *frac = 0.f;
+    if (*frac > 0.99999994f) *frac = 0.99999994f;
+    return lo;
+}
+static float env_pdf(const nro_scene* s, int x, int y, v3 n) {
+    float st = sqrtf(fmaxf(0.f, 1.f - n.y * n.y));
+    if (!(st > 0.f) || !(s->env_total > 0.f)) return 0.f;
+    const float* px = s->env_rgba + 4 * ((size_t)y * s->env_w + x);
+    float lum = (px[0] + px[1]) + px[2];
+    return s->env_sin[y] * lum * (float)s->env_w * (float)s->env_h / (s->env_total * (2.f * PT_PI * PT_PI) * st);
+}
+static int env_sample(const nro_scene* s, v3 albedo, v3 hit_point, v3 normal, v3 thr, float e1, float e2, ray_t* shadow, v3* contrib) {
+    const float C_PI = 3.14159265358979323846264338327950288f;
+    int w = s->env_w, h = s->env_h;
+    float jy, jx;
+    int y = cdf_pick(s->env_row_cdf, h, e1, &jy);
+    int x = cdf_pick(s->env_col_cdf + (size_t)y * w, w, e2, &jx);
+    float u = ((float)x + jx) / (float)w, v = ((float)y + jy) / (float)h;
+    float sp, cp, st, ct;
+    sincos_det(2.f * C_PI * u, &sp, &cp);
+    sincos_det(C_PI * v, &st, &ct);
+    v3 d = V(st * -sp, ct, st * -cp);
+    float cos_s = vdot(normal, d);
+    if (!(cos_s > 0.f)) return 0;
+    float p_env = env_pdf(s, x, y, d);
+    if (!(p_env > 0.f)) return 0;
+    const float* px = s->env_rgba + 4 * ((size_t)y * w + x);
+    v3 f = vscale(vdivs(albedo, PT_PI), cos_s);
+    *contrib = vscale(vmul(vmul(thr, f), V(px[0], px[1], px[2])), 1.0f / (p_env + PDF_HEMISPHERE));
+    if (contrib->x == 0.f && contrib->y == 0.f && contrib->z == 0.f) return 0;
+    shadow->o = hit_point; shadow->d = d;
+    return 1;
+}
+static float mis_env_weight(const nro_scene* s, v3 d) {
+    if (!(vdot(d, d) > 0.f) || !(vdot(d, d) < INFINITY)) return 1.f;
+    v3 n = vnormalize(d);
+    float u = 0.5f + atan2f(n.x, n.z) * (0.5f / PT_PI);
+    float cy = n.y; if (cy > 1.f) cy = 1.f; if (cy < -1.f) cy = -1.f;
+    float v = acosf(cy) * (1.0f / PT_PI);
+    int x = (int)(u * (float)s->env_w), y = (int)(v * (float)s->env_h);
+    if (x < 0) x = 0; if (x > s->env_w - 1) x = s->env_w - 1;
+    if (y < 0) y = 0; if (y > s->env_h - 1) y = s->env_h - 1;
+    return PDF_HEMISPHERE / (PDF_HEMISPHERE + env_pdf(s, x, y, n));
+}
+
 /* trace(): AccPathTracer.cpp:121-181 / SimplePathTracer.cpp:144-177, restated as a forward
  * throughput loop (the recursion is a product of per-bounce factors) with a small explicit stack
  * for the glass two-branch case.  branch_bits identifies the branch for the RNG. */
@@ -831,7 +910,7 @@ static v3 pt_trace(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t s
     v3 L = V(0, 0, 0);
     work_t stack[256];
     int sp = 0;
-    if (s->n_area == 0) nee = 0;
+    if (nee == 1 && s->n_area == 0) nee = 0;
     stack[sp].ray = ray0; stack[sp].thr = V(1, 1, 1); stack[sp].depth = 0; stack[sp].branch = 0; sp++;
     while (sp > 0) {
         work_t wk = stack[--sp];
@@ -880,7 +959,17 @@ static v3 pt_trace(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t s
                 } else {
                     /* type 0; any other type falls off the end of the reference's trace() (UB) - treated as Lambertian */
                     v3 albedo = ld3(m->diffuse_color);
-                    if (nee && d + 1 < s->depth) {   /* only where the continuation is really traced (AccPathTracer.cpp:122) */
+                    if (nee == 2 && d + 1 < s->depth) {   /* the environment map sampled directly */
+                        ray_t shadow; v3 contrib;
+                        if (env_sample(s, albedo, h.p, h.n, thr, u01(rn[2]), u01(rn[3]), &shadow, &contrib)) {
+                            (*rays)++;
+                            hit_t sh = closest_hit(s, shadow, NULL, NULL);
+                            v3 srad; int swhich;
+                            closest_light_which(s, shadow, &srad, &swhich);
+                            if (!sh.hit && swhich < 0) L = vadd(L, contrib);   /* seen iff the ray leaves the scene */
+                        }
+                        mis = 1;
+                    } else if (nee && d + 1 < s->depth) {   /* only where the continuation is really traced (AccPathTracer.cpp:122) */
                         ray_t shadow; v3 contrib; int li;
                         if (nee_sample(s, albedo, h.p, h.n, thr, u01(rn[2]), u01(rn[3]), &shadow, &contrib, &li)) {
                             (*rays)++;
@@ -895,10 +984,14 @@ static v3 pt_trace(const nro_scene* s, uint64_t seed, uint32_t pixel, uint32_t s
                 }
             } else if (tl != INFINITY) {
                 v3 add = vmul(thr, radiance);
-                if (nee && weigh_light) add = vscale(add, mis_light_weight(s, ray, which, tl));
+                if (nee == 1 && weigh_light) add = vscale(add, mis_light_weight(s, ray, which, tl));
                 L = vadd(L, add); break;
             } else {
-                if (s->env_rgba && s->mode == NRCU_MODE_ACC) L = vadd(L, vmul(thr, env_lookup(s, ray.d)));
+                if (s->env_rgba && s->mode == NRCU_MODE_ACC) {
+                    v3 add = vmul(thr, env_lookup(s, ray.d));
+                    if (nee == 2 && weigh_light) add = vscale(add, mis_env_weight(s, ray.d));
+                    L = vadd(L, add);
+                }
                 break;
             }
         }
@@ -935,7 +1028,12 @@ void nro_render_pt_pixels_flags(const nro_scene* s, uint64_t seed, uint32_t s0, 
                                 const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out) {
     if (s1 == 0 && s0 == 0) s1 = s->spp;
     pt_ctx* c = (pt_ctx*)calloc(1, sizeof(pt_ctx));
-    c->s = s; c->seed = seed; c->s0 = s0; c->s1 = s1; c->glass_mode = glass_mode; c->nee = (flags & NRCU_FLAG_NEE) != 0; c->pixels = pixels; c->accum4 = accum4;
+    c->s = s; c->seed = seed; c->s0 = s0; c->s1 = s1; c->glass_mode = glass_mode; c->pixels = pixels; c->accum4 = accum4;
+    c->nee = (flags & NRCU_FLAG_NEE) != 0;
+    if ((flags & NRCU_FLAG_ENV_IS) && s->env_rgba && s->mode == NRCU_MODE_ACC) {
+        if (!s->env_sin) env_build_tables((nro_scene*)s);
+        if (s->env_total > 0.f) c->nee = 2;
+    }
     if (!pixels) n_pixels = s->width * s->height;
     parallel_for(n_pixels, 64, pt_body, c);
     uint64_t total = 0;

@@ -71,3 +71,24 @@ def lens_small(fs):
 def lens_wide(fs):
     fs.cam_aperture = 6.0             # a visibly defocused view: lens radius 3, focused on the back of the box
     fs.cam_focus_distance = 900.0
+
+
+def env_sun(fs, w=64, h=32):
+    """Environment map with a small very bright region (a 'sun') over a dim sky: the case importance sampling exists for."""
+    rng = np.random.default_rng(5)
+    tex = rng.uniform(0.02, 0.2, (h, w, 4)).astype(np.float32)
+    tex[5:8, 10:14, :3] = 60.0
+    tex[20:22, 40:50, :3] = [8, 4, 1]
+    fs.add_texture(tex)
+    fs.ambient_type, fs.ambient_environment_map = 1, 0
+
+
+def env_smooth(fs, w=64, h=32):
+    y, x = np.linspace(0, 1, h)[:, None], np.linspace(0, 1, w)[None, :]
+    tex = np.stack([0.5 + 0.5 * np.sin(6.28 * x) * np.ones_like(y), 0.3 + 0.7 * y * np.ones_like(x), 0.2 + 0.8 * (x * y), np.ones((h, w))], -1)
+    fs.add_texture(tex.astype(np.float32))
+    fs.ambient_type, fs.ambient_environment_map = 1, 0
+
+
+def diffuse_spheres(fs):
+    fs.sphere_material[:] = fs.add_material(0, diffuse_color=[0.7, 0.6, 0.5])

@@ -26,6 +26,7 @@ struct EmuScene {
     uint32_t spp;
     std::vector<float> mesh_pos;
     std::vector<f4> geom, shade, box, nodes, env, leaf_geom, leaf_box, big_geom, big_box, big_bound, bound;
+    std::vector<float> env_tab;
     std::vector<uint32_t> big_meta;
     int n_big = 0;
     std::vector<uint32_t> meta, leaf_prims;
@@ -138,6 +139,10 @@ EmuScene* emu_create(const nrcu_scene* sc, int mode) {
             es->env.resize(cnt);
             std::memcpy(es->env.data(), sc->texture_rgba + sc->texture_offset[ti], cnt * sizeof(f4));
             ds.env_rgba = es->env.data(); ds.env_w = (int)sc->texture_width[ti]; ds.env_h = (int)sc->texture_height[ti];
+            es->env_tab.assign(2 * (size_t)ds.env_h + cnt, 0.f);   // the k_env_rows / k_env_marginal work items, one after the other
+            for (int y = 0; y < ds.env_h; y++) env_table_row(ds.env_rgba, ds.env_w, ds.env_h, y, es->env_tab.data());
+            ds.env_total = env_table_marginal(ds.env_h, es->env_tab.data());
+            ds.env_tab = es->env_tab.data();
         }
     }
     if (mode != NRCU_MODE_RAYCAST && n > 0) emu_build_bvh(*es);
@@ -192,7 +197,8 @@ void emu_render_raycast(EmuScene* es, float* rgba) {
 // that split (glass branch mode) go through a small stack.  accum: w*h*4 (or n_pixels*4), sums + count.
 void emu_render_pt(EmuScene* es, uint64_t seed, uint32_t s0, uint32_t s1, int glass_branch,
                    const uint32_t* pixels, uint32_t n_pixels, float* accum4, uint64_t* rays_out, uint32_t flags) {
-    es->ds.nee = (flags & NRCU_FLAG_NEE) && es->ds.n_area_lights > 0;
+    es->ds.nee = ((flags & NRCU_FLAG_ENV_IS) && es->ds.mode == MODE_ACC && es->ds.env_tab && es->ds.env_total > 0.f) ? 2
+               : (((flags & NRCU_FLAG_NEE) && es->ds.n_area_lights > 0) ? 1 : 0);
     const DScene& ds = es->ds;
     if (s0 == 0 && s1 == 0) s1 = es->spp;
     uint64_t rays = 0;

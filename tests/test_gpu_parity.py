@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, env_texture, glassify, lens_small, lens_wide, load_scene, microfacet, random_rays
+from conftest import GOLDEN, diffuse_spheres, env_smooth, env_sun, env_texture, glassify, lens_small, lens_wide, load_scene, microfacet, random_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -529,3 +529,45 @@ def test_branching_glass_queue_overflow_retries_or_fails_loudly(ctx):
     np.testing.assert_allclose(big[..., :3], ref[..., :3], rtol=2e-4, atol=1e-6)   # float atomics: order varies
     if st["max_queue"] > cap:
         assert st["wave_retries"] >= 1
+
+
+@pytest.mark.gpu
+def test_env_map_importance_sampling(ctx):
+    """NRCU_FLAG_ENV_IS (extension of the environment-map extension): same-RNG agreement with the oracle's independent C port,
+    the expectation of the plain estimator, and the variance reduction it exists for."""
+    fs = load_scene("env_map_spheres", width=64, height=40, samples_per_pixel=16, depth=6, cam_aspect=1.6)
+    diffuse_spheres(fs)
+    env_sun(fs)
+    ctx.upload(fs, 2)
+    acc, st = accum_device(ctx, seed=3, flags=2, samples_per_wave=4)
+    oacc, orays = oracle(fs, 2).render_pt_accum(seed=3, flags=2)
+    rel = np.abs(acc[..., :3] - oacc[..., :3]) / np.maximum(np.abs(oacc[..., :3]), 1e-3)
+    close = (rel < 1e-3).all(-1)
+    print(f"env IS: {close.mean() * 100:.2f}% pixels within 1e-3 of the oracle, rays {st['rays']} vs {orays}")
+    assert close.mean() >= 0.99 and abs(st["rays"] - orays) <= 2e-3 * orays + 2
+    plain, st0 = accum_device(ctx, seed=3)
+    assert st["rays"] > st0["rays"]
+    # same expectation (smooth map, 2048 spp) ...
+    fs = load_scene("env_map_spheres", width=64, height=40, samples_per_pixel=2048, depth=6, cam_aspect=1.6)
+    diffuse_spheres(fs)
+    env_smooth(fs)
+    ctx.upload(fs, 2)
+    a, _ = accum_device(ctx, seed=1, flags=2)
+    b, _ = accum_device(ctx, seed=1)
+    lit = np.abs(a - b)[..., :3].sum(-1) > 0
+    ma, mb = a[lit][:, :3].mean(0), b[lit][:, :3].mean(0)
+    print(f"env IS mean {ma / 2048} vs plain {mb / 2048} on {lit.sum()} sphere pixels")
+    assert np.allclose(ma, mb, rtol=3e-3)
+    # ... and far less noise where the light is concentrated ("sun" map): per-pixel variance between independent slices
+    fs = load_scene("env_map_spheres", width=64, height=40, samples_per_pixel=8 * 64, depth=4, cam_aspect=1.6)
+    diffuse_spheres(fs)
+    env_sun(fs)
+    ctx.upload(fs, 2)
+
+    def slice_var(flags):
+        sl = np.stack([accum_device(ctx, seed=9, s0=64 * k, s1=64 * (k + 1), flags=flags)[0][..., :3] / 64 for k in range(8)])
+        return sl.var(0, ddof=1)[lit].mean(), sl.mean(0)[lit].mean()
+    (v_is, m_is), (v_pl, m_pl) = slice_var(2), slice_var(0)
+    print(f"sun map: variance of a 64-spp estimate {v_is:.3e} (importance sampled) vs {v_pl:.3e} (plain); means {m_is:.4f} / {m_pl:.4f}")
+    assert v_is < 0.2 * v_pl
+    assert abs(m_is - m_pl) < 0.1 * m_pl          # 512 spp of a heavy-tailed estimator: loose, the tight check is the smooth map above

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, glassify, load_scene, microfacet
+from conftest import GOLDEN, diffuse_spheres, env_smooth, env_sun, glassify, load_scene, microfacet
 from oracle import pyoracle as po
 
 
@@ -132,3 +132,30 @@ def test_nee_port_equals_the_host_build_of_the_device_code(name, mode, depth, gl
     assert (rel < 1e-3).all(-1).mean() >= 0.99
     plain, prays = po.OracleScene(fs, mode).render_pt_accum(seed=17, glass_mode=glass)
     assert orays > prays and not np.array_equal(plain, o)
+
+
+def test_env_importance_sampling_port_and_expectation():
+    """NRCU_FLAG_ENV_IS (extension): the oracle's C restatement equals the host build of the device code on the same RNG,
+    and the estimator has the expectation of the plain miss lookup (smooth map: both converge; agreement to 1e-3)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+    import pyemu
+    fs = load_scene("env_map_spheres", width=40, height=24, samples_per_pixel=12, depth=6, cam_aspect=40 / 24)
+    diffuse_spheres(fs)
+    env_sun(fs)
+    o, orays = po.OracleScene(fs, 2).render_pt_accum(seed=3, flags=2)
+    e, erays = pyemu.EmuScene(fs, 2).render_pt_accum(seed=3, flags=2)
+    plain, prays = po.OracleScene(fs, 2).render_pt_accum(seed=3)
+    assert orays == erays and orays > prays                      # shadow rays towards the map are counted
+    rel = np.abs(o[..., :3] - e[..., :3]) / np.maximum(np.abs(e[..., :3]), 1e-3)
+    assert (rel < 1e-3).all(-1).mean() >= 0.99
+    fs = load_scene("env_map_spheres", width=40, height=24, samples_per_pixel=1024, depth=6, cam_aspect=40 / 24)
+    diffuse_spheres(fs)
+    env_smooth(fs)
+    osc = po.OracleScene(fs, 2)
+    a, _ = osc.render_pt_accum(seed=1, flags=2)
+    b, _ = osc.render_pt_accum(seed=1)
+    lit = np.abs(a - b)[..., :3].sum(-1) > 0                     # pixels that see a sphere
+    assert lit.mean() > 0.03
+    ma, mb = a[lit][:, :3].mean(0), b[lit][:, :3].mean(0)
+    assert np.allclose(ma, mb, rtol=3e-3), (ma, mb)
