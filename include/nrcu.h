@@ -289,6 +289,30 @@ int nrcu_render_progressive(nrcu_ctx* ctx, const nrcu_render_params* params, uin
  * devices; ms_* = maximum over the devices. */
 int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params* params, float* rgba_out, nrcu_stats* stats);
 
+/* Metropolis light transport (counterpart of the reference's MetropolisLightTransport component,
+ * components/metropolis_light_transport/src/Metropolis.cpp:25-135): Kelemen-style Markov chains in primary sample space -
+ * large steps with probability large_step_prob, the reference's exponential small-step perturbation, expected-value
+ * accumulation, b from n_init independent samples - driving THIS backend's path sampler (the scene's own materials and
+ * lights; the reference's sampler is bidirectional with hard-coded colours).  The frame has the expectation of nrcu_render's.
+ * One chain per GPU thread; the scene must have been uploaded in NRCU_MODE_SIMPLE or NRCU_MODE_ACC, depth <= 32. */
+enum nrcu_mlt_tone {
+    NRCU_MLT_TONE_SQRT = 0,       /* sqrt, like the path tracers (AccPathTracer.cpp:14-16) */
+    NRCU_MLT_TONE_REFERENCE = 1,  /* pow(1 - exp(-x), 1/2.2), the reference MLT's own (Metropolis.cpp:118-123) */
+    NRCU_MLT_TONE_LINEAR = 2      /* none: linear radiance (what the tests compare with the path tracer's mean) */
+};
+typedef struct nrcu_mlt_params {
+    uint64_t seed;
+    uint32_t mutations_per_pixel; /* total mutations = this x width x height; 0 = the scene's samples_per_pixel */
+    uint32_t chains;              /* 0 = automatic (at most 2^18, at least 64 mutations per chain) */
+    uint32_t n_init;              /* samples that estimate b; 0 = 262144 (the reference uses 10000) */
+    float large_step_prob;        /* 0 = the reference's 0.3 */
+    uint32_t tone_map;            /* nrcu_mlt_tone */
+    uint32_t reserved;
+} nrcu_mlt_params;
+/* stats: paths = mutations, rays as counted by the chains, max_queue = chains, iterations = mutations per chain,
+ * wave_retries = accepted mutations / 1024. */
+int nrcu_render_mlt(nrcu_ctx* ctx, const nrcu_mlt_params* params, float* rgba_out, nrcu_stats* stats);
+
 /* d_rgba[p] = (sqrt(d_accum[p].rgb / d_accum[p].a), 1); both DEVICE pointers; may alias. */
 int nrcu_resolve(nrcu_ctx* ctx, const float* d_accum, float* d_rgba);
 

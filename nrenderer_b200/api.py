@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(PKG, "libnrcuda.so")
 ABI_SYMBOLS = [
     "nrcu_abi_version", "nrcu_device_count", "nrcu_create", "nrcu_destroy", "nrcu_last_error", "nrcu_upload_scene",
     "nrcu_primitive_count", "nrcu_download_primitives", "nrcu_render", "nrcu_render_accumulate", "nrcu_resolve",
-    "nrcu_render_multi", "nrcu_render_progressive", "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
+    "nrcu_render_multi", "nrcu_render_progressive", "nrcu_render_mlt", "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
 ]
 
 
@@ -47,6 +47,12 @@ class NrcuStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class NrcuMltParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("mutations_per_pixel", C.c_uint32), ("chains", C.c_uint32), ("n_init", C.c_uint32),
+                ("large_step_prob", C.c_float), ("tone_map", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+MLT_TONE_SQRT, MLT_TONE_REFERENCE, MLT_TONE_LINEAR = 0, 1, 2
 UPDATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 _LIB = None
 
@@ -75,6 +81,7 @@ def load_library() -> C.CDLL:
     L.nrcu_render_accumulate.argtypes = [vp, vp, vp, vp]
     L.nrcu_render_multi.argtypes = [vp, i32, vp, vp, vp]
     L.nrcu_render_progressive.argtypes = [vp, vp, u32, vp, UPDATE_FN, vp, vp]
+    L.nrcu_render_mlt.argtypes = [vp, vp, vp, vp]
     L.nrcu_resolve.argtypes = [vp, vp, vp]
     L.nrcu_trace_batch.argtypes = [vp, vp, u32, vp, vp]
     L.nrcu_set_stream.argtypes = [vp, vp]
@@ -161,6 +168,15 @@ class Context:
         assert out.dtype == np.float32 and out.size == self.width * self.height * 4 and out.flags.c_contiguous
         p, st = self._params(seed, 0, 0, glass_mode, samples_per_wave, flags, scheduler), NrcuStats()
         self._check(self._lib.nrcu_render(self._h, C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render")
+        return out, st.as_dict()
+
+    def render_mlt(self, seed=0, mutations_per_pixel=0, chains=0, n_init=0, large_step_prob=0.0, tone_map=MLT_TONE_SQRT, out: np.ndarray | None = None):
+        """nrcu_render_mlt: Metropolis light transport over this backend's path sampler. Returns (rgba[h,w,4], stats dict)."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        p, st = NrcuMltParams(seed=seed, mutations_per_pixel=mutations_per_pixel, chains=chains, n_init=n_init,
+                              large_step_prob=large_step_prob, tone_map=tone_map), NrcuStats()
+        self._check(self._lib.nrcu_render_mlt(self._h, C.addressof(p), out.ctypes.data, C.addressof(st)), "nrcu_render_mlt")
         return out, st.as_dict()
 
     def render_progressive(self, on_update, samples_per_update=0, seed=0, glass_mode=0, out: np.ndarray | None = None):

@@ -16,7 +16,7 @@ REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libnrcuda.so")
 PLUGIN_DIR = os.path.join(PKG, "plugin")
-PLUGINS = {0: "CudaRayCast", 1: "CudaSimplePathTracer", 2: "CudaAccPathTracer"}
+PLUGINS = {0: "CudaRayCast", 1: "CudaSimplePathTracer", 2: "CudaAccPathTracer", 3: "CudaMetropolisLightTransport"}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

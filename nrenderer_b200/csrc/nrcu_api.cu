@@ -1187,6 +1187,67 @@ int nrcu_render_multi(nrcu_ctx* const* ctxs, int n_ctx, const nrcu_render_params
     return NRCU_OK;
 }
 
+int nrcu_render_mlt(nrcu_ctx* ctx, const nrcu_mlt_params* params, float* rgba_out, nrcu_stats* stats) {
+    if (!ctx) return NRCU_ERR_INVALID;
+    if (!ctx->have_scene) { ctx->error = "nrcu_render_mlt: no scene uploaded"; return NRCU_ERR_STATE; }
+    if (!rgba_out) { ctx->error = "rgba_out is null"; return NRCU_ERR_INVALID; }
+    if (ctx->mode == NRCU_MODE_RAYCAST) { ctx->error = "nrcu_render_mlt needs a scene uploaded in a path-tracing mode"; return NRCU_ERR_STATE; }
+    const DScene& ds = ctx->ds;
+    if (ds.depth > NRCU_MLT_MAX_DEPTH) { ctx->error = "nrcu_render_mlt: depth > 32"; return NRCU_ERR_INVALID; }
+    CTX_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t npix = ds.width * ds.height;
+    const uint64_t seed = params ? params->seed : 0;
+    const uint32_t mpp = params && params->mutations_per_pixel ? params->mutations_per_pixel : ctx->spp;
+    const uint64_t total = (uint64_t)mpp * npix;
+    uint32_t chains = params && params->chains ? params->chains : (uint32_t)std::min<uint64_t>(1u << 18, std::max<uint64_t>(1, total / 64));
+    chains = (uint32_t)std::min<uint64_t>(chains, std::max<uint64_t>(total, 1));
+    const uint32_t per_chain = (uint32_t)std::min<uint64_t>(0x7fffffffu, (total + chains - 1) / std::max(chains, 1u));
+    const uint32_t n_init = params && params->n_init ? params->n_init : (1u << 18);
+    const float p_large = params && params->large_step_prob > 0.f ? std::min(params->large_step_prob, 1.f) : 0.3f;
+    const int tone = params ? (int)params->tone_map : 0;
+    CTX_CUDA(ctx->rgba_dev.ensure(sizeof(f4) * (size_t)npix));
+    CTX_CUDA(ctx->accum_own.ensure(sizeof(f4) * (size_t)npix));
+    CTX_CUDA(ctx->ws[0].counters.ensure(sizeof(uint32_t) * 64));
+    unsigned long long* d_cnt = ctx->ws[0].counters.as<unsigned long long>();         // [0] rays, [1] accepted mutations
+    DevBuf& scratch = ctx->ws[0].hits;                                                // b-estimation: n_init floats + n_init doubles
+    CTX_CUDA(scratch.ensure(sizeof(double) * (size_t)n_init + sizeof(float) * (size_t)n_init + 16));
+    double* d_cdf = scratch.as<double>();
+    float* d_scalar = reinterpret_cast<float*>(d_cdf + n_init);
+    CTX_CUDA(cudaMemsetAsync(ctx->ws[0].counters.p, 0, 32, st));
+    CTX_CUDA(cudaMemsetAsync(ctx->accum_own.p, 0, sizeof(f4) * (size_t)npix, st));
+    const uint64_t launches0 = ctx->launches;
+    const bool gate = ctx->mode == NRCU_MODE_ACC;
+    CTX_CUDA(cudaEventRecord(ctx->ev_begin, st));
+    if (total > 0) {
+        if (gate) k_mlt_b<true><<<grid_for(n_init, 128), 128, 0, st>>>(ds, seed, n_init, d_scalar, d_cnt);
+        else k_mlt_b<false><<<grid_for(n_init, 128), 128, 0, st>>>(ds, seed, n_init, d_scalar, d_cnt);
+        CTX_LAUNCH_CHECK("k_mlt_b");
+        k_mlt_cdf<<<1, 1024, 0, st>>>(d_scalar, n_init, d_cdf);
+        CTX_LAUNCH_CHECK("k_mlt_cdf");
+        if (gate) k_mlt_chains<true><<<grid_for(chains, 128), 128, 0, st>>>(ds, seed, chains, per_chain, d_cdf, n_init, p_large, ctx->accum_own.as<f4>(), d_cnt);
+        else k_mlt_chains<false><<<grid_for(chains, 128), 128, 0, st>>>(ds, seed, chains, per_chain, d_cdf, n_init, p_large, ctx->accum_own.as<f4>(), d_cnt);
+        CTX_LAUNCH_CHECK("k_mlt_chains");
+    }
+    const double n_mut = (double)chains * per_chain;
+    const float scale = n_mut > 0 ? (float)(((double)ds.width + 2.0) * ((double)ds.height + 2.0) / (4.0 * n_mut)) : 0.f;
+    k_mlt_resolve<<<grid_for(npix, 256), 256, 0, st>>>(ctx->accum_own.as<f4>(), ctx->rgba_dev.as<f4>(), npix, scale, tone);
+    CTX_LAUNCH_CHECK("k_mlt_resolve");
+    CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
+    CTX_CUDA(cudaMemcpyAsync(rgba_out, ctx->rgba_dev.p, sizeof(f4) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+    unsigned long long h_cnt[2] = {0, 0};
+    CTX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        CTX_CUDA(cudaEventElapsedTime(&stats->ms_total, ctx->ev_begin, ctx->ev_end));
+        stats->paths = total ? (uint64_t)n_mut : 0; stats->rays = h_cnt[0]; stats->kernel_launches = ctx->launches - launches0;
+        stats->ms_trace = stats->ms_total; stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
+        stats->max_queue = chains; stats->iterations = per_chain; stats->wave_retries = (uint32_t)std::min<unsigned long long>(0xffffffffull, h_cnt[1] >> 10);
+    }
+    return check_overflow(ctx);
+}
+
 int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim_id, float* t) {
     if (!ctx) return NRCU_ERR_INVALID;
     if (!ctx->have_scene) { ctx->error = "nrcu_trace_batch: no scene uploaded"; return NRCU_ERR_STATE; }

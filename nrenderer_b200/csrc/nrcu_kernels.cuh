@@ -6,6 +6,7 @@
 #include "nrcu_bvh.cuh"
 #include "nrcu_prep.cuh"
 #include "nrcu_shade.cuh"
+#include "nrcu_mlt.cuh"
 
 namespace nrcu {
 
@@ -487,6 +488,128 @@ __global__ void __launch_bounds__(NRCU_TRACE_THREADS) k_trace3(DScene s, PathQue
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Metropolis light transport (bodies in nrcu_mlt.cuh): one Markov chain per thread
+// ---------------------------------------------------------------------------------------------
+// numbers of mutation `mut` of chain `chain`: [0] large-step decision, [1] acceptance, [2 + i] state i
+struct MltNumbers {
+    uint64_t seed; uint32_t chain, mut, stream; u32x4 blk; uint32_t have;
+    __device__ __forceinline__ MltNumbers(uint64_t sd, uint32_t c, uint32_t m, uint32_t st) : seed(sd), chain(c), mut(m), stream(st), have(0xffffffffu) {}
+    __device__ __forceinline__ float get(uint32_t k) {
+        if ((k >> 2) != have) { have = k >> 2; blk = rng_block(seed, chain, mut, stream, have); }
+        const uint32_t c = k & 3u;
+        return u01(c == 0 ? blk.x : (c == 1 ? blk.y : (c == 2 ? blk.z : blk.w)));
+    }
+};
+// film coordinate (pixel units) -> the (up to) four pixels whose two-pixel-wide footprint contains it; row 0 = top
+__device__ __forceinline__ void mlt_splat(f4* film, const DScene& s, float fx, float fy, vec3 c, float wgt) {
+    if (!(wgt > 0.f) || !(wgt < NRCU_INF)) return;
+    const int j0 = (int)floorf(fx), i0 = (int)floorf(fy);
+    for (int dj = 0; dj < 2; dj++) for (int di = 0; di < 2; di++) {
+        const int j = j0 + dj, i = i0 + di;
+        if (j < 0 || j >= (int)s.width || i < 0 || i >= (int)s.height) continue;
+        f4* px = film + (size_t)((int)s.height - 1 - i) * s.width + j;
+        atomicAdd(&px->x, c.x * wgt); atomicAdd(&px->y, c.y * wgt); atomicAdd(&px->z, c.z * wgt);
+    }
+}
+// b = mean scalar contribution of independent samples (Metropolis.cpp:83-92, N_Init).  The scalar contribution of every
+// sample is kept: the chains start from samples drawn in proportion to it (below), their numbers being reproducible from
+// (seed, sample index).
+__device__ __forceinline__ void mlt_init_numbers(uint64_t seed, uint32_t sample, uint32_t ns, float* u) {
+    MltNumbers rn(seed, sample, 0u, NRCU_STREAM_MLT - 1u);
+    for (uint32_t k = 0; k < ns; k++) u[k] = rn.get(k);
+}
+template <bool GATE>
+__global__ void __launch_bounds__(128) k_mlt_b(DScene s, uint64_t seed, uint32_t n_samples, float* scalar, unsigned long long* ray_counter) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t rays = 0;
+    if (i < n_samples) {
+        float u[NRCU_MLT_STATES(NRCU_MLT_MAX_DEPTH)];
+        mlt_init_numbers(seed, i, NRCU_MLT_STATES(s.depth), u);
+        float fx, fy;
+        scalar[i] = mlt_scalar(mlt_eval<GATE>(s, u, fx, fy, rays));
+    }
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, o);
+    if ((threadIdx.x & 31) == 0 && rays) atomicAdd(ray_counter, (unsigned long long)rays);
+}
+// Inclusive prefix sums (double) of the n scalar contributions, one block: cdf[i] = sum_{j<=i} scalar[j]; cdf[n-1] = n b.
+__global__ void __launch_bounds__(1024) k_mlt_cdf(const float* scalar, uint32_t n, double* cdf) {
+    __shared__ double part[1024];
+    const uint32_t per = (n + 1023u) / 1024u, lo = threadIdx.x * per, hi = min(n, lo + per);
+    double sum = 0.0;
+    for (uint32_t i = lo; i < hi; i++) sum += (double)scalar[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { double run = 0.0; for (int t = 0; t < 1024; t++) { double v = part[t]; part[t] = run; run += v; } }
+    __syncthreads();
+    double run = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; i++) { run += (double)scalar[i]; cdf[i] = run; }
+}
+// The chains (Metropolis.cpp:25-69).  counters: [0] rays, [1] accepted mutations.  A chain starts from one of the b-estimation
+// samples, drawn with probability proportional to its scalar contribution: the chain is then in its stationary
+// distribution from the first mutation on, which the expected-value weights below assume - the reference starts ONE long
+// chain anywhere and lets 2 M mutations forget the start; a GPU runs 10^5 short chains, where that start-up bias would
+// darken the frame.
+template <bool GATE>
+__global__ void __launch_bounds__(128) k_mlt_chains(DScene s, uint64_t seed, uint32_t n_chains, uint32_t mutations, const double* cdf, uint32_t n_init,
+                                                  float p_large, f4* film, unsigned long long* counters) {
+    const uint32_t chain = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t rays = 0, accepted = 0;
+    const double total = cdf[n_init - 1];
+    const float b = (float)(total / (double)n_init);
+    if (chain < n_chains && b > 0.f) {
+        const uint32_t ns = NRCU_MLT_STATES(s.depth);
+        float cur[NRCU_MLT_STATES(NRCU_MLT_MAX_DEPTH)], prop[NRCU_MLT_STATES(NRCU_MLT_MAX_DEPTH)];
+        float cfx, cfy;
+        {
+            MltNumbers rn(seed, chain, 0u, NRCU_STREAM_MLT);
+            const double target = ((double)rn.get(0) + (double)rn.get(1) * (1.0 / 16777216.0)) * total;   // 48 random bits
+            uint32_t lo = 0, hi = n_init - 1;
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (target < cdf[mid]) hi = mid; else lo = mid + 1; }
+            mlt_init_numbers(seed, lo, ns, cur);
+        }
+        vec3 Lc = mlt_eval<GATE>(s, cur, cfx, cfy, rays);
+        float Ic = mlt_scalar(Lc);
+        const float s1f = 2.0f / (float)(s.width + s.height);
+        for (uint32_t m = 1; m <= mutations; m++) {
+            MltNumbers rn(seed, chain, m, NRCU_STREAM_MLT);
+            const bool large = rn.get(0) <= p_large;
+            const float r_acc = rn.get(1);
+            if (large) for (uint32_t k = 0; k < ns; k++) prop[k] = rn.get(2u + k);                 // large_step: a fresh path
+            else {
+                prop[0] = mlt_perturb(cur[0], s1f, 0.1f, rn.get(2)); prop[1] = mlt_perturb(cur[1], s1f, 0.1f, rn.get(3));   // the pixel location
+                for (uint32_t k = 2; k < ns; k++) prop[k] = mlt_perturb(cur[k], 1.0f / 1024.0f, 1.0f / 64.0f, rn.get(2u + k));
+            }
+            float pfx, pfy;
+            const vec3 Lp = mlt_eval<GATE>(s, prop, pfx, pfy, rays);
+            const float Ip = mlt_scalar(Lp);
+            // the reference leaves `a` uninitialised when the current path carries nothing; a dark state is always left
+            const float a = Ic > 0.f ? fminf(1.f, Ip / Ic) : 1.f;
+            if (Ip > 0.f) mlt_splat(film, s, pfx, pfy, Lp, (a + (large ? 1.f : 0.f)) / (Ip / b + p_large));
+            if (Ic > 0.f) mlt_splat(film, s, cfx, cfy, Lc, (1.f - a) / (Ic / b + p_large));
+            if (r_acc <= a) {
+                for (uint32_t k = 0; k < ns; k++) cur[k] = prop[k];
+                Lc = Lp; Ic = Ip; cfx = pfx; cfy = pfy; accepted++;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { rays += __shfl_down_sync(0xffffffffu, rays, o); accepted += __shfl_down_sync(0xffffffffu, accepted, o); }
+    if ((threadIdx.x & 31) == 0) { if (rays) atomicAdd(counters, (unsigned long long)rays); if (accepted) atomicAdd(counters + 1, (unsigned long long)accepted); }
+}
+// film sums -> frame: x scale (film area / (4 mutations): every film sample lies in four pixel footprints), then the tone map:
+// 0 sqrt (the path tracers' gamma, AccPathTracer.cpp:14-16), 1 the reference MLT's pow(1 - exp(-x), 1/2.2) (Metropolis.cpp:118-123), 2 none
+__global__ void k_mlt_resolve(const f4* film, f4* rgba, uint32_t npix, float scale, int tone) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    f4 v = film[p];
+    float c[3] = {v.x * scale, v.y * scale, v.z * scale};
+    for (int k = 0; k < 3; k++) {
+        if (tone == 0) c[k] = sqrtf(c[k]);
+        else if (tone == 1) c[k] = powf(1.f - expf(-c[k]), 1.f / 2.2f);
+    }
+    rgba[p] = mk4(c[0], c[1], c[2], 1.f);
 }
 
 // Brute-force variant for the RayCast-mode parity probe (nrcu_trace_batch in NRCU_MODE_RAYCAST).

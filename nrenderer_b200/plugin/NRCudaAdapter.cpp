@@ -7,6 +7,8 @@
 // file is compiled three times:  -DNRCU_PLUGIN_MODE=0 -> "CudaRayCast"           (replaces RayCast,          ray_cast/src/Adapter.cpp:11-34)
 //                                -DNRCU_PLUGIN_MODE=1 -> "CudaSimplePathTracer"  (replaces SimplePathTracer, simple_path_tracing/src/Adapter.cpp:13-30)
 //                                -DNRCU_PLUGIN_MODE=2 -> "CudaAccPathTracer"     (replaces AccPathTracer,    acc_path_tracing/src/Adapter.cpp:13-30)
+//                                -DNRCU_PLUGIN_MODE=3 -> "CudaMetropolisLightTransport" (counterpart of MetropolisLightTransport,
+//                                                        metropolis_light_transport/src/Adapter.cpp:13-36: nrcu_render_mlt, the reference MLT's tone map)
 // render() never throws and treats the Scene as read-only (the reference components mutate it in
 // place); the frame is published through getServer().screen.set exactly like ray_cast/src/Adapter.cpp:15-19.
 // It is compiled by g++ against the reference's headers and talks to the kernels only through the
@@ -27,6 +29,13 @@
 
 #ifndef NRCU_PLUGIN_MODE
 #define NRCU_PLUGIN_MODE 2
+#endif
+// the scene mode the component uploads with: the Metropolis component samples paths like SimplePathTracer's closest hit
+// (brute-force semantics, no leaf gate: metropolis_light_transport/src/Metropolis.cpp:143-177) with AccPathTracer's materials
+#if NRCU_PLUGIN_MODE == 3
+#define NRCU_SCENE_MODE NRCU_MODE_ACC
+#else
+#define NRCU_SCENE_MODE NRCU_PLUGIN_MODE
 #endif
 
 using namespace NRenderer;
@@ -79,7 +88,7 @@ namespace NRCuda
                     }
                     sh.ctx_device = dev;
                 }
-                if (nrcu_upload_scene(sh.ctx, &view, NRCU_PLUGIN_MODE) != NRCU_OK) {
+                if (nrcu_upload_scene(sh.ctx, &view, NRCU_SCENE_MODE) != NRCU_OK) {
                     logger.error(std::string("NRCuda: ") + nrcu_last_error(sh.ctx));
                     publishBlack(w, h);
                     return;
@@ -102,7 +111,7 @@ namespace NRCuda
                             }
                             it = sh.extra.emplace(d, c).first;
                         }
-                        if (nrcu_upload_scene(it->second, &view, NRCU_PLUGIN_MODE) != NRCU_OK) {
+                        if (nrcu_upload_scene(it->second, &view, NRCU_SCENE_MODE) != NRCU_OK) {
                             logger.warning("NRCuda: device " + std::to_string(d) + " skipped: " + nrcu_last_error(it->second));
                             continue;
                         }
@@ -118,6 +127,15 @@ namespace NRCuda
                 RGBA* pixels = new RGBA[(size_t)w * h];   // plugin owns the buffer, Screen::set copies it (RayCastRenderer.cpp:7-10)
                 int rc;
                 const char* prog = std::getenv("NRCU_PROGRESSIVE");
+#if NRCU_PLUGIN_MODE == 3
+                nrcu_mlt_params mp{};
+                mp.seed = params.seed;
+                mp.tone_map = NRCU_MLT_TONE_REFERENCE;           // Metropolis.cpp:118-123
+                if (const char* e = std::getenv("NRCU_MLT_MUTATIONS_PER_PIXEL")) mp.mutations_per_pixel = (uint32_t)std::atoi(e);
+                if (const char* e = std::getenv("NRCU_MLT_TONE")) mp.tone_map = (uint32_t)std::atoi(e);
+                (void)prog;
+                rc = nrcu_render_mlt(sh.ctx, &mp, reinterpret_cast<float*>(pixels), &st);
+#else
                 if (prog && std::atoi(prog) > 0 && devs.size() == 1) {
                     // publish intermediate frames: the GUI re-uploads whenever Screen::isUpdated() (ScreenView.cpp:168-173)
                     struct Pub { unsigned w, h; } pub{w, h};
@@ -128,6 +146,7 @@ namespace NRCuda
                                                      return 0;
                                                  }, &pub, &st);
                 } else rc = nrcu_render_multi(devs.data(), (int)devs.size(), &params, reinterpret_cast<float*>(pixels), &st);
+#endif
                 if (rc != NRCU_OK) {
                     std::string why = nrcu_last_error(sh.ctx);   // the root context carries "device N: ..." for a failed peer
                     for (size_t g = 1; g < devs.size(); g++) {
@@ -170,6 +189,11 @@ const static std::string description =
     "CUDA (sm_100a) wavefront path tracer, SimplePathTracer semantics:\n"
     "Lambertian only, uniform hemisphere sampling, area lights hit by chance.";
 REGISTER_RENDERER(CudaSimplePathTracer, description, NRCuda::Adapter);
+#elif NRCU_PLUGIN_MODE == 3
+const static std::string description =
+    "CUDA (sm_100a) Metropolis light transport in primary sample space\n"
+    "(one Markov chain per GPU thread over the path tracer's sampler).";
+REGISTER_RENDERER(CudaMetropolisLightTransport, description, NRCuda::Adapter);
 #else
 const static std::string description =
     "CUDA (sm_100a) wavefront path tracer, AccPathTracer semantics:\n"

@@ -49,7 +49,7 @@ def test_fixtures_are_what_the_reference_importers_produce(tmp_path):
 def test_cuda_plugins_register_through_the_reference_factory():
     """The adapters load next to the reference's own plugins and register under their names."""
     from nrenderer_b200 import build
-    plugins = [build.plugin_path(m) for m in (0, 1, 2)]
+    plugins = [build.plugin_path(m) for m in (0, 1, 2, 3)]
     if not all(os.path.exists(p) for p in plugins):
         pytest.skip("plugin adapters not built")
     cmd = [os.path.join(po.REF_DIR, "nr_headless"), "--list"]
@@ -57,7 +57,7 @@ def test_cuda_plugins_register_through_the_reference_factory():
         cmd += ["--plugin", p]
     env = dict(os.environ, LD_LIBRARY_PATH=po.REF_DIR)
     names = set(subprocess.run(cmd, capture_output=True, text=True, check=True, env=env).stdout.split())
-    assert {"CudaRayCast", "CudaSimplePathTracer", "CudaAccPathTracer", "RayCast", "SimplePathTracer", "AccPathTracer"} <= names
+    assert {"CudaRayCast", "CudaSimplePathTracer", "CudaAccPathTracer", "CudaMetropolisLightTransport", "RayCast", "SimplePathTracer", "AccPathTracer"} <= names
 
 
 @pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")

@@ -571,3 +571,35 @@ def test_env_map_importance_sampling(ctx):
     print(f"sun map: variance of a 64-spp estimate {v_is:.3e} (importance sampled) vs {v_pl:.3e} (plain); means {m_is:.4f} / {m_pl:.4f}")
     assert v_is < 0.2 * v_pl
     assert abs(m_is - m_pl) < 0.1 * m_pl          # 512 spp of a heavy-tailed estimator: loose, the tight check is the smooth map above
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,mode,depth", [("path_tracing_cornel", 1, 5), ("pt_glass", 2, 6)])
+def test_metropolis_frame_has_the_expectation_of_the_path_traced_frame(ctx, name, mode, depth):
+    """nrcu_render_mlt (counterpart of components/metropolis_light_transport): Markov chains in primary sample
+    space over the path tracer's own sampler.  No parity contract with the reference's MLT (bidirectional sampler, hard-coded
+    colours, racy threads) - the check is that the Metropolis frame converges to the frame nrcu_render converges to."""
+    from nrenderer_b200 import api
+    w, h, spp = 48, 40, 4096
+    fs = load_scene(name, width=w, height=h, samples_per_pixel=spp, depth=depth, cam_aspect=w / h)
+    ctx.upload(fs, mode)
+    acc, _ = accum_device(ctx, seed=1)
+    pt = acc[..., :3] / acc[..., 3:4]
+    mlt, st = ctx.render_mlt(seed=2, mutations_per_pixel=spp, tone_map=api.MLT_TONE_LINEAR)
+    acceptance = st["wave_retries"] * 1024 / max(st["paths"], 1)
+    rel_mean = abs(mlt[..., :3].mean() - pt.mean()) / pt.mean()
+    # block-averaged comparison (4x4 pixels): both estimates are noisy per pixel, the structure of the image must agree
+    blk = lambda a: a[: h // 4 * 4, : w // 4 * 4].reshape(h // 4, 4, w // 4, 4, 3).mean((1, 3))
+    a, b = blk(mlt[..., :3]), blk(pt)
+    corr = np.corrcoef(a.reshape(-1), b.reshape(-1))[0, 1]
+    rel_rmse = np.sqrt(((a - b) ** 2).mean()) / b.mean()
+    print(f"MLT {name}: {st['paths']} mutations on {st['max_queue']} chains, acceptance {acceptance:.2f}, rays/mutation {st['rays'] / st['paths']:.2f}, "
+          f"{st['ms_total']:.1f} ms; mean {mlt[..., :3].mean():.5f} vs path traced {pt.mean():.5f} ({rel_mean * 100:.2f} %), block correlation {corr:.4f}, block rmse {rel_rmse * 100:.1f} %")
+    assert (mlt[..., 3] == 1).all() and np.isfinite(mlt).all() and (mlt[..., :3] >= 0).all()
+    assert 0.02 < acceptance < 0.98 and st["rays"] > st["paths"]
+    assert rel_mean < 0.03
+    assert corr > 0.97 and rel_rmse < 0.25
+    # the reference MLT's tone map and the sqrt gamma are pointwise functions of the linear frame
+    again, _ = ctx.render_mlt(seed=2, mutations_per_pixel=64, tone_map=api.MLT_TONE_LINEAR)
+    toned, _ = ctx.render_mlt(seed=2, mutations_per_pixel=64, tone_map=api.MLT_TONE_REFERENCE)
+    assert np.allclose(toned[..., :3], np.power(1 - np.exp(-again[..., :3].astype(np.float64)), 1 / 2.2), rtol=2e-2, atol=2e-2)   # float atomics: the two runs differ in the last bits

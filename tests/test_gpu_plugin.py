@@ -154,3 +154,24 @@ def test_env_map_from_an_image_file_through_the_reference_loader(tmp_path):
         c.close()
     assert np.array_equal(img.view(np.uint32), np.clip(want, 0, 1).view(np.uint32))
     assert img[..., :3].mean() > 0.05          # lit by the map (the reference renders this scene black)
+
+
+def test_metropolis_plugin_registers_and_renders():
+    """libNRCudaMetropolisLightTransport.so registers "CudaMetropolisLightTransport" (counterpart of the reference's
+    MetropolisLightTransport, metropolis_light_transport/src/Adapter.cpp:36) and publishes a frame in the reference MLT's
+    tone map; with NRCU_MLT_TONE=0 (sqrt) it is comparable with CudaSimplePathTracer's frame."""
+    from nrenderer_b200 import build
+    so = build.plugin_path(3)
+    if not (po.ref_available() and os.path.exists(so)):
+        pytest.fail("plugin adapters not built")
+    fs = load_scene("path_tracing_cornel", width=48, height=40, samples_per_pixel=1024, depth=5, cam_aspect=1.2)
+    img, info = po.run_reference(fs, "CudaMetropolisLightTransport", extra_plugins=[so], env={"NRCU_SEED": "4", "NRCU_MLT_TONE": "0"}, timeout=900)
+    ref, _ = run_plugin(fs, 1, env={"NRCU_SEED": "4"})
+    assert info["errors"] == 0 and img.shape == ref.shape
+    a, b = img[..., :3].astype(np.float64) ** 2, ref[..., :3].astype(np.float64) ** 2     # undo the sqrt gamma (frames were clamped to [0,1] by Screen::set)
+    dark = b.max(-1) < 0.9                                                                   # unclamped pixels
+    rel = abs(a[dark].mean() - b[dark].mean()) / b[dark].mean()
+    print(f"CudaMetropolisLightTransport via the plugin API: {info['seconds']:.3f} s; linear mean {a[dark].mean():.5f} vs CudaSimplePathTracer {b[dark].mean():.5f} ({rel * 100:.2f} %)")
+    assert rel < 0.05
+    toned, info2 = po.run_reference(fs, "CudaMetropolisLightTransport", extra_plugins=[so], env={"NRCU_SEED": "4"}, timeout=900)
+    assert info2["errors"] == 0 and (toned[..., 3] == 1).all() and 0.05 < toned[..., :3].mean() < 0.95
