@@ -17,6 +17,7 @@ import os
 import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
 SMS, SCHEDULERS = 148, 4
 PATHS_PER_WAVE = 32 * 1920 * 1080   # bench.py default workload (cfg3): 64 Mi path slots per wave -> 32 spp of 1080p
 KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
@@ -84,6 +85,11 @@ def main():
     n_waves = sum(1 for d in render if d["kernel"].startswith("k_accumulate"))
     inst_complete = sum(d.get("smsp__inst_executed.sum", 0) for d in render[:last_acc + 1])
     warp_inst_per_path = inst_complete / (n_waves * PATHS_PER_WAVE) if n_waves else None
+    dram_complete = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in render[:last_acc + 1])
+    dram_per_path = dram_complete / (n_waves * PATHS_PER_WAVE) if n_waves else None
+    lane_complete = sum(d.get("smsp__inst_executed.sum", 0) * d.get("smsp__thread_inst_executed_per_inst_executed.ratio", 0) for d in render[:last_acc + 1])
+    import bench   # the hash of the kernel sources this capture was taken from (bench.py prints profile_stale when it differs)
+    csrc_sha = bench.csrc_hash()
     ch = [k for k in kernels if k.startswith(("k_raygen", "k_big", "k_trace"))]
     ch_time = sum(kernels[k]["time_us"] for k in ch)
     ch_inst = sum(kernels[k]["warp_inst"] for k in ch)
@@ -100,6 +106,7 @@ def main():
             hot.append({"kernel": short(r[hdr.index("Kernel Name")]), **{k: r[hdr.index(k)] for k in cols[1:]}})
     summary = {
         "round": rnd,
+        "csrc_sha": csrc_sha,
         "source": {"launch_list": os.path.basename(launch_csv), "captured_launches": len(launches), "full_capture": os.path.basename(raw_csv)},
         "render_kernel_time_us": round(T, 1),
         "kernels": kernels,
@@ -107,7 +114,9 @@ def main():
         # closest-hit DRAM traffic per captured unit of work, and the issue-slot utilisation of the closest-hit kernels:
         # warp instructions issued / (elapsed cycles x 148 SMs x 4 schedulers), clock from the capture (1.965 GHz locked by ncu --clock-control none = application clocks)
         "closest_hit_dram_bytes_per_step_equiv": None,
-        "issue": {"warp_inst_per_path_sample": warp_inst_per_path, "complete_waves_in_capture": n_waves, "paths_per_wave": PATHS_PER_WAVE,
+        "issue": {"warp_inst_per_path_sample": warp_inst_per_path, "dram_bytes_per_path_sample": dram_per_path,
+                  "threads_per_inst_step": round(lane_complete / max(inst_complete, 1), 2),
+                  "complete_waves_in_capture": n_waves, "paths_per_wave": PATHS_PER_WAVE,
                   "closest_hit_warp_inst_per_us": round(ch_inst / ch_time, 1),
                   "peak_warp_inst_per_us_at_1965MHz": SMS * SCHEDULERS * 1965.0,
                   "frac_of_issue_peak": round(ch_inst / ch_time / (SMS * SCHEDULERS * 1965.0), 4),
@@ -121,7 +130,9 @@ def main():
     summary["closest_hit_dram_bytes_per_step_equiv"] = round(ch_dram / max(sum(kernels[k]["launches"] for k in ch if k.startswith("k_raygen")), 1))   # per wave
     json.dump(summary, open(os.path.join(out_dir, f"{rnd}_summary.json"), "w"), indent=1)
     with open(os.path.join(out_dir, f"{rnd}_summary.md"), "w") as f:
-        f.write(f"# {rnd} profile summary (ncu, B200, `bench.py --steps 2 --warmup 1`, first {len(launches)} launches)\n\n")
+        f.write(f"# {rnd} profile summary (ncu, B200, `bench.py --steps 1 --warmup 1 --spp 128 --no-cpu-baseline --no-e2e --no-other-workloads`, first {len(launches)} launches; kernel sources {csrc_sha})\n\n")
+        f.write(f"Whole step: **{warp_inst_per_path:.1f} warp instructions and {dram_per_path:.0f} DRAM bytes per path sample**, {lane_complete / max(inst_complete, 1):.1f} active lanes per instruction "
+                f"(complete waves of the capture: {n_waves} x {PATHS_PER_WAVE} paths).\n\n")
         f.write("| kernel | launches | time (us) | share | warp-inst | lanes/inst | issue-active % | DRAM B/launch | DRAM GB/s |\n|---|---|---|---|---|---|---|---|---|\n")
         for k, a in sorted(kernels.items(), key=lambda kv: -kv[1]["time_us"]):
             f.write(f"| `{k}` | {a['launches']} | {a['time_us']:.0f} | {a['share']*100:.1f} % | {a['warp_inst']/1e6:.0f} M | {a['threads_per_inst']} | {a['issue_active_pct']} | {a['dram_bytes_per_launch']/1e6:.1f} M | {a['dram_gbs']} |\n")
