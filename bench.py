@@ -370,13 +370,11 @@ def cuda_arm(args):
     def resolve(acc, out):
         ctx.resolve(acc.data_ptr(), out.data_ptr())
 
-    coll_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-
-    def step(want_stats):
+    def step(want_stats, coll_ev=None):
         flush.fill_(1)
         return multigpu.render_frame(
-            lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=want_stats),
-            resolve, accum, rgba, spp, rank, world, collective_events=coll_ev if want_stats else None)
+            lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=want_stats, flags=4 if want_stats else 0),   # 4 = NRCU_FLAG_KERNEL_TIMES
+            resolve, accum, rgba, spp, rank, world, collective_events=coll_ev)
 
     for _ in range(args.warmup):
         step(False)
@@ -385,31 +383,49 @@ def cuda_arm(args):
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"rays": 0, "paths": 0, "kernel_launches": 0, "ms_trace": 0.0, "ms_shade": 0.0, "ms_stage2": 0.0, "iterations": 0}
-    sched, coll_ms = 0, 0.0
+    coll_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] if world > 1 else []
+    # The timed steps are enqueued WITHOUT per-kernel statistics: reading back ~1 000 event spans per step would stall the
+    # host - and with it the reduce - for about a millisecond after every frame.  Rays, launches and kernel times are taken
+    # from one more, untimed step of the same frame (same seed: every step traces exactly the same paths).
     ev0.record()
-    for _ in range(args.steps):
-        st = step(True)
-        for k in agg:
-            agg[k] += st[k] if st else 0
-        sched = st["scheduler"] if st else sched
-        if world > 1:
-            coll_ev[1].synchronize()
-            coll_ms += coll_ev[0].elapsed_time(coll_ev[1])
+    for k in range(args.steps):
+        step(False, coll_events[k] if coll_events else None)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_stage2"], coll_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([agg["rays"], agg["paths"], agg["kernel_launches"]], dtype=torch.float64, device=dev)
+    ctx.synchronize()      # reports a traversal-stack overflow of the asynchronous steps, if any
+    coll_ms = sum(a.elapsed_time(b) for a, b in coll_events)
+    st = step(True) or {}
+    barrier()
+    agg = {k: st.get(k, 0) * args.steps for k in ("rays", "paths", "kernel_launches", "ms_trace", "ms_shade", "ms_stage2", "iterations")}
+    sched = st.get("scheduler", 0)
+    coll_iso = 0.0
+    if world > 1:   # the exchange step on its own: all ranks start together, 10 repetitions
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(12):
+            if rep == 2:
+                barrier(); e0.record()
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                resolve(accum, rgba)
+        e1.record()
+        torch.cuda.synchronize()
+        coll_iso = e0.elapsed_time(e1) / 10
+        step(False)          # leave the frame of the workload in rgba again
+        barrier()
+    t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_stage2"], coll_ms, coll_iso], dtype=torch.float64, device=dev)
+    sums = torch.tensor([agg["rays"], agg["paths"], agg["kernel_launches"], sched], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mx = sums.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, ms_trace, ms_shade, ms_stage2, coll_ms = t.tolist()
-    rays, paths, launches = sums.tolist()
+        sums[3] = mx[3]
+    ms, ms_trace, ms_shade, ms_stage2, coll_ms, coll_iso = t.tolist()
+    rays, paths, launches, sched = sums.tolist()
     launches += args.steps * (1 if rank == 0 else 0)   # resolve
     value = paths / (ms * 1e-3) * 1e-6
-    scheduler = {1: "waves", 2: "regen"}.get(sched, "?")
+    scheduler = {1: "waves", 2: "regen"}.get(int(sched), "?")
 
     # ---- cfg5 (4K, 4096 spp: the configuration the north star's scaling claim is quoted on), 3 steps at every N --------------------
     cfg5 = None
@@ -423,14 +439,13 @@ def cuda_arm(args):
             flush.fill_(1)
             return multigpu.render_frame(lambda acc, a, b: ctx.render_accumulate(acc.data_ptr(), s0=a, s1=b, seed=args.seed, want_stats=stats),
                                          resolve, acc5, rgba5, f5.samples_per_pixel, rank, world)
-        step5(False)
+        st = step5(True)            # warm-up (allocations) and the step that is counted: rays / paths of one frame
+        r5, p5 = (3 * st["rays"], 3 * st["paths"]) if st else (0, 0)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r5 = p5 = 0
         e0.record()
         for _ in range(3):
-            st = step5(True)
-            r5 += st["rays"] if st else 0; p5 += st["paths"] if st else 0
+            step5(False)
         e1.record()
         barrier()
         t5 = torch.tensor([e0.elapsed_time(e1), r5, p5], dtype=torch.float64, device=dev)
@@ -501,6 +516,7 @@ def cuda_arm(args):
         "kernel_ms": {"closest_hit": ms_trace / args.steps, "of_which_bvh_traversal": ms_stage2 / args.steps, "shade": ms_shade / args.steps,
                       "note": "per-kernel CUDA-event spans summed over the concurrent streams: they overlap, so they add up to more than ms_per_step"},
         "iterations_per_step": agg["iterations"] / args.steps,
+        "counters_from": "one untimed step of the same frame after the timed region (same seed, same paths); the timed steps run without per-kernel event read-backs",
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": roof,
@@ -508,8 +524,10 @@ def cuda_arm(args):
         "clocks": clocks,
     }
     if world > 1:
-        line["collective"] = {"what": "zero-copy NCCL reduce(sum, fp32) of the linear frame to rank 0 + k_resolve", "ms_per_step": coll_ms / args.steps,
-                              "bytes": w * h * 16}
+        line["collective"] = {"what": "NCCL reduce(sum, fp32) of the linear frame to rank 0 + k_resolve", "bytes": w * h * 16,
+                              "ms_per_step_in_the_timed_region": coll_ms / args.steps, "ms_isolated": coll_iso,
+                              "note": "in the timed region the span starts when a rank has finished its slice, so it contains the wait for the slowest rank; "
+                                      "isolated = the same reduce + resolve with all ranks starting together (max over ranks)"}
     ref_bpr = REFERENCE_TRAVERSAL_BYTES_PER_RAY.get(WORKLOADS[args.workload][0])
     if ref_bpr and ms_trace > 0:
         line["reference_traversal_equivalent"] = {"gbytes_per_s": rays * ref_bpr / (ms * 1e-3) * 1e-9, "bytes_per_ray": ref_bpr,

@@ -190,12 +190,15 @@ enum nrcu_render_flags {
                                   estimation at Lambertian vertices - one shadow ray per diffuse bounce towards a uniformly
                                   sampled point of an area light; same expectation as the reference's estimator, far
                                   lower variance.  Ignored in RayCast mode. */
-    NRCU_FLAG_ENV_IS = 1u << 1 /* EXTENSION to the environment-map extension: at Lambertian vertices one direction is
+    NRCU_FLAG_ENV_IS = 1u << 1,/* EXTENSION to the environment-map extension: at Lambertian vertices one direction is
                                   drawn from the map's luminance x sin(theta) distribution (marginal/conditional CDF tables built at
                                   upload) and its shadow ray is combined with the hemisphere sample by the balance heuristic.  Same
                                   expectation as the plain miss lookup, far lower variance for maps with small bright regions.  Takes
                                   effect only when the scene's ambient is an environment map; it then replaces NRCU_FLAG_NEE's light
                                   sampling at those vertices (one shadow ray per vertex). */
+    NRCU_FLAG_KERNEL_TIMES = 1u << 2 /* fill nrcu_stats.ms_trace / ms_shade / ms_stage2: two CUDA events around every kernel launch
+                                  (~4 000 per cfg3 frame) and their read-back, about 1 % of a frame.  Without it a stats request costs
+                                  one synchronisation: paths, rays, launches and ms_total only. */
 };
 
 /* How the (pixel, sample) paths are scheduled onto the GPU.  Both schedulers trace exactly the same paths (the RNG is
@@ -225,13 +228,13 @@ typedef struct nrcu_stats {
     uint64_t rays;             /* closest-hit queries + shadow rays actually traced (device counter) */
     uint64_t kernel_launches;  /* launches of this library's kernels during the call */
     float ms_total;            /* CUDA-event time of the whole call on the context's stream */
-    float ms_trace;            /* time inside the closest-hit kernels: k_raygen (camera rays + fused stage 1), k_big, k_trace* */
-    float ms_shade;            /* time inside the shading kernels */
+    float ms_trace;            /* NRCU_FLAG_KERNEL_TIMES: time inside the closest-hit kernels: k_raygen (camera rays + fused stage 1), k_big, k_trace* */
+    float ms_shade;            /* NRCU_FLAG_KERNEL_TIMES: time inside the shading kernels */
     float ms_setup;            /* scene preparation + BVH build at upload time */
     uint32_t bvh_nodes;        /* wide nodes */
     uint32_t n_primitives;     /* primitives after mesh flattening */
     uint32_t max_queue;        /* high-water mark of the ray queue (branching glass mode: the unclamped demand) */
-    float ms_stage2;           /* the part of ms_trace spent in the BVH traversal kernels (k_trace*) */
+    float ms_stage2;           /* NRCU_FLAG_KERNEL_TIMES: the part of ms_trace spent in the BVH traversal kernels (k_trace*) */
     uint32_t scheduler;        /* nrcu_scheduler that ran (WAVES or REGEN) */
     uint32_t iterations;       /* REGEN: stage-1/stage-2/shade rounds; WAVES: waves x bounces */
     uint32_t wave_retries;     /* branching glass mode: waves re-rendered with fewer samples because the queue overflowed */

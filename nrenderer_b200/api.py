@@ -15,6 +15,7 @@ from .flatscene import FlatScene, MODE_ACC, MODE_RAYCAST, MODE_SIMPLE  # noqa: F
 
 FLAG_NEE = 1   # nrcu_render_flags.NRCU_FLAG_NEE
 FLAG_ENV_IS = 2   # nrcu_render_flags.NRCU_FLAG_ENV_IS
+FLAG_KERNEL_TIMES = 4   # nrcu_render_flags.NRCU_FLAG_KERNEL_TIMES: per-kernel CUDA-event spans in the stats
 SCHED_AUTO, SCHED_WAVES, SCHED_REGEN = 0, 1, 2   # nrcu_scheduler
 ERR_OVERFLOW = 6
 

@@ -657,12 +657,12 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + CS * (6 * (size_t)ds.depth + 24));
     const int sms = sm_count(ctx->device);
     const unsigned shade_grid = (unsigned)sms * (NP > 1 ? dual_shade() : NRCU_SHADE_MINB), big_grid = (unsigned)sms * (NP > 1 ? dual_big() : 8);
-    const bool timing = stats != nullptr, gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
+    const bool want_stats = stats != nullptr, timing = want_stats && params && (params->flags & NRCU_FLAG_KERNEL_TIMES), gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
     size_t ev_i = 0;
     struct Span { size_t a, b; int kind; };
     std::vector<Span> spans;
     for (int p = 0; p < NP; p++) CTX_CUDA(cudaMemsetAsync(ctx->ws[p].counters.p, 0, sizeof(uint32_t) * CNT_QUEUE0, S[0]));
-    if (timing) CTX_CUDA(cudaEventRecord(ctx->ev_begin, S[0]));
+    if (want_stats) CTX_CUDA(cudaEventRecord(ctx->ev_begin, S[0]));
     if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_fork, S[0])); for (int p = 1; p < NP; p++) CTX_CUDA(cudaStreamWaitEvent(S[p], ctx->ev_fork, 0)); }
     const uint64_t launches0 = ctx->launches;
     bool acc_recorded = false;
@@ -791,7 +791,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         g0 += k * (uint32_t)NP;
     }
     for (int p = 1; p < NP; p++) { CTX_CUDA(cudaEventRecord(ctx->ev_join, S[p])); CTX_CUDA(cudaStreamWaitEvent(S[0], ctx->ev_join, 0)); }
-    if (timing) {
+    if (want_stats) {
         cudaStream_t st = S[0];
         CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
         uint32_t h_cnt[4], h_wave[NRCU_MAX_WAVES][4];
@@ -880,12 +880,12 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     const int sms = sm_count(ctx->device);
     const unsigned share = (unsigned)NP;
     const unsigned big_grid = (unsigned)sms * (NP > 1 ? dual_big() : 8);
-    const bool timing = stats != nullptr, gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
+    const bool want_stats = stats != nullptr, timing = want_stats && params && (params->flags & NRCU_FLAG_KERNEL_TIMES), gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
     size_t ev_i = 0;
     struct Span { size_t a, b; int kind; };
     std::vector<Span> spans;
     CTX_CUDA(cudaMemsetAsync(ctx->ws[0].counters.p, 0, sizeof(uint32_t) * CNT_QUEUE0, S[0]));
-    if (timing) CTX_CUDA(cudaEventRecord(ctx->ev_begin, S[0]));
+    if (want_stats) CTX_CUDA(cudaEventRecord(ctx->ev_begin, S[0]));
     if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_fork, S[0])); for (int p = 1; p < NP; p++) CTX_CUDA(cudaStreamWaitEvent(S[p], ctx->ev_fork, 0)); }
     const uint64_t launches0 = ctx->launches;
     for (int p = 0; p < NP; p++) {
@@ -958,7 +958,7 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         k_accumulate_lanes<<<grid_for(npix, 256), 256, 0, S[0]>>>(P[p].lacc, d_accum, npix, P[p].lanes, p == 0 ? n_samples : 0u, d_rays);
         CTX_LAUNCH_CHECK("k_accumulate_lanes");
     }
-    if (timing) {
+    if (want_stats) {
         cudaStream_t st = S[0];
         CTX_CUDA(cudaEventRecord(ctx->ev_end, st));
         unsigned long long rays = 0;
