@@ -527,7 +527,8 @@ static int sm_count(int device) {
 // first, batch-of-32 kernel kept for A/B measurements).
 static int trace_variant() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_VARIANT"); v = e ? std::atoi(e) : 2; } return v; }
 static uint32_t trace_refill() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_REFILL"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; if (v > 32) v = 32; } return (uint32_t)v; }
-static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 128) << 20; return v; }
+static uint32_t wave_slots_target() { static uint32_t v = env_u32("NRCU_WAVE_MSLOTS", 256) << 20; return v; }
+static uint32_t wave_min_groups() { static uint32_t v = std::max<uint32_t>(1, env_u32("NRCU_WAVE_MIN_GROUPS", 1)); return v; }
 static uint32_t trace_taper(int k) {
     static uint32_t v[2] = {0xffffffffu, 0xffffffffu}; static bool init = false;
     if (!init) { init = true; const char* e = std::getenv("NRCU_TRACE_TAPER"); unsigned a = 0xffffffffu, b = 0xffffffffu; if (e) std::sscanf(e, "%u,%u", &a, &b); v[0] = a; v[1] = b; }
@@ -619,6 +620,11 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     if ((uint64_t)k * npix > 0x7fffffffull) k = std::max<uint32_t>(1, (uint32_t)(0x7fffffffull / npix));
     int NP = glass_branch ? 1 : std::max(1, std::min<int>(concurrent_waves(), (int)(s1 - s0)));
     if (NP > 1 && !explicit_k) k = std::max<uint32_t>(1, k / (uint32_t)NP);
+    // NRCU_WAVE_MIN_GROUPS (default 1 = off): at least that many groups of concurrent waves where the samples allow it.
+    // Measured on a 128-spp slice (what each GPU renders at N = 8) once the host no longer waits for statistics after
+    // every frame: one group of two 64-spp waves 3109, two groups of 32-spp waves 3078-3088, three groups 3068
+    // Mpath-samples/s - fewer, bigger launches win even for short slices (profiles/r2_history.md)
+    if (!explicit_k && !glass_branch) k = std::max<uint32_t>(1, std::min<uint32_t>(k, (s1 - s0 + (uint32_t)NP * wave_min_groups() - 1) / ((uint32_t)NP * wave_min_groups())));
     NP = std::max(1, std::min<int>(NP, (int)((s1 - s0 + k - 1) / k)));   // also with no samples at all: one (idle) wave set
     const unsigned share = (unsigned)NP;
     uint32_t slots = k * npix;
