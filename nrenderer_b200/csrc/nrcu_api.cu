@@ -828,6 +828,8 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
 // ---------------------------------------------------------------------------------------------
 #define NRCU_REGEN_BATCH 8      // iterations enqueued between two looks at the alive flags
 #define NRCU_REGEN_RING 4       // batches whose counters / flags are live at any time
+static bool regen_fused() { static uint32_t v = env_u32("NRCU_REGEN_FUSED", 0); return v != 0; }
+static unsigned fused_blocks() { static uint32_t v = env_u32("NRCU_FUSED_BLOCKS", NRCU_FUSED_MINB); return v ? v : 1; }
 static uint32_t regen_slots_target() { static uint32_t v = env_u32("NRCU_REGEN_MSLOTS", 64) << 20; return v; }
 
 static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_accum, nrcu_stats* stats, uint32_t s0, uint32_t s1) {
@@ -869,7 +871,8 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         NP = std::max(1, std::min<int>(NP, (int)K));
     }
     const uint32_t samples_per_lane = (n_samples + K - 1) / K;
-    uint64_t t_max = (uint64_t)samples_per_lane * ds.depth;   // a lane renders its samples one after the other, <= depth rays each
+    const bool fused = regen_fused();
+    uint64_t t_max = (uint64_t)samples_per_lane * ds.depth + (fused ? 1 : 0);   // a lane renders its samples one after the other, <= depth rays each
     { static uint32_t dbg = env_u32("NRCU_REGEN_MAX_ITERS", 0); if (dbg) t_max = std::min<uint64_t>(t_max, dbg); }   // steady-state measurements only: truncates the frame
     if (!ctx->h_flags) CTX_CUDA(cudaHostAlloc(&ctx->h_flags, sizeof(uint32_t) * NRCU_MAX_WAVES * NRCU_REGEN_RING * NRCU_REGEN_FLAGS * NRCU_REGEN_FLAG_STRIDE, cudaHostAllocDefault));
     cudaStream_t S[NRCU_MAX_WAVES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
@@ -929,6 +932,22 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                 uint32_t* ib = iter_block(pp, t);
                 uint32_t *n_surv = ib, *fetch = ib + CS, *flags = ib + 2 * CS;
                 const uint32_t* flags_prev = t ? iter_block(pp, t - 1) + 2 * CS : nullptr;
+                if (fused && t > 0) {   // NRCU_REGEN_FUSED: shade (hits of iteration t-1) + stage 1 of the new rays in one kernel, then stage 2
+                    if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
+                    const unsigned fgrid = (unsigned)sms * fused_blocks();
+                    if (gate) k_regen_fused<true><<<fgrid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, seed, s0, n_samples, K, pp.lane0, pp.n_slots, pp.q, pp.hits, pp.lacc, pp.surv, n_surv, flags_prev, flags);
+                    else k_regen_fused<false><<<fgrid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, seed, s0, n_samples, K, pp.lane0, pp.n_slots, pp.q, pp.hits, pp.lacc, pp.surv, n_surv, flags_prev, flags);
+                    CTX_LAUNCH_CHECK("k_regen_fused");
+                    if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 1}); }
+                    if (bvh) {
+                        if (gate) launch_stage2<true>(ctx, st, share, ds, pp.q, pp.hits, pp.surv, n_surv, fetch, nullptr);
+                        else launch_stage2<false>(ctx, st, share, ds, pp.q, pp.hits, pp.surv, n_surv, fetch, nullptr);
+                        CTX_LAUNCH_CHECK("k_trace");
+                    }
+                    if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 2}); ev_i += 3; }
+                    if (p == 0) iterations++;
+                    continue;
+                }
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                 if (t == 0) {
                     const unsigned gen_grid = std::min<unsigned>(grid_for(pp.n_slots, 256), (unsigned)sms * 8);
@@ -947,6 +966,12 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                     CTX_LAUNCH_CHECK("k_trace");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 2), st); spans.push_back({ev_i + 1, ev_i + 2, 2}); }
+                if (fused) {   // iteration 0 of the fused form: first rays + stage 1 + stage 2 only; everybody is alive
+                    CTX_CUDA(cudaMemsetAsync(flags, 0xff, sizeof(uint32_t), st));
+                    if (timing) ev_i += 4;
+                    if (p == 0) iterations++;
+                    continue;
+                }
                 k_shade_regen<<<dim3(grid_for(npix, 256), pp.lanes), shade_block, 0, st>>>(ds, seed, s0, n_samples, K, pp.lane0, pp.q, pp.hits, pp.lacc, flags_prev, flags);
                 CTX_LAUNCH_CHECK("k_shade_regen");
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i + 2, ev_i + 3, 1}); ev_i += 4; }

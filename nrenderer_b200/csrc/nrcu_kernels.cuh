@@ -823,6 +823,132 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_regen(DScene s, 
         flags_out[((blockIdx.x + blockIdx.y) % NRCU_REGEN_FLAGS) * NRCU_REGEN_FLAG_STRIDE] = 1u;
 }
 
+// Fused iteration of the regeneration scheduler (NRCU_REGEN_FUSED=1): shade the slot's vertex with the hit the previous
+// iteration found, continue or regenerate in place, and run stage 1 of the closest hit on the NEW ray while it is still
+// in registers - one kernel per iteration (+ the stage-2 traversal of the survivors).  The point is not the saved ray
+// round trip but the mix: the shading phase of a warp is latency bound (dependent gathers), the stage-1 phase issue bound
+// (~1 000 ALU instructions per 32 rays); in one kernel the slot data of the NEXT loop iteration is requested before stage 1
+// starts, so its latency is covered by a thousand instructions of the same warp, and warps in different phases share an SM.
+#ifndef NRCU_FUSED_MINB
+#define NRCU_FUSED_MINB 3
+#endif
+template <bool GATE>
+__global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS, NRCU_FUSED_MINB) k_regen_fused(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_samples, uint32_t K, uint32_t lane0, uint32_t n_slots,
+                                                                                      PathQueue q, float2* hits, f4* lacc, uint32_t* surv, uint32_t* n_surv,
+                                                                                      const uint32_t* flags_prev, uint32_t* flags_out) {
+    __shared__ BigList bl;
+    __shared__ unsigned short pairs[NRCU_BIGB_WARPS][32 * NRCU_MAX_BIG];
+    __shared__ float rays[NRCU_BIGB_WARPS][6][32];
+    __shared__ unsigned long long best[NRCU_BIGB_WARPS][32];
+    if (!regen_anyone_alive(flags_prev)) return;
+    bl.load(s);
+    const uint32_t n = n_slots, npix = s.width * s.height;
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned short* my_pairs = pairs[wib];
+    f4 a = mk4(0, 0, 0, 0), c = mk4(0, 0, 0, __int_as_float((int)NRCU_SLOT_DEAD)); float2 b = make_float2(0.f, 0.f), h = b;
+    auto load_slot = [&](uint32_t j) {
+        c = mk4(0, 0, 0, __int_as_float((int)NRCU_SLOT_DEAD));
+        if (j >= n) return;
+        c = q.c[j]; a = q.a[j]; b = q.b[j]; h = hits[j];
+    };
+    load_slot(warp_global * 32u + lane);
+    bool any_alive = false;
+    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
+        const uint32_t i = base + lane;
+        const uint32_t state = (uint32_t)f2i(c.w);
+        bool live = state != NRCU_SLOT_DEAD;
+        if (!__any_sync(0xffffffffu, live)) { load_slot(i + warps_total * 32u); continue; }
+        // ---- shading phase: one path vertex per live slot ----------------------------------------------------------
+        Ray r; r.o = mk3(0.f); r.d = mk3(0.f);
+        if (live) {
+            if (!(a.x == a.x)) h = make_float2(NRCU_INF, __int_as_float(-1));
+            const uint32_t pixel = i % npix, lane_id = lane0 + i / npix, bounce = state & ((1u << NRCU_SLOT_BOUNCE_BITS) - 1u);
+            uint32_t j = state >> NRCU_SLOT_BOUNCE_BITS;
+            Ray ray; ray.o = mk3(a.x, a.y, a.z); ray.d = mk3(a.w, b.x, b.y);
+            const PathStep ps = path_vertex<false>(s, seed, pixel, sample0 + lane_id + j * K, bounce, 0u, ray, mk3(c.x, c.y, c.z), h.x, __float_as_int(h.y), 0, false);
+            if (ps.action == PATH_CONTINUE) {
+                r = ps.next;
+                q.c[i] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)(state + 1u)));
+            } else {
+                f4 v = lacc[i];
+                lacc[i] = mk4(v.x + ps.radiance.x, v.y + ps.radiance.y, v.z + ps.radiance.z, v.w + (float)(bounce + 1u));
+                j++;
+                const uint32_t next_lane_sample = lane_id + j * K;
+                if (next_lane_sample < n_samples) {
+                    r = pt_camera_ray(s, seed, pixel, sample0 + next_lane_sample);
+                    q.c[i] = mk4(1.f, 1.f, 1.f, i2f((int)(j << NRCU_SLOT_BOUNCE_BITS)));
+                } else {
+                    live = false;
+                    q.a[i] = mk4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+                    q.c[i] = mk4(0.f, 0.f, 0.f, __int_as_float((int)NRCU_SLOT_DEAD));
+                }
+            }
+            if (live) {
+                q.a[i] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
+                q.b[i] = make_float2(r.d.y, r.d.z);
+                live = r.o.x == r.o.x;      // a NaN origin hits nothing: no stage 1, the next iteration shades it as a miss
+                if (!live) hits[i] = make_float2(NRCU_INF, __int_as_float(-1));
+                any_alive = true;
+            }
+        }
+        // ---- the next loop iteration's slot data: in flight during stage 1 -------------------------------------------
+        load_slot(i + warps_total * 32u);
+        // ---- stage 1 of the closest hit on the new rays (k_big_balanced's body) ---------------------------------------
+        const RayPrep rp = prep_ray(r);
+        rays[wib][0][lane] = r.o.x; rays[wib][1][lane] = r.o.y; rays[wib][2][lane] = r.o.z;
+        rays[wib][3][lane] = r.d.x; rays[wib][4][lane] = r.d.y; rays[wib][5][lane] = r.d.z;
+        best[wib][lane] = NRCU_BEST_NONE;
+        uint32_t total = 0;
+        const float nox = live ? -rp.oinv.x : -NRCU_INF;
+        const vec3 ainv = mk3(fabsf(rp.inv.x), fabsf(rp.inv.y), fabsf(rp.inv.z));
+        for (uint32_t k = 0; k < s.n_big; k++) {
+            float tn, tf;
+            slab_center_extent(bl.bd[2 * k], bl.bd[2 * k + 1], rp, ainv, nox, tn, tf);
+            const bool cand = tn <= tf;
+            const uint32_t m = __ballot_sync(0xffffffffu, cand);
+            if (cand) my_pairs[total + __popc(m & lt)] = (unsigned short)(lane | (k << 5));
+            total += __popc(m);
+        }
+        __syncwarp();
+        for (uint32_t jb = 0; jb < total; jb += 32u) {
+            const uint32_t jj = jb + lane;
+            if (jj < total) {
+                const uint32_t p = my_pairs[jj], ol = p & 31u, k = p >> 5;
+                Ray pr; pr.o = mk3(rays[wib][0][ol], rays[wib][1][ol], rays[wib][2][ol]); pr.d = mk3(rays[wib][3][ol], rays[wib][4][ol], rays[wib][5][ol]);
+                float bt = __uint_as_float((uint32_t)(best[wib][ol] >> 32));
+                int bi = 0x7fffffff;
+                prim_test<false>(pr, mk3(0.f), bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b, bl.m[k], bt, bi);
+                if (bi != 0x7fffffff) atomicMin(&best[wib][ol], ((unsigned long long)__float_as_uint(bt) << 32) | (unsigned long long)(((uint32_t)bi << 5) | k));
+            }
+        }
+        __syncwarp();
+        bool more = false;
+        if (live) {
+            const unsigned long long key = best[wib][lane];
+            float best_t = NRCU_INF; int best_id = -1;
+            if (key != NRCU_BEST_NONE) {
+                best_t = __uint_as_float((uint32_t)(key >> 32)); best_id = (int)((uint32_t)key >> 5);
+                if (GATE) {
+                    const uint32_t kb = (uint32_t)key & 31u;
+                    const vec3 ginv = gate_inverse(r, rp);
+                    if (!bounds_intersectp_inv(bl.b[2 * kb], bl.b[2 * kb + 1], r, ginv.x, ginv.y, ginv.z)) {
+                        best_t = NRCU_INF; best_id = -1;
+                        for (uint32_t k = 0; k < s.n_big; k++)
+                            prim_test<true>(r, ginv, bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b + 2 * k, bl.m[k], best_t, best_id);
+                    }
+                }
+            }
+            hits[i] = make_float2(best_t, __int_as_float(best_id));
+            more = bvh_reachable(s, rp, best_t);
+        }
+        __syncwarp();
+        append_survivors(more, i, surv, n_surv);
+    }
+    if (__any_sync(0xffffffffu, any_alive) && lane == 0) flags_out[(warp_global % NRCU_REGEN_FLAGS) * NRCU_REGEN_FLAG_STRIDE] = 1u;
+}
+
 // End of the frame (or slice): accum[p].rgb += the lanes' sums in lane order, accum[p].a += n_samples (passed for the
 // first partition only); the rays the lanes counted go to the context's ray counter, one atomic per CTA.
 __global__ void __launch_bounds__(256) k_accumulate_lanes(const f4* lacc, f4* accum, uint32_t npix, uint32_t lanes, uint32_t n_samples, unsigned long long* ray_counter) {

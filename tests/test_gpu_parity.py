@@ -603,3 +603,32 @@ def test_metropolis_frame_has_the_expectation_of_the_path_traced_frame(ctx, name
     again, _ = ctx.render_mlt(seed=2, mutations_per_pixel=64, tone_map=api.MLT_TONE_LINEAR)
     toned, _ = ctx.render_mlt(seed=2, mutations_per_pixel=64, tone_map=api.MLT_TONE_REFERENCE)
     assert np.allclose(toned[..., :3], np.power(1 - np.exp(-again[..., :3].astype(np.float64)), 1 / 2.2), rtol=2e-2, atol=2e-2)   # float atomics: the two runs differ in the last bits
+
+
+@pytest.mark.gpu
+def test_fused_regeneration_kernel_traces_the_same_paths():
+    """NRCU_REGEN_FUSED=1 (k_regen_fused: shade + regenerate + stage 1 in one kernel; an experiment that is kept because it is
+    measured in profiles/r2_history.md): same frame and ray count as the three-kernel form of the regeneration scheduler."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from conftest import load_scene
+        import nrenderer_b200 as nr
+        c = nr.Context(0)
+        fs = load_scene("bunny5k_cornel", width=96, height=54, samples_per_pixel=12, depth=20, cam_aspect=16 / 9)
+        c.upload(fs, 2)
+        acc = torch.zeros(54, 96, 4, device="cuda:0"); torch.cuda.synchronize()
+        st = c.render_accumulate(acc.data_ptr(), seed=5, scheduler=2)
+        np.save(sys.argv[1], acc.cpu().numpy()); print("RAYS", st["rays"], st["scheduler"])
+    """ % (os.path.dirname(GOLDEN), os.path.dirname(os.path.dirname(GOLDEN))))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        out = {}
+        for fused in ("0", "1"):
+            path = os.path.join(td, f"f{fused}.npy")
+            r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=dict(os.environ, NRCU_REGEN_FUSED=fused), timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            out[fused] = (np.load(path), [ln for ln in r.stdout.splitlines() if ln.startswith("RAYS")][0])
+    assert out["0"][1] == out["1"][1] and out["0"][1].endswith(" 2")
+    assert np.array_equal(out["0"][0].view(np.uint32), out["1"][0].view(np.uint32))
