@@ -33,6 +33,7 @@
 #ifndef NRCU_H
 #define NRCU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -323,6 +324,13 @@ int nrcu_resolve(nrcu_ctx* ctx, const float* d_accum, float* d_rgba);
  * same traversal kernel the renderer uses.  prim_id[i] = primitive id (see
  * nrcu_primitive_count) or -1; t[i] = hit distance or +inf. */
 int nrcu_trace_batch(nrcu_ctx* ctx, const float* rays, uint32_t n, int32_t* prim_id, float* t);
+
+/* Page-locked host memory for the frame a caller hands to nrcu_render* (the reference's components allocate their pixel
+ * buffer with new[], ray_cast/src/RayCastRenderer.cpp:7-10; a pinned buffer makes the device -> host copy of the frame a
+ * single DMA at PCIe speed instead of a staged copy through the driver's bounce buffer).  NULL when the allocation fails:
+ * callers fall back to ordinary memory, which every entry point accepts as well. */
+void* nrcu_host_alloc(size_t bytes);
+void nrcu_host_free(void* p);
 
 /* Stream plumbing for callers that own a CUDA stream (e.g. torch): cudaStream_t as void*. */
 int nrcu_set_stream(nrcu_ctx* ctx, void* cuda_stream);

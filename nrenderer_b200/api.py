@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "nrcu_abi_version", "nrcu_device_count", "nrcu_create", "nrcu_destroy", "nrcu_last_error", "nrcu_upload_scene",
     "nrcu_primitive_count", "nrcu_download_primitives", "nrcu_render", "nrcu_render_accumulate", "nrcu_resolve",
     "nrcu_render_multi", "nrcu_render_progressive", "nrcu_render_mlt", "nrcu_trace_batch", "nrcu_set_stream", "nrcu_synchronize", "nrcu_philox4x32",
+    "nrcu_host_alloc", "nrcu_host_free",
 ]
 
 
@@ -85,6 +86,10 @@ def load_library() -> C.CDLL:
     L.nrcu_render_mlt.argtypes = [vp, vp, vp, vp]
     L.nrcu_resolve.argtypes = [vp, vp, vp]
     L.nrcu_trace_batch.argtypes = [vp, vp, u32, vp, vp]
+    L.nrcu_host_alloc.restype = vp
+    L.nrcu_host_alloc.argtypes = [C.c_size_t]
+    L.nrcu_host_free.argtypes = [vp]
+    L.nrcu_host_free.restype = None
     L.nrcu_set_stream.argtypes = [vp, vp]
     L.nrcu_synchronize.argtypes = [vp]
     L.nrcu_philox4x32.argtypes = [vp, vp, vp]

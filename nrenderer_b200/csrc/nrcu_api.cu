@@ -193,6 +193,13 @@ int nrcu_destroy(nrcu_ctx* ctx) {
     return NRCU_OK;
 }
 
+void* nrcu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void nrcu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int nrcu_set_stream(nrcu_ctx* ctx, void* cuda_stream) {
     if (!ctx) return NRCU_ERR_INVALID;
     cudaSetDevice(ctx->device);

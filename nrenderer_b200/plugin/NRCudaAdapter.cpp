@@ -49,7 +49,20 @@ namespace NRCuda
         nrcu_ctx* ctx = nullptr;               // primary device: NRCU_DEVICE (default 0)
         int ctx_device = -1;
         std::map<int, nrcu_ctx*> extra;        // further devices when NRCU_DEVICES > 1, keyed by DEVICE INDEX (sample slices, nrcu_render_multi)
-        ~SharedContext() { for (auto& kv : extra) nrcu_destroy(kv.second); if (ctx) nrcu_destroy(ctx); }
+        // The frame buffer the component owns (ray_cast/src/RayCastRenderer.cpp:7-10 allocates one per render with new[]):
+        // page-locked and kept across renders, so that the frame comes back in one DMA; plain memory if pinning fails.
+        RGBA* frame = nullptr; size_t frame_pixels = 0; bool frame_pinned = false;
+        RGBA* frameBuffer(size_t n) {
+            if (frame && frame_pixels >= n) return frame;
+            releaseFrame();
+            frame = static_cast<RGBA*>(nrcu_host_alloc(n * sizeof(RGBA)));
+            frame_pinned = frame != nullptr;
+            if (!frame) frame = new RGBA[n];
+            frame_pixels = n;
+            return frame;
+        }
+        void releaseFrame() { if (frame) { if (frame_pinned) nrcu_host_free(frame); else delete[] frame; } frame = nullptr; frame_pixels = 0; }
+        ~SharedContext() { releaseFrame(); for (auto& kv : extra) nrcu_destroy(kv.second); if (ctx) nrcu_destroy(ctx); }
     };
     static SharedContext& shared() { static SharedContext s; return s; }
 
@@ -124,7 +137,7 @@ namespace NRCuda
                 if (const char* e = std::getenv("NRCU_ENV_IS")) if (std::atoi(e)) params.flags |= NRCU_FLAG_ENV_IS;   // extension: importance-sample the environment map
                 if (const char* e = std::getenv("NRCU_GLASS_BRANCH")) params.glass_mode = std::atoi(e) ? NRCU_GLASS_BRANCH : NRCU_GLASS_STOCHASTIC;
                 nrcu_stats st{};
-                RGBA* pixels = new RGBA[(size_t)w * h];   // plugin owns the buffer, Screen::set copies it (RayCastRenderer.cpp:7-10)
+                RGBA* pixels = sh.frameBuffer((size_t)w * h);   // the plugin owns the buffer, Screen::set copies it (RayCastRenderer.cpp:7-10)
                 int rc;
                 const char* prog = std::getenv("NRCU_PROGRESSIVE");
 #if NRCU_PLUGIN_MODE == 3
@@ -154,12 +167,10 @@ namespace NRCuda
                         if (pe && *pe && why.find(pe) == std::string::npos) why += " | device " + std::to_string(dev_ids[g]) + ": " + pe;
                     }
                     logger.error("NRCuda: " + why);
-                    delete[] pixels;
                     publishBlack(w, h);
                     return;
                 }
                 getServer().screen.set(pixels, (int)w, (int)h);
-                delete[] pixels;
                 double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
                 char buf[320];
                 std::snprintf(buf, sizeof(buf),
