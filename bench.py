@@ -496,7 +496,7 @@ def cuda_arm(args):
         e2e.update({"value": w * h * spp / sec * 1e-6, "seconds_per_exec": sec, "seconds_best": info["seconds"],
                     "path": "nr_headless -> ComponentFactory::createComponent<RenderComponent> -> exec() -> NRCuda::Adapter::render (flatten, nrcu_upload_scene, "
                             + ("nrcu_render_multi over %d devices: peer-read reduce fused with the resolve" % world if world > 1 else "nrcu_render")
-                            + ", pageable RGBA buffer) -> Screen::set; wall clock around exec(), through RenderComponent::exec",
+                            + ", the adapter's frame buffer) -> Screen::set; wall clock around exec(), through RenderComponent::exec",
                     "plugin_log": info.get("last_log"),
                     "max_abs_diff_vs_device_timed_frame": float(np.abs(np.clip(frame_nccl, 0, 1) - frame).max())})
     except Exception as ex:

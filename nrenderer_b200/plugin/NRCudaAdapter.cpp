@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "server/Server.hpp"
@@ -113,22 +114,30 @@ namespace NRCuda
                 if (const char* e = std::getenv("NRCU_DEVICES")) {
                     const int n_dev = nrcu_device_count();
                     const int want = std::min(std::string(e) == "all" ? n_dev : std::atoi(e), n_dev);
-                    for (int d = 0; d < n_dev && (int)devs.size() < want; d++) {
+                    // the scene is replicated: every further device gets its own context (kept across renders) and its own
+                    // upload + BVH build, all of them at the same time on their own host threads
+                    struct Job { int d; nrcu_ctx* ctx; bool created; int rc; std::string err; };
+                    std::vector<Job> jobs;
+                    for (int d = 0; d < n_dev && (int)jobs.size() + 1 < want; d++) {
                         if (d == dev) continue;
                         auto it = sh.extra.find(d);
-                        if (it == sh.extra.end()) {
-                            nrcu_ctx* c = nullptr;
-                            if (nrcu_create(d, &c) != NRCU_OK) {
-                                logger.warning("NRCuda: device " + std::to_string(d) + " skipped: " + nrcu_last_error(nullptr));
-                                continue;
-                            }
-                            it = sh.extra.emplace(d, c).first;
+                        jobs.push_back({d, it == sh.extra.end() ? nullptr : it->second, false, NRCU_OK, {}});
+                    }
+                    std::vector<std::thread> pool;
+                    for (auto& j : jobs) pool.emplace_back([&j, &view]() {
+                        if (!j.ctx) {
+                            j.rc = nrcu_create(j.d, &j.ctx);
+                            if (j.rc != NRCU_OK) { j.err = nrcu_last_error(nullptr); j.ctx = nullptr; return; }
+                            j.created = true;
                         }
-                        if (nrcu_upload_scene(it->second, &view, NRCU_SCENE_MODE) != NRCU_OK) {
-                            logger.warning("NRCuda: device " + std::to_string(d) + " skipped: " + nrcu_last_error(it->second));
-                            continue;
-                        }
-                        devs.push_back(it->second); dev_ids.push_back(d);
+                        j.rc = nrcu_upload_scene(j.ctx, &view, NRCU_SCENE_MODE);
+                        if (j.rc != NRCU_OK) j.err = nrcu_last_error(j.ctx);
+                    });
+                    for (auto& t : pool) t.join();
+                    for (auto& j : jobs) {
+                        if (j.created && j.ctx) sh.extra.emplace(j.d, j.ctx);
+                        if (j.rc != NRCU_OK) { logger.warning("NRCuda: device " + std::to_string(j.d) + " skipped: " + j.err); continue; }   // a device that fails is left out, the others carry on
+                        devs.push_back(j.ctx); dev_ids.push_back(j.d);
                     }
                 }
                 nrcu_render_params params{};
