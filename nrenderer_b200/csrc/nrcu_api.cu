@@ -73,6 +73,12 @@ struct Sub { void* p = nullptr; template <typename T> T* as() const { return rei
 #ifndef NRCU_OPT_RAYCOUNT
 #define NRCU_OPT_RAYCOUNT 1
 #endif
+#ifndef NRCU_SHADE_POOL_DEFAULT
+#define NRCU_SHADE_POOL_DEFAULT 1
+#endif
+#ifndef NRCU_QUEUE_REGIONS_DEFAULT
+#define NRCU_QUEUE_REGIONS_DEFAULT 16
+#endif
 #ifndef NRCU_SCHED_DEFAULT
 #define NRCU_SCHED_DEFAULT NRCU_SCHED_WAVES
 #endif
@@ -492,6 +498,13 @@ int nrcu_download_primitives(const nrcu_ctx* cctx, uint32_t* kind, float* data16
 // rendering
 // ---------------------------------------------------------------------------------------------
 enum { CNT_RAYS = 0 /* u64 */, CNT_HIGH_WATER = 2, CNT_QUEUE0 = 64 /* [depth+2] queue sizes, [depth+2] fetch cursors, [depth+2] survivor counts */ };
+#define NRCU_MAX_REGIONS 32   /* queue regions (QRegions in nrcu_kernels.cuh): lane r of a warp keeps region r's count */
+// Regions per queue (power of two, 1 = the plain compacted queue).  NRCU_QUEUE_REGIONS overrides.
+static uint32_t queue_regions_log2() {
+    static int v = -1;
+    if (v < 0) { uint32_t k = env_u32("NRCU_QUEUE_REGIONS", NRCU_QUEUE_REGIONS_DEFAULT); v = 0; while ((2u << v) <= k && (2u << v) <= NRCU_MAX_REGIONS) v++; }
+    return (uint32_t)v;
+}
 
 static int ensure_wave(nrcu_ctx* ctx, int set, uint32_t slots, uint32_t capacity, uint32_t depth, bool branch_bits, bool shadow_queue) {
     // The wave buffers are power-of-two sized (32 Mi x 16 B = 512 MiB) and the kernels stream through ten of
@@ -515,7 +528,7 @@ static int ensure_wave(nrcu_ctx* ctx, int set, uint32_t slots, uint32_t capacity
     }
     CTX_CUDA(w.surv.ensure(sizeof(uint32_t) * (size_t)capacity));
     CTX_CUDA(w.L.ensure(sizeof(f4) * (size_t)slots));
-    CTX_CUDA(w.counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + counter_stride() * (6 * (size_t)depth + 24))));
+    CTX_CUDA(w.counters.ensure(sizeof(uint32_t) * (CNT_QUEUE0 + counter_stride() * ((6 + NRCU_MAX_REGIONS) * ((size_t)depth + 4)))));
     return NRCU_OK;
 }
 
@@ -541,7 +554,9 @@ static uint32_t trace_taper(int k) {
     if (!init) { init = true; const char* e = std::getenv("NRCU_TRACE_TAPER"); unsigned a = 0xffffffffu, b = 0xffffffffu; if (e) std::sscanf(e, "%u,%u", &a, &b); v[0] = a; v[1] = b; }
     return v[k];
 }
-static bool big_balanced() { static uint32_t v = env_u32("NRCU_BIG_BALANCED", 1); return v != 0; }
+static uint32_t big_balanced() { static uint32_t v = env_u32("NRCU_BIG_BALANCED", 2); return v; }   // 0 per-lane k_big, 1 k_big_balanced, 2 k_big_balanced64 (needs NRCU_OPT_RAYCOUNT)
+static bool shade_pool() { static uint32_t v = env_u32("NRCU_SHADE_POOL", NRCU_SHADE_POOL_DEFAULT); return v != 0; }   // k_shade_pool instead of k_shade where it applies
+static unsigned dual_big64() { static uint32_t v = env_u32("NRCU_CONC_BIG64", 12); return v ? v : 1; }
 static uint32_t trace_w_node() { static uint32_t v = env_u32("NRCU_TRACE_WNODE", 1); return v; }
 static uint32_t trace_w_prim() { static uint32_t v = env_u32("NRCU_TRACE_WPRIM", 1); return v; }
 static unsigned trace_blocks_per_sm() { static int v = -1; if (v < 0) { const char* e = std::getenv("NRCU_TRACE_BLOCKS"); v = e ? std::atoi(e) : 8; if (v < 1) v = 1; } return (unsigned)v; }
@@ -574,7 +589,7 @@ static void launch_stage2(nrcu_ctx* ctx, cudaStream_t st, unsigned share, const 
 template <bool GATE>
 static void launch_closest_hit(nrcu_ctx* ctx, cudaStream_t st, unsigned share, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* surv,
                                uint32_t* n_surv, uint32_t* fetch, unsigned long long* rays, int* launches) {
-    k_big<GATE><<<(unsigned)sm_count(ctx->device) * (share > 1 ? dual_big() : 8), 256, 0, st>>>(ds, q, n_ptr, hits, surv, n_surv, rays);
+    k_big<GATE><<<(unsigned)sm_count(ctx->device) * (share > 1 ? dual_big() : 8), 256, 0, st>>>(ds, q, QRegions{n_ptr, 0u, 1u}, hits, surv, n_surv, rays);
     (*launches)++;
     if (ds.root_ref == NRCU_REF_EMPTY) return;
     launch_stage2<GATE>(ctx, st, share, ds, q, hits, surv, n_surv, fetch, rays);
@@ -638,10 +653,18 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     // branching glass mode: room for 4 rays per path slot, and never less than 4 Mi entries (small frames at many bounces)
     auto branch_capacity = [](uint32_t sl) { return (uint32_t)std::min<uint64_t>(0x7fffffffull, std::max<uint64_t>((uint64_t)sl * 4, 4ull << 20)); };
     uint32_t capacity = glass_branch ? branch_capacity(slots) : slots;
+    // Queue regions (QRegions in nrcu_kernels.cuh): K counters per queue instead of one.  Region r of the queue that enters
+    // bounce d + 1 receives the survivors of the input blocks pb = r (mod K), at most ceil(blocks / K) x 32 entries, so the
+    // array extent grows by at most 32 K entries per bounce: `slack`.  The branching glass mode keeps the plain queue
+    // (its overflow handling clamps ONE counter).
+    const uint32_t logk = glass_branch ? 0u : queue_regions_log2(), K = 1u << logk;
+    // k_shade_pool numbers its output rounds per warp: a region can be one round per shading warp longer than the others.
+    const uint32_t pool_slack = (shade_pool() && !glass_branch && direct_sampling_mode(ctx, params) == 0) ? 32u * (K + 1u) * (uint32_t)sm_count(ctx->device) * std::max(dual_shade(), (unsigned)NRCU_SHADE_MINB) * 8u : 0u;
+    const uint32_t slack = (K > 1 ? 32u * K * (ds.depth + 2) : 0u) + (K > 1 ? pool_slack : 0u);
     int rc;
     for (;;) {   // the default wave size assumes a B200's 180 GB; on a fuller or smaller device shrink the waves instead of failing
         rc = NRCU_OK;
-        for (int p = 0; p < NP && rc == NRCU_OK; p++) rc = ensure_wave(ctx, p, slots, capacity, ds.depth, glass_branch != 0, nee);
+        for (int p = 0; p < NP && rc == NRCU_OK; p++) rc = ensure_wave(ctx, p, slots, capacity + slack, ds.depth, glass_branch != 0, nee);
         if (rc == NRCU_OK) break;
         cudaError_t last = cudaGetLastError();
         (void)last;
@@ -667,7 +690,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     // the high-water mark lives in set 0's counter block; every wave counts its rays in its own block
     uint32_t* cnt0 = ctx->ws[0].counters.as<uint32_t>();
     const size_t CS = counter_stride();
-    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + CS * (6 * (size_t)ds.depth + 24));
+    const size_t cnt_bytes = sizeof(uint32_t) * (CNT_QUEUE0 + CS * ((6 + (K > 1 ? K : 0)) * ((size_t)ds.depth + 2)));
     const int sms = sm_count(ctx->device);
     const unsigned shade_grid = (unsigned)sms * (NP > 1 ? dual_shade() : NRCU_SHADE_MINB), big_grid = (unsigned)sms * (NP > 1 ? dual_big() : 8);
     const bool want_stats = stats != nullptr, timing = want_stats && params && (params->flags & NRCU_FLAG_KERNEL_TIMES), gate = ctx->mode == NRCU_MODE_ACC, bvh = ds.root_ref != NRCU_REF_EMPTY;
@@ -682,7 +705,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
 
     struct Pipe {
         bool live; uint32_t w0, kw, n_slots;
-        PathQueue q[2], qs; uint32_t* cnt; uint32_t *d_qn, *d_fetch, *d_nsurv, *d_nshadow, *d_sfetch, *d_snsurv;
+        PathQueue q[2], qs; uint32_t* cnt; uint32_t *d_qn, *d_fetch, *d_nsurv, *d_nshadow, *d_sfetch, *d_snsurv, *d_qr;
         float2* hb; uint32_t* surv; f4* L; cudaStream_t st; unsigned long long* d_rays;
     } P[NRCU_MAX_WAVES];
     for (int p = 0; p < NP; p++) {
@@ -700,6 +723,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         pp.d_nshadow = pp.cnt + CNT_QUEUE0 + CS * 3 * (ds.depth + 2);   // NEE: shadow rays of bounce d, their fetch cursors and survivors
         pp.d_sfetch = pp.cnt + CNT_QUEUE0 + CS * 4 * (ds.depth + 2);
         pp.d_snsurv = pp.cnt + CNT_QUEUE0 + CS * 5 * (ds.depth + 2);
+        pp.d_qr = pp.cnt + CNT_QUEUE0 + CS * 6 * (ds.depth + 2);       // K > 1: region r of the queue entering bounce d counts at d_qr[CS (K d + r)]
         pp.hb = w.hits.as<float2>(); pp.surv = w.surv.as<uint32_t>(); pp.L = w.L.as<f4>();
     }
 
@@ -728,14 +752,22 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                 if (!pp.live) continue;
                 cudaStream_t st = pp.st;
                 PathQueue qi = pp.q[d & 1], qo = pp.q[(d + 1) & 1];
+                // the queue entering bounce 0 is dense (one counter, written by k_raygen); later queues come in K regions
+                const QRegions rin = (K > 1 && d > 0) ? QRegions{pp.d_qr + CS * K * d, logk, (uint32_t)CS} : QRegions{pp.d_qn + CS * d, 0u, (uint32_t)CS};
+                uint32_t* const cnt_out = K > 1 ? pp.d_qr + CS * K * (d + 1) : pp.d_qn + CS * (d + 1);
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                 if (d > 0) {
-                    if (big_balanced()) {
-                        if (gate) k_big_balanced<true, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u);
-                        else k_big_balanced<false, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u);
+                    if (big_balanced() == 2 && NRCU_OPT_RAYCOUNT) {
+                        const unsigned g64 = (unsigned)sms * dual_big64();
+                        if (gate) k_big_balanced64<true><<<g64, 32 * NRCU_BIG64_WARPS, 0, st>>>(ds, qi, rin, pp.hb, pp.surv, pp.d_nsurv + CS * d);
+                        else k_big_balanced64<false><<<g64, 32 * NRCU_BIG64_WARPS, 0, st>>>(ds, qi, rin, pp.hb, pp.surv, pp.d_nsurv + CS * d);
                     }
-                    else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
-                    else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, pp.d_qn + CS * d, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
+                    else if (big_balanced()) {
+                        if (gate) k_big_balanced<true, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, rin.cnt, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u, rin.logk, rin.cs);
+                        else k_big_balanced<false, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, rin.cnt, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u, rin.logk, rin.cs);
+                    }
+                    else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, rin, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
+                    else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, rin, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
                     CTX_LAUNCH_CHECK("k_big");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 3), st); spans.push_back({ev_i, ev_i + 3, 0}); }
@@ -745,7 +777,10 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                     CTX_LAUNCH_CHECK("k_trace");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i + 3, ev_i + 1, 2}); }
-#define NRCU_SHADE(N, B) k_shade<N, B><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, pp.d_qn + CS * d, pp.hb, qo, pp.d_qn + CS * (d + 1), capacity, pp.L, pp.qs, pp.d_nshadow + CS * d)
+#define NRCU_SHADE(N, B) k_shade<N, B><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, rin, pp.hb, qo, cnt_out, logk, capacity + slack, pp.L, pp.qs, pp.d_nshadow + CS * d)
+                if (shade_pool() && !nee && !glass_branch)
+                    k_shade_pool<false><<<shade_grid, 256, 0, st>>>(ds, seed, d, pp.w0, qi, rin, pp.hb, qo, cnt_out, logk, capacity + slack, pp.L);
+                else
 #if NRCU_OPT_BRANCH_TEMPLATE
                 if (glass_branch) { if (nee) NRCU_SHADE(true, true); else NRCU_SHADE(false, true); }
                 else { if (nee) NRCU_SHADE(true, false); else NRCU_SHADE(false, false); }
@@ -797,7 +832,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             Pipe& pp = P[p];
             if (!pp.live) continue;
             if (NP > 1 && acc_recorded) CTX_CUDA(cudaStreamWaitEvent(pp.st, ctx->ev_acc, 0));
-            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw, pp.d_qn, nee ? pp.d_nshadow : nullptr, (uint32_t)CS, ds.depth, NRCU_RC_A);
+            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw, pp.d_qn, pp.d_qr, K, nee ? pp.d_nshadow : nullptr, (uint32_t)CS, ds.depth, NRCU_RC_A);
             CTX_LAUNCH_CHECK("k_accumulate");
             if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_acc, pp.st)); acc_recorded = true; }
         }
@@ -962,8 +997,8 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                     else k_regen_init<false><<<gen_grid, 256, 0, st>>>(ds, seed, s0, n_samples, pp.lane0, pp.n_slots, pp.q, pp.lacc, pp.hits, pp.surv, n_surv);
                     CTX_LAUNCH_CHECK("k_regen_init");
                 } else {
-                    if (gate) k_big_balanced<true, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots);
-                    else k_big_balanced<false, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots);
+                    if (gate) k_big_balanced<true, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots, 0u, 1u);
+                    else k_big_balanced<false, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots, 0u, 1u);
                     CTX_LAUNCH_CHECK("k_big_balanced (slots)");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }

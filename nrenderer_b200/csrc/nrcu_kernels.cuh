@@ -76,6 +76,31 @@ __global__ void k_raycast(DScene s, f4* rgba, unsigned long long* ray_counter) {
 // slot = sample_in_wave * n_pixels + pixel identifies the path; its radiance lands in L[slot].
 struct PathQueue { f4* a; float2* b; f4* c; uint32_t* d; };
 
+// QUEUE REGIONS.  Every warp of the shading kernel allocates its output entries with one lane-0 atomicAdd on the queue's
+// size counter; the L2 serialises atomics per address (1.5/ns, tools/micro/atomic_bench.cu) and everything else that is
+// routed to that slice waits behind them (ncu source page of k_shade: the two hottest stall sites are the shuffle that
+// waits for the atomic and the first use of the prefetched queue entry).  So a queue is split into K = 2^logk REGIONS, each
+// with a counter on a line of its own; the shading warp that works on input block pb (32 entries) appends to region
+// pb mod K.  Regions are interleaved in the array by blocks of 32 entries - entry p of region r lives at
+// ((p / 32) K + r) 32 + p mod 32 - so the queue stays ONE flat array that consumers walk block by block with their
+// software pipeline intact; a block's live lanes are those below its region's count.  The regions receive every K-th
+// block's survivors and stay equally long up to a few blocks, so the only dead lanes are those of the last blocks.
+// K = 1 is the plain compacted queue.
+struct QRegions { const uint32_t* cnt; uint32_t logk, cs; };   // count of region r at cnt[r * cs]
+// lane r keeps region r's count; returns the number of 32-entry blocks the queue spans in the array
+__device__ __forceinline__ uint32_t regions_begin(const QRegions& qr, uint32_t lane, uint32_t& my_cnt) {
+    my_cnt = lane < (1u << qr.logk) ? qr.cnt[(size_t)lane * qr.cs] : 0u;
+    const uint32_t b = (my_cnt + 31u) >> 5;
+    uint32_t ext = b ? ((b - 1u) << qr.logk) + lane + 1u : 0u;   // region r's last block sits at array block (b - 1) K + r
+    for (int o = 16; o > 0; o >>= 1) ext = max(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+    return ext;
+}
+// is lane `lane` of array block pb a live entry?
+__device__ __forceinline__ bool region_live(const QRegions& qr, uint32_t my_cnt, uint32_t pb, uint32_t lane) {
+    const uint32_t c = __shfl_sync(0xffffffffu, my_cnt, pb & ((1u << qr.logk) - 1u));
+    return ((pb >> qr.logk) << 5) + lane < c;
+}
+
 // The wide-primitive list staged in shared memory (read as warp-wide broadcasts).
 struct BigList {
     f4 g[NRCU_MAX_BIG * 3]; f4 b[NRCU_MAX_BIG * 2]; f4 bd[NRCU_MAX_BIG * 2]; uint32_t m[NRCU_MAX_BIG];
@@ -151,29 +176,31 @@ __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_
 // BVH (conservative test against the BVH bounds with the provisional t) to the survivor list with one
 // atomic per warp.  On the Cornell-box scenes most rays end here.
 template <bool GATE>
-__global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
+__global__ void __launch_bounds__(256) k_big(DScene s, PathQueue q, QRegions rin, float2* hits,
                                             uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
     __shared__ BigList bl;
     bl.load(s);
-    const uint32_t n = *n_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t my_cnt;
+    const uint32_t nblocks = regions_begin(rin, lane, my_cnt);
     // software pipeline as in k_shade: the next ray is requested before waiting for the survivor-list atomic
     f4 a = mk4(0, 0, 0, 0); float2 b = make_float2(0.f, 0.f);
-    { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
-    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
-        const uint32_t i = base + lane;
+    if (warp_global < nblocks) { const uint32_t i0 = warp_global * 32u + lane; a = q.a[i0]; b = q.b[i0]; }
+    for (uint32_t pb = warp_global; pb < nblocks; pb += warps_total) {
+        const uint32_t i = pb * 32u + lane;
+        const bool live = region_live(rin, my_cnt, pb, lane);
         bool more = false;
-        if (i < n) {
+        if (live) {
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             more = stage1<GATE>(s, bl, r, i, hits);
         }
-        if (lane == 0 && ray_counter) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        if (ray_counter) { const uint32_t ml = __ballot_sync(0xffffffffu, live); if (lane == 0) atomicAdd(ray_counter, (unsigned long long)__popc(ml)); }
         const uint32_t m = __ballot_sync(0xffffffffu, more);
         uint32_t start = 0;
         if (lane == 0 && m) start = atomicAdd(n_surv, (uint32_t)__popc(m));
-        { const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; } }
+        if (pb + warps_total < nblocks) { const uint32_t inext = i + warps_total * 32u; a = q.a[inext]; b = q.b[inext]; }
         if (m) {
             start = __shfl_sync(0xffffffffu, start, 0);
             if (more) surv[start + __popc(m & ((1u << lane) - 1u))] = i;
@@ -203,25 +230,32 @@ __device__ __forceinline__ bool regen_anyone_alive(const uint32_t* flags) {
     if (threadIdx.x < NRCU_REGEN_FLAGS) v = flags[threadIdx.x * NRCU_REGEN_FLAG_STRIDE];
     return __syncthreads_or((int)v) != 0;
 }
+#ifndef NRCU_BIGB_MINB
+#define NRCU_BIGB_MINB 4
+#endif
 template <bool GATE, bool SLOTS>
-__global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
-                                                                       uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter, uint32_t n_fixed) {
+__global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS, NRCU_BIGB_MINB) k_big_balanced(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
+                                                                       uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter, uint32_t n_fixed,
+                                                                       uint32_t in_logk, uint32_t in_cs) {
     __shared__ BigList bl;
     __shared__ unsigned short pairs[NRCU_BIGB_WARPS][32 * NRCU_MAX_BIG];
     __shared__ float rays[NRCU_BIGB_WARPS][6][32];
     __shared__ unsigned long long best[NRCU_BIGB_WARPS][32];
     if (SLOTS && !regen_anyone_alive(n_ptr)) return;
     bl.load(s);
-    const uint32_t n = SLOTS ? n_fixed : *n_ptr;
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, lt = (1u << lane) - 1u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // the wavefront's queue comes in regions (QRegions above); the slot array of the regeneration scheduler is one dense range
+    const QRegions rin = {n_ptr, SLOTS ? 0u : in_logk, in_cs};
+    uint32_t my_cnt = 0;
+    const uint32_t n = SLOTS ? n_fixed : regions_begin(rin, lane, my_cnt) * 32u;   // array extent in entries (whole blocks)
     unsigned short* my_pairs = pairs[wib];
     f4 a = mk4(0, 0, 0, 0); float2 b = make_float2(0.f, 0.f);
     { const uint32_t i0 = warp_global * 32u + lane; if (i0 < n) { a = q.a[i0]; b = q.b[i0]; } }
     for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
         const uint32_t i = base + lane;
-        const bool live = SLOTS ? (i < n && a.x == a.x) : i < n;
+        const bool live = SLOTS ? (i < n && a.x == a.x) : region_live(rin, my_cnt, base >> 5, lane);
         if (SLOTS && !__any_sync(0xffffffffu, live)) {   // a warp of finished slots (end of the frame): only keep the pipeline going
             const uint32_t inext = i + warps_total * 32u; if (inext < n) { a = q.a[inext]; b = q.b[inext]; }
             continue;
@@ -284,8 +318,127 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS) k_big_balanced(DScene s,
             more = bvh_reachable(s, rp, best_t);
         }
         __syncwarp();   // the shared lists are rewritten by the next iteration
-        if (!SLOTS && ray_counter && lane == 0) atomicAdd(ray_counter, (unsigned long long)min(32u, n - base));
+        if (!SLOTS && ray_counter) { const uint32_t ml = __ballot_sync(0xffffffffu, live); if (lane == 0) atomicAdd(ray_counter, (unsigned long long)__popc(ml)); }
         append_survivors(more, i, surv, n_surv);
+    }
+}
+
+// k_big_balanced with TWO rays per lane (64 rays per warp iteration).  Same passes, same arithmetic, same answers; what
+// changes is the shape of the work:
+//   * pass 1 tests one wide primitive against two independent rays per lane: the record is read once (2 LDS.128 per 64
+//     rays), and the two slab tests interleave in the pipeline (the kernel ran at 77 % issue-active whether 3 or 4 CTAs
+//     were resident per SM, i.e. it waits on its own dependent chains, not for warps);
+//   * the pair list of 64 rays (~135 pairs) fills the 32-wide rounds of pass 2 better than two lists of ~67 (2.75 rounds
+//     per 32 rays -> ~2.35), and the loop overhead, the prefetch and the survivor append are paid once per 64 rays.
+// Four warps per CTA: the pair list of a warp is 64 x NRCU_MAX_BIG entries.
+#define NRCU_BIG64_WARPS 4
+#ifndef NRCU_BIG64_MINB
+#define NRCU_BIG64_MINB 6
+#endif
+template <bool GATE>
+__global__ void __launch_bounds__(32 * NRCU_BIG64_WARPS, NRCU_BIG64_MINB) k_big_balanced64(DScene s, PathQueue q, QRegions rin, float2* hits,
+                                                                                         uint32_t* surv, uint32_t* n_surv) {
+    __shared__ BigList bl;
+    __shared__ unsigned short pairs[NRCU_BIG64_WARPS][64 * NRCU_MAX_BIG];
+    __shared__ float rays[NRCU_BIG64_WARPS][6][64];
+    __shared__ unsigned long long best[NRCU_BIG64_WARPS][64];
+    bl.load(s);
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t my_cnt;
+    const uint32_t n = regions_begin(rin, lane, my_cnt) * 32u;   // array extent in entries (whole blocks of 32)
+    unsigned short* my_pairs = pairs[wib];
+    f4 a0 = mk4(0, 0, 0, 0), a1 = a0; float2 b0 = make_float2(0.f, 0.f), b1 = b0;
+    {
+        const uint32_t i0 = warp_global * 64u + lane;
+        if (i0 < n) { a0 = q.a[i0]; b0 = q.b[i0]; }
+        if (i0 + 32u < n) { a1 = q.a[i0 + 32u]; b1 = q.b[i0 + 32u]; }
+    }
+    for (uint32_t base = warp_global * 64u; base < n; base += warps_total * 64u) {
+        const uint32_t i0 = base + lane, i1 = i0 + 32u;
+        const bool live0 = region_live(rin, my_cnt, base >> 5, lane), live1 = region_live(rin, my_cnt, (base >> 5) + 1u, lane);   // a block past the extent has no live lane
+        Ray r0, r1;
+        r0.o = mk3(a0.x, a0.y, a0.z); r0.d = mk3(a0.w, b0.x, b0.y);
+        r1.o = mk3(a1.x, a1.y, a1.z); r1.d = mk3(a1.w, b1.x, b1.y);
+        const RayPrep rp0 = prep_ray(r0), rp1 = prep_ray(r1);
+        rays[wib][0][lane] = r0.o.x; rays[wib][1][lane] = r0.o.y; rays[wib][2][lane] = r0.o.z;
+        rays[wib][3][lane] = r0.d.x; rays[wib][4][lane] = r0.d.y; rays[wib][5][lane] = r0.d.z;
+        rays[wib][0][lane + 32] = r1.o.x; rays[wib][1][lane + 32] = r1.o.y; rays[wib][2][lane + 32] = r1.o.z;
+        rays[wib][3][lane + 32] = r1.d.x; rays[wib][4][lane + 32] = r1.d.y; rays[wib][5][lane + 32] = r1.d.z;
+        best[wib][lane] = NRCU_BEST_NONE; best[wib][lane + 32] = NRCU_BEST_NONE;
+        // pass 1 (see k_big_balanced): an x offset of -inf keeps a lane without a ray out of the candidate lists
+        uint32_t total = 0;
+        const float nox0 = live0 ? -rp0.oinv.x : -NRCU_INF, nox1 = live1 ? -rp1.oinv.x : -NRCU_INF;
+        const vec3 ainv0 = mk3(fabsf(rp0.inv.x), fabsf(rp0.inv.y), fabsf(rp0.inv.z)), ainv1 = mk3(fabsf(rp1.inv.x), fabsf(rp1.inv.y), fabsf(rp1.inv.z));
+        for (uint32_t k = 0; k < s.n_big; k++) {
+            const f4 bc = bl.bd[2 * k], bh = bl.bd[2 * k + 1];
+            float tn0, tf0, tn1, tf1;
+            slab_center_extent(bc, bh, rp0, ainv0, nox0, tn0, tf0);
+            slab_center_extent(bc, bh, rp1, ainv1, nox1, tn1, tf1);
+            const bool c0 = tn0 <= tf0, c1 = tn1 <= tf1;
+            const uint32_t m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
+            const uint32_t n0 = __popc(m0);
+            if (c0) my_pairs[total + __popc(m0 & lt)] = (unsigned short)(lane | (k << 6));
+            if (c1) my_pairs[total + n0 + __popc(m1 & lt)] = (unsigned short)((lane + 32u) | (k << 6));
+            total += n0 + __popc(m1);
+        }
+        {   // prefetch the next 64 rays
+            const uint32_t j0 = i0 + warps_total * 64u;
+            if (j0 < n) { a0 = q.a[j0]; b0 = q.b[j0]; }
+            if (j0 + 32u < n) { a1 = q.a[j0 + 32u]; b1 = q.b[j0 + 32u]; }
+        }
+        __syncwarp();
+        // pass 2: 32 exact tests per round
+        for (uint32_t jb = 0; jb < total; jb += 32u) {
+            const uint32_t j = jb + lane;
+            if (j < total) {
+                const uint32_t p = my_pairs[j], ol = p & 63u, k = p >> 6;
+                Ray pr; pr.o = mk3(rays[wib][0][ol], rays[wib][1][ol], rays[wib][2][ol]); pr.d = mk3(rays[wib][3][ol], rays[wib][4][ol], rays[wib][5][ol]);
+                float bt = __uint_as_float((uint32_t)(best[wib][ol] >> 32));
+                int bi = 0x7fffffff;
+                prim_test<false>(pr, mk3(0.f), bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b, bl.m[k], bt, bi);
+                if (bi != 0x7fffffff) atomicMin(&best[wib][ol], ((unsigned long long)__float_as_uint(bt) << 32) | (unsigned long long)(((uint32_t)bi << 5) | k));
+            }
+        }
+        __syncwarp();
+        bool more0 = false, more1 = false;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+            const bool live = hlf ? live1 : live0;
+            if (live) {
+                const Ray& r = hlf ? r1 : r0;
+                const RayPrep& rp = hlf ? rp1 : rp0;
+                const unsigned long long key = best[wib][lane + 32 * hlf];
+                float best_t = NRCU_INF; int best_id = -1;
+                if (key != NRCU_BEST_NONE) {
+                    best_t = __uint_as_float((uint32_t)(key >> 32)); best_id = (int)((uint32_t)key >> 5);
+                    if (GATE) {
+                        const uint32_t kb = (uint32_t)key & 31u;
+                        const vec3 ginv = gate_inverse(r, rp);
+                        if (!bounds_intersectp_inv(bl.b[2 * kb], bl.b[2 * kb + 1], r, ginv.x, ginv.y, ginv.z)) {   // rare: gate per candidate
+                            best_t = NRCU_INF; best_id = -1;
+                            for (uint32_t k = 0; k < s.n_big; k++)
+                                prim_test<true>(r, ginv, bl.g[3 * k], bl.g[3 * k + 1], bl.g[3 * k + 2], bl.b + 2 * k, bl.m[k], best_t, best_id);
+                        }
+                    }
+                }
+                hits[hlf ? i1 : i0] = make_float2(best_t, __int_as_float(best_id));
+                const bool more = bvh_reachable(s, rp, best_t);
+                if (hlf) more1 = more; else more0 = more;
+            }
+        }
+        __syncwarp();   // the shared lists are rewritten by the next iteration
+        {   // both halves' survivors with one atomic
+            const uint32_t m0 = __ballot_sync(0xffffffffu, more0), m1 = __ballot_sync(0xffffffffu, more1);
+            if (m0 | m1) {
+                uint32_t start = 0;
+                if (lane == 0) start = atomicAdd(n_surv, (uint32_t)(__popc(m0) + __popc(m1)));
+                start = __shfl_sync(0xffffffffu, start, 0);
+                if (more0) surv[start + __popc(m0 & lt)] = i0;
+                if (more1) surv[start + __popc(m0) + __popc(m1 & lt)] = i1;
+            }
+        }
     }
 }
 
@@ -643,32 +796,38 @@ __global__ void k_trace_linear_rc(DScene s, PathQueue q, uint32_t n, float2* hit
 #endif
 template <bool NEE, bool BRANCH_T>
 __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64_t seed, uint32_t d, int glass_branch_rt, uint32_t sample0,
-                                              PathQueue qi, const uint32_t* n_in_ptr, const float2* hits,
-                                              PathQueue qo, uint32_t* n_out_ptr, uint32_t out_capacity, f4* L,
+                                              PathQueue qi, QRegions rin, const float2* hits,
+                                              PathQueue qo, uint32_t* n_out_ptr, uint32_t out_logk, uint32_t out_capacity, f4* L,
                                               PathQueue qs, uint32_t* n_shadow_ptr) {
 #if NRCU_OPT_BRANCH_TEMPLATE
     constexpr bool BRANCH = BRANCH_T;
 #else
     const bool BRANCH = glass_branch_rt != 0;   // A/B only: the round-1 form with the mode as a kernel argument
 #endif
-    const uint32_t n = *n_in_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t npix = s.width * s.height;
+    uint32_t my_cnt;
+    const uint32_t nblocks = regions_begin(rin, lane, my_cnt);
     f4 a = mk4(0, 0, 0, 0), c = a; float2 b = make_float2(0.f, 0.f), h = b; uint32_t br = 0;
-    auto load_entry = [&](uint32_t j) {
-        if (j >= n) return;
+    // Whole blocks are read (lanes past their region's count hold entries nobody uses), and the block index is clamped
+    // instead of tested: with a branch around them ptxas sank these loads below the shuffle that waits for the slot
+    // atomic, so the atomic's round trip and the loads' latency added up in every iteration (ncu source page: the two
+    // hottest stall sites of the kernel); without control flow they issue right behind the atomic.
+    auto load_entry = [&](uint32_t blk) {
+        const uint32_t j = min(blk, nblocks - 1u) * 32u + lane;
         a = qi.a[j]; b = qi.b[j]; c = qi.c[j]; h = hits[j];
         if (BRANCH) br = qi.d[j];
     };
-    load_entry(warp_global * 32u + lane);
-    for (uint32_t base = warp_global * 32u; base < n; base += warps_total * 32u) {
-        const uint32_t i = base + lane;
+    if (nblocks == 0) return;
+    load_entry(warp_global);
+    for (uint32_t pb = warp_global; pb < nblocks; pb += warps_total) {
+        const bool live = region_live(rin, my_cnt, pb, lane);
         int n_out = 0;
         PathStep ps;
         uint32_t slot = 0, branch = 0;
-        if (i < n) {
+        if (live) {
             Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
             vec3 thr = mk3(c.x, c.y, c.z);
             slot = (uint32_t)f2i(c.w) & 0x7fffffffu; branch = br;
@@ -694,11 +853,12 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
         const uint32_t m1 = __ballot_sync(0xffffffffu, n_out >= 1), m2 = BRANCH ? __ballot_sync(0xffffffffu, n_out == 2) : 0u;
         const uint32_t total = __popc(m1) + __popc(m2);
         uint32_t start = 0;
-        if (lane == 0 && total) start = atomicAdd(n_out_ptr, total);
-        load_entry(i + warps_total * 32u);   // prefetch the next iteration's entry while the atomic is in flight
+        const uint32_t r_out = pb & ((1u << out_logk) - 1u);   // this block's survivors go to region pb mod K of the output queue
+        if (lane == 0 && total) start = atomicAdd(n_out_ptr + (size_t)r_out * rin.cs, total);
+        load_entry(pb + warps_total);   // prefetch the next iteration's entry while the atomic is in flight
         const uint32_t lt = (1u << lane) - 1u;
         if (NEE) {   // shadow rays of this bounce, compacted into their own queue
-            const bool sh = i < n && ps.nee;
+            const bool sh = live && ps.nee;
             const uint32_t ms = __ballot_sync(0xffffffffu, sh);
             if (ms) {
                 uint32_t s0 = 0;
@@ -715,7 +875,9 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
         }
         if (total == 0) continue;   // warp-uniform
         start = __shfl_sync(0xffffffffu, start, 0);
-        const uint32_t pos1 = start + __popc(m1 & lt), pos2 = start + __popc(m1) + __popc(m2 & lt);
+        // entry p of region r sits at ((p / 32) K + r) 32 + p mod 32 (K = 1: at p)
+        const uint32_t p1 = start + __popc(m1 & lt), p2 = start + __popc(m1) + __popc(m2 & lt);
+        const uint32_t pos1 = ((((p1 >> 5) << out_logk) + r_out) << 5) | (p1 & 31u), pos2 = ((((p2 >> 5) << out_logk) + r_out) << 5) | (p2 & 31u);
         if (n_out >= 1 && pos1 < out_capacity) {
             qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
             qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
@@ -729,6 +891,143 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
             qo.d[pos2] = branch | (1u << (d & 31u));
         }
     }
+}
+
+// k_shade with a per-warp POOL of surface hits (the default estimator: no NEE, no branching glass).
+// In k_shade a lane whose ray left the scene or reached the light has nothing to do during the ~700 instructions of the
+// surface shading (hit record and material gathers, Philox, hemisphere sample, Onb, two normalisations, six IEEE
+// divisions): 22-24 of 32 lanes per instruction at the bounces after the first (ncu), and the whole frame runs at the issue
+// rate the stage-1 kernel has alone, so idle lanes are lost throughput.  Here a warp works in two phases:
+//   A  (every entry of a block)  closest light, "is the object hit in front of it?"; a path that ends here stores its
+//      radiance at once; a surface hit is appended - ballot/popc rank, 12 words - to the warp's ring in shared memory;
+//   B  (whenever the ring holds 32 hits, and once at the end for the rest)  path_vertex_hit on 32 DENSE lanes, then the
+//      usual warp-aggregated append to the next queue.
+// Same arithmetic per path, same result per slot; only the order in which a warp meets its paths changes.
+// Output region of a round: the warp's round counter, rotated by the warp index - every warp spreads its rounds evenly
+// over the K regions, so the regions stay equally long up to one round per warp (the slack nrcu_api.cu allocates).
+#define NRCU_POOL_RING 64
+// Where the next block's queue entry is requested: 0 before phase A, 1 before the shading round, 2 at the end of the
+// iteration (default), 3 = 0 through cp.async into shared memory.  Same-call A/B on cfg3 (profiles/r2_history.md):
+// 0 3144, 1 3181, 2 3305, 3 3297 Mpath-samples/s - the twelve registers of an entry in flight across the shading round cost
+// 60-70 bytes of spills per thread, which matters more than the exposed load latency (other warps cover it).
+#ifndef NRCU_POOL_PREFETCH_LATE
+#define NRCU_POOL_PREFETCH_LATE 2
+#endif
+template <bool DUMMY>
+__global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_pool(DScene s, uint64_t seed, uint32_t d, uint32_t sample0,
+                                                                       PathQueue qi, QRegions rin, const float2* hits,
+                                                                       PathQueue qo, uint32_t* n_out_ptr, uint32_t out_logk, uint32_t out_capacity, f4* L) {
+    __shared__ float ring[8][12][NRCU_POOL_RING];   // [warp][word][entry]: o.xyz d.xyz thr.xyz slot t id
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t npix = s.width * s.height;
+    uint32_t my_cnt;
+    const uint32_t nblocks = regions_begin(rin, lane, my_cnt);
+    if (nblocks == 0) return;
+    float (*rg)[NRCU_POOL_RING] = ring[wib];
+    uint32_t head = 0, fill = 0, round = warp_global;   // ring state and round counter: warp-uniform
+    f4 a, c; float2 b, h;
+#if NRCU_POOL_PREFETCH_LATE == 3
+    // the next block travels global -> shared with cp.async (no registers held across the shading round)
+    __shared__ f4 st_a[8][32], st_c[8][32];
+    __shared__ float2 st_b[8][32], st_h[8][32];
+    auto cp16 = [](void* dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); };
+    auto cp8 = [](void* dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); };
+    auto load_entry = [&](uint32_t blk) {
+        const uint32_t j = min(blk, nblocks - 1u) * 32u + lane;
+        cp16(&st_a[wib][lane], qi.a + j); cp8(&st_b[wib][lane], qi.b + j); cp16(&st_c[wib][lane], qi.c + j); cp8(&st_h[wib][lane], hits + j);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto take_entry = [&]() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        a = st_a[wib][lane]; b = st_b[wib][lane]; c = st_c[wib][lane]; h = st_h[wib][lane];
+    };
+#else
+    auto load_entry = [&](uint32_t blk) {   // clamped, no branch: see k_shade
+        const uint32_t j = min(blk, nblocks - 1u) * 32u + lane;
+        a = qi.a[j]; b = qi.b[j]; c = qi.c[j]; h = hits[j];
+    };
+    auto take_entry = [&]() {};
+#endif
+    // phase B on the `take` oldest ring entries
+    auto shade_round = [&](uint32_t take) {
+        int n_out = 0;
+        PathStep ps;
+        uint32_t slot = 0;
+        if (lane < take) {
+            const uint32_t e = (head + lane) & (NRCU_POOL_RING - 1u);
+            Ray r; r.o = mk3(rg[0][e], rg[1][e], rg[2][e]); r.d = mk3(rg[3][e], rg[4][e], rg[5][e]);
+            const vec3 thr = mk3(rg[6][e], rg[7][e], rg[8][e]);
+            slot = (uint32_t)f2i(rg[9][e]);
+            const float t = rg[10][e]; const int id = f2i(rg[11][e]);
+            path_step_init(ps, r, thr);
+            path_vertex_hit<false>(ps, s, seed, slot % npix, sample0 + slot / npix, d, 0u, r, thr, t, id, 0);
+            if (ps.action == PATH_TERMINATE) {
+                if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);
+            } else n_out = 1;
+        }
+        const uint32_t m1 = __ballot_sync(0xffffffffu, n_out != 0), total = __popc(m1);
+        const uint32_t r_out = round & ((1u << out_logk) - 1u);
+        round++;
+        if (total == 0) return;   // warp-uniform
+        uint32_t start = 0;
+        if (lane == 0) start = atomicAdd(n_out_ptr + (size_t)r_out * rin.cs, total);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        const uint32_t p1 = start + __popc(m1 & lt);
+        const uint32_t pos1 = ((((p1 >> 5) << out_logk) + r_out) << 5) | (p1 & 31u);
+        if (n_out && pos1 < out_capacity) {
+            qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
+            qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
+            qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)slot));
+        }
+    };
+    load_entry(warp_global);
+    for (uint32_t pb = warp_global; pb < nblocks; pb += warps_total) {
+        // ---- phase A: where does the path go? ----------------------------------------------------------------------
+        const bool live = region_live(rin, my_cnt, pb, lane);
+        bool surface = false;
+        take_entry();
+        Ray r; r.o = mk3(a.x, a.y, a.z); r.d = mk3(a.w, b.x, b.y);
+        const vec3 thr = mk3(c.x, c.y, c.z);
+        const float slot_f = c.w, t = h.x, id_f = h.y;
+#if !NRCU_POOL_PREFETCH_LATE || NRCU_POOL_PREFETCH_LATE == 3
+        load_entry(pb + warps_total);   // the next block: in flight during this block's phase A and the shading round
+#endif
+        if (live) {
+            vec3 radiance;
+            const float tl = closest_light(s, r, radiance);
+            const int id = __float_as_int(id_f);
+            if (id >= 0 && t < tl) surface = true;
+            else {   // path_vertex's other branches: the light, or nothing (environment map / black)
+                vec3 out = mk3(0.f);
+                if (tl != NRCU_INF) out = thr * radiance;
+                else if (s.env_rgba && s.mode == MODE_ACC) out = thr * env_lookup(s, r.d);
+                if (out.x != 0.f || out.y != 0.f || out.z != 0.f) L[(uint32_t)f2i(slot_f) & 0x7fffffffu] = mk4(out.x, out.y, out.z, 0.f);
+            }
+        }
+        const uint32_t ms = __ballot_sync(0xffffffffu, surface);
+        if (surface) {
+            const uint32_t e = (head + fill + __popc(ms & lt)) & (NRCU_POOL_RING - 1u);
+            rg[0][e] = r.o.x; rg[1][e] = r.o.y; rg[2][e] = r.o.z; rg[3][e] = r.d.x; rg[4][e] = r.d.y; rg[5][e] = r.d.z;
+            rg[6][e] = thr.x; rg[7][e] = thr.y; rg[8][e] = thr.z; rg[9][e] = i2f((int)((uint32_t)f2i(slot_f) & 0x7fffffffu)); rg[10][e] = t; rg[11][e] = id_f;
+        }
+        fill += __popc(ms);
+        __syncwarp();
+#if NRCU_POOL_PREFETCH_LATE == 1
+        load_entry(pb + warps_total);   // requested before the shading round, not live during phase A
+#endif
+        // ---- phase B: a dense warp of surface hits --------------------------------------------------------------------
+        if (fill >= 32u) {
+            shade_round(32u);
+            head = (head + 32u) & (NRCU_POOL_RING - 1u); fill -= 32u;
+            __syncwarp();
+        }
+#if NRCU_POOL_PREFETCH_LATE == 2
+        load_entry(pb + warps_total);
+#endif
+    }
+    if (fill) shade_round(fill);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1004,12 +1303,14 @@ __global__ void k_clamp_count(uint32_t* n_ptr, uint32_t capacity, uint32_t* high
 // through one closest-hit query - so thread 0 adds those counters up here instead of every warp of the closest-hit kernels
 // sending an atomic per 32 rays.
 __global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k, uint32_t n_samples,
-                             const uint32_t* qn, const uint32_t* nshadow, uint32_t counter_stride, uint32_t depth, unsigned long long* ray_counter) {
+                             const uint32_t* qn, const uint32_t* qr, uint32_t regions, const uint32_t* nshadow, uint32_t counter_stride, uint32_t depth, unsigned long long* ray_counter) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0 && ray_counter) {
         unsigned long long rays = 0;
         for (uint32_t d = 0; d < depth; d++) {
-            rays += qn[(size_t)counter_stride * d];
+            // bounce 0's queue is dense (qn[0]); with regions > 1 the queue entering bounce d >= 1 is counted per region in qr
+            if (d == 0 || regions <= 1) rays += qn[(size_t)counter_stride * d];
+            else for (uint32_t r = 0; r < regions; r++) rays += qr[(size_t)counter_stride * ((size_t)regions * d + r)];
             if (nshadow && d + 1 < depth) rays += nshadow[(size_t)counter_stride * d];
         }
         *ray_counter += rays;   // one wave accumulates at a time on this counter (its own block of counters)

@@ -463,18 +463,13 @@ NR_HD bool nee_visible(const DScene& s, const Ray& shadow, int light, float t_ob
     return !(id_obj >= 0 && t_obj < tl);
 }
 
-// One iteration of trace() for a ray at bounce `d` (d < depth) whose closest object hit is
-// (t, id) — AccPathTracer.cpp:121-181.  `branch` = glass branch bits (RNG block).
-template <bool NEE = false>
-NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
-                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode, bool skip_light = false) {
-    PathStep ps; ps.action = PATH_TERMINATE; ps.radiance = mk3(0.f);
-    ps.next = ray; ps.thr = thr; ps.next2 = ray; ps.thr2 = mk3(0.f);
-    ps.nee = false; ps.shadow = ray; ps.nee_contrib = mk3(0.f); ps.nee_light = -1; ps.next_skips_light = false;
-    vec3 radiance;
-    int which_light = -1;
-    float tl = closest_light(s, ray, radiance, NEE ? &which_light : nullptr);
-    if (id >= 0 && t < tl) {
+// The surface-hit branch of trace() (AccPathTracer.cpp:131-172): the ray's closest object hit (t, id) is in front of
+// every light.  `ps` comes in initialised (path_vertex below); shared by the per-vertex form and by the pooled shading
+// kernel, which runs it on dense warps of surface hits only.
+template <bool NEE>
+NR_HD void path_vertex_hit(PathStep& ps, const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
+                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode) {
+    {
         vec3 hp = ray_at(ray, t);
         int material;
         vec3 n = hit_normal(s, id, hp, material);
@@ -489,7 +484,7 @@ NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint3
             } else {
                 float q = g.reflex_rate.x + g.reflex_rate.y + g.reflex_rate.z;
                 float q2 = g.refraction_rate.x + g.refraction_rate.y + g.refraction_rate.z;
-                if (refl_zero || !(q + q2 > 0.f)) return ps;
+                if (refl_zero || !(q + q2 > 0.f)) return;
                 float pr = q / (q + q2);
                 u32x4 rn = rng_block(seed, pixel, sample, d, branch);
                 if (u01(rn.z) < pr) { ps.thr = thr * (g.reflex_rate / pr); ps.next = g.reflex; }
@@ -504,7 +499,7 @@ NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint3
         } else {
             // type 0 (any other type falls off the end of the reference's trace(): treated as Lambertian)
             u32x4 rn = rng_block(seed, pixel, sample, d, branch);
-vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(rn.y), f);
+            vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(rn.y), f);
             ps.thr = thr * f; ps.action = PATH_CONTINUE;
             // NEE only where the continuation will really be traced: at the depth limit the reference returns the
             // ambient colour without looking for the light (AccPathTracer.cpp:122)
@@ -520,6 +515,26 @@ vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(r
             if (ps.action == PATH_SPLIT) add = add + ps.thr2 * s.ambient;
             ps.radiance = add; ps.action = PATH_TERMINATE;
         }
+    }
+}
+NR_HD void path_step_init(PathStep& ps, const Ray& ray, vec3 thr) {
+    ps.action = PATH_TERMINATE; ps.radiance = mk3(0.f);
+    ps.next = ray; ps.thr = thr; ps.next2 = ray; ps.thr2 = mk3(0.f);
+    ps.nee = false; ps.shadow = ray; ps.nee_contrib = mk3(0.f); ps.nee_light = -1; ps.next_skips_light = false;
+}
+
+// One iteration of trace() for a ray at bounce `d` (d < depth) whose closest object hit is
+// (t, id) — AccPathTracer.cpp:121-181.  `branch` = glass branch bits (RNG block).
+template <bool NEE = false>
+NR_HD PathStep path_vertex(const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
+                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode, bool skip_light = false) {
+    PathStep ps;
+    path_step_init(ps, ray, thr);
+    vec3 radiance;
+    int which_light = -1;
+    float tl = closest_light(s, ray, radiance, NEE ? &which_light : nullptr);
+    if (id >= 0 && t < tl) {
+        path_vertex_hit<NEE>(ps, s, seed, pixel, sample, d, branch, ray, thr, t, id, glass_branch_mode);
     } else if (tl != NRCU_INF) {
         ps.radiance = thr * radiance;
         if (NEE && skip_light && s.nee == 1) ps.radiance = ps.radiance * mis_light_weight(s, ray, which_light, tl);
