@@ -92,7 +92,7 @@ struct nrcu_ctx {
     uint32_t spp = 0;
     DScene ds{};
     // scene buffers
-    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, materials, area_lights, env, env_tab;
+    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, materials, mat_head, area_lights, env, env_tab;
     // scene-prep sources kept for nrcu_download_primitives
     DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
@@ -274,6 +274,7 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
     UP(mesh_ioff, sc->n_meshes ? sc->mesh_index_offset : &zero_off, (size_t)sc->n_meshes + 1);
     UP(mesh_pos, sc->mesh_positions, 3 * (size_t)hp.total_vertices); UP(mesh_idx, sc->mesh_indices, hp.total_indices); UP(mesh_mat, sc->mesh_material, sc->n_meshes);
     UP(materials, hp.materials.data(), hp.materials.size());
+    UP(mat_head, hp.mat_head.data(), hp.mat_head.size());
     UP(area_lights, hp.lights.data(), hp.lights.size());
 #undef UP
     DScene& ds = ctx->ds;
@@ -332,6 +333,7 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
     ds.prim_geom = ctx->prim_geom.as<f4>(); ds.prim_shade = ctx->prim_shade.as<f4>(); ds.prim_box = ctx->prim_box.as<f4>();
     ds.prim_meta = ctx->prim_meta.as<uint32_t>();
     ds.materials = ctx->materials.as<DMaterial>();
+    ds.mat_head = ctx->mat_head.as<f4>();
     ds.area_lights = ctx->area_lights.as<f4>();
     ctx->spp = sc->samples_per_pixel;
     ctx->mode = mode;

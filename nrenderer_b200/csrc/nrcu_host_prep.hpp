@@ -25,6 +25,7 @@ struct HostPrep {
     std::vector<uint32_t> src_a, src_b;      // primitive order: kind | entity << 2, mesh triangle index
     std::vector<uint32_t> mesh_nodes;        // entity of every MESH node in node order (one transform launch each)
     std::vector<DMaterial> materials;
+    std::vector<f4> mat_head;                // DScene::mat_head
     std::vector<f4> lights;                  // NRCU_LIGHT_F4 float4 per area light
     DCamera cam;
     float mf_u1, mf_u2, mf_cos_phi, mf_sin_phi;
@@ -107,6 +108,12 @@ inline std::string host_prepare(const nrcu_scene* sc, int mode, HostPrep& hp) {
             if (!(m.present & NRCU_MP_ROUGHNESS)) m.roughness = 0.2f;
             if (!(m.present & NRCU_MP_F0)) m.f0 = 0.04;
         }
+    }
+    hp.mat_head.resize(hp.materials.size());
+    for (size_t i = 0; i < hp.materials.size(); i++) {
+        const DMaterial& m = hp.materials[i];
+        const float pi = 3.1415926535898f;   // acc_path_tracing/include/shaders/Shader.hpp:17 (NRCU_PT_PI)
+        hp.mat_head[i] = mk4(m.diffuse_color[0] / pi, m.diffuse_color[1] / pi, m.diffuse_color[2] / pi, i2f((int)m.type));
     }
     // area lights: quad record with n = cross(u,v) (xAreaLight, intersections.cpp:74-93) + radiance
     hp.lights.assign(std::max(sc->n_area_lights, 1u) * NRCU_LIGHT_F4, mk4(0, 0, 0, 0));

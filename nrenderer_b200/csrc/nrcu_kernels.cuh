@@ -906,6 +906,9 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
 // Output region of a round: the warp's round counter, rotated by the warp index - every warp spreads its rounds evenly
 // over the K regions, so the regions stay equally long up to one round per warp (the slack nrcu_api.cu allocates).
 #define NRCU_POOL_RING 64
+#ifndef NRCU_POOL_EARLY_ATOMIC
+#define NRCU_POOL_EARLY_ATOMIC 1
+#endif
 // Where the next block's queue entry is requested: 0 before phase A, 1 before the shading round, 2 at the end of the
 // iteration (default), 3 = 0 through cp.async into shared memory.  Same-call A/B on cfg3 (profiles/r2_history.md):
 // 0 3144, 1 3181, 2 3305, 3 3297 Mpath-samples/s - the twelve registers of an entry in flight across the shading round cost
@@ -951,28 +954,42 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_pool(DScene s, u
     auto take_entry = [&]() {};
 #endif
     // phase B on the `take` oldest ring entries
+    const bool last_bounce = d + 1 == s.depth;
     auto shade_round = [&](uint32_t take) {
         int n_out = 0;
         PathStep ps;
         uint32_t slot = 0;
-        if (lane < take) {
+        const bool act = lane < take;
+        Ray r; vec3 thr = mk3(0.f); HitSetup hs; hs.type = 0u;
+        if (act) {
             const uint32_t e = (head + lane) & (NRCU_POOL_RING - 1u);
-            Ray r; r.o = mk3(rg[0][e], rg[1][e], rg[2][e]); r.d = mk3(rg[3][e], rg[4][e], rg[5][e]);
-            const vec3 thr = mk3(rg[6][e], rg[7][e], rg[8][e]);
+            r.o = mk3(rg[0][e], rg[1][e], rg[2][e]); r.d = mk3(rg[3][e], rg[4][e], rg[5][e]);
+            thr = mk3(rg[6][e], rg[7][e], rg[8][e]);
             slot = (uint32_t)f2i(rg[9][e]);
-            const float t = rg[10][e]; const int id = f2i(rg[11][e]);
+            hs = hit_setup(s, r, rg[10][e], f2i(rg[11][e]));
+        }
+        // When every vertex of the round sits on a material that always continues the path (Lambertian, conductor), the
+        // number of output entries is known before the shading: the slot atomic is issued here and its round trip hides
+        // behind the ~600 instructions of the shading instead of being waited for right after them (ncu: 13 % of the
+        // kernel's stall samples sat on that shuffle).
+        const uint32_t r_out = round & ((1u << out_logk) - 1u);
+        round++;
+        const bool early = NRCU_POOL_EARLY_ATOMIC && __all_sync(0xffffffffu, !act || type_always_continues(hs.type));
+        uint32_t start = 0, total = last_bounce ? 0u : take;
+        if (early && lane == 0 && total) start = atomicAdd(n_out_ptr + (size_t)r_out * rin.cs, total);
+        if (act) {
             path_step_init(ps, r, thr);
-            path_vertex_hit<false>(ps, s, seed, slot % npix, sample0 + slot / npix, d, 0u, r, thr, t, id, 0);
+            path_vertex_shade<false>(ps, s, seed, slot % npix, sample0 + slot / npix, d, 0u, r, thr, hs, 0);
             if (ps.action == PATH_TERMINATE) {
                 if (ps.radiance.x != 0.f || ps.radiance.y != 0.f || ps.radiance.z != 0.f) L[slot] = mk4(ps.radiance.x, ps.radiance.y, ps.radiance.z, 0.f);
             } else n_out = 1;
         }
-        const uint32_t m1 = __ballot_sync(0xffffffffu, n_out != 0), total = __popc(m1);
-        const uint32_t r_out = round & ((1u << out_logk) - 1u);
-        round++;
+        const uint32_t m1 = __ballot_sync(0xffffffffu, n_out != 0);
+        if (!early) {
+            total = __popc(m1);
+            if (lane == 0 && total) start = atomicAdd(n_out_ptr + (size_t)r_out * rin.cs, total);
+        }
         if (total == 0) return;   // warp-uniform
-        uint32_t start = 0;
-        if (lane == 0) start = atomicAdd(n_out_ptr + (size_t)r_out * rin.cs, total);
         start = __shfl_sync(0xffffffffu, start, 0);
         const uint32_t p1 = start + __popc(m1 & lt);
         const uint32_t pos1 = ((((p1 >> 5) << out_logk) + r_out) << 5) | (p1 & 31u);

@@ -86,7 +86,7 @@ NR_HD vec3 mlt_eval(const DScene& s, const float* u, float& film_x, float& film_
                 if (!shade_microfacet(s, m, ray, hp, n, nr, f)) return L;
                 ray = nr; thr = thr * f;
             } else {
-                ray = shade_lambertian(ld3(m.diffuse_color), hp, n, e1, e2, f); thr = thr * f;
+                { const f4 mh = ldg4(s.mat_head + material); ray = shade_lambertian(mk3(mh.x, mh.y, mh.z), hp, n, e1, e2, f); } thr = thr * f;
             }
             if (d + 1 == s.depth) return L + thr * s.ambient;   // trace() at the depth limit (AccPathTracer.cpp:122)
         } else if (tl != NRCU_INF) {

@@ -112,6 +112,7 @@ struct DScene {
     vec3 bvh_lo, bvh_hi;          // padded bounds of everything inside the BVH (lo > hi when it is empty)
     // shading
     const DMaterial* materials;
+    const f4* mat_head;           // per material: (diffuseColor / pi  - Lambertian.cpp:30, the same fp32 division -, type bits): one gather for the common case
     uint32_t n_materials;
     const f4* area_lights;        // NRCU_LIGHT_F4 float4 per light: quad record (as a plane with n = cross(u,v)), radiance, u, v
     uint32_t n_area_lights;

@@ -163,7 +163,9 @@ NR_HD void sincos_det(float a, float& s, float& c) {
 
 // Lambertian::shade (Lambertian.cpp:16-34) + HemiSphere::sample3d (Hemisphere.hpp:24-32) + Onb (Onb.hpp:17-27);
 // factor = attenuation * dot(N, dir) / pdf as used at AccPathTracer.cpp:142.
-NR_HD Ray shade_lambertian(vec3 albedo, vec3 hit_point, vec3 normal, float e1, float e2, vec3& factor) {
+// `attenuation` = albedo / PI (Lambertian.cpp:30), precomputed per material at upload with the same fp32 division
+// (DScene::mat_head): three IEEE divisions per vertex less - 5 % of the shading kernel's instructions.
+NR_HD Ray shade_lambertian(vec3 attenuation, vec3 hit_point, vec3 normal, float e1, float e2, vec3& factor) {
     const float C_PI = 3.14159265358979323846264338327950288f;
     float r = sqrtf(1 - e1 * e1);
     float sn, cs;
@@ -187,9 +189,6 @@ NR_HD Ray shade_lambertian(vec3 albedo, vec3 hit_point, vec3 normal, float e1, f
     vec3 local = x * u + y * v + z * w;
     Ray out; out.o = hit_point; out.d = normalize(local);
     float pdf = 1 / (2 * NRCU_PT_PI);
-    // (albedo / PI precomputed per material was measured twice - at the end of the record and inside its first 32-byte
-    // sector - and lost 0.5 % both times although it removes three IEEE divisions: profiles/r2_history.md)
-    vec3 attenuation = albedo / NRCU_PT_PI;
     float n_dot_in = dot(normal, out.d);
     factor = attenuation * n_dot_in / pdf;
     return out;
@@ -466,15 +465,27 @@ NR_HD bool nee_visible(const DScene& s, const Ray& shadow, int light, float t_ob
 // The surface-hit branch of trace() (AccPathTracer.cpp:131-172): the ray's closest object hit (t, id) is in front of
 // every light.  `ps` comes in initialised (path_vertex below); shared by the per-vertex form and by the pooled shading
 // kernel, which runs it on dense warps of surface hits only.
+// hit point, normal, material of the hit - everything the shading needs that does not depend on random numbers.
+struct HitSetup { vec3 hp, n; int material; f4 mh; uint32_t type; };
+NR_HD HitSetup hit_setup(const DScene& s, const Ray& ray, float t, int id) {
+    HitSetup hs;
+    hs.hp = ray_at(ray, t);
+    hs.n = hit_normal(s, id, hs.hp, hs.material);
+    hs.mh = ldg4(s.mat_head + hs.material);
+    hs.type = s.mode == MODE_ACC ? (uint32_t)f2i(hs.mh.w) : 0u;
+    return hs;
+}
+// Does a vertex on a material of this type always continue the path (below the depth limit)?  Lambertian and conductor
+// vertices do; glass and microfacet vertices can end it (Glass.cpp:15-57, Microfacet.cpp:71-118).
+NR_HD bool type_always_continues(uint32_t type) { return type != 2u && type != 3u; }
 template <bool NEE>
-NR_HD void path_vertex_hit(PathStep& ps, const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
-                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode) {
+NR_HD void path_vertex_shade(PathStep& ps, const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
+                             const Ray& ray, vec3 thr, const HitSetup& hs, int glass_branch_mode) {
     {
-        vec3 hp = ray_at(ray, t);
-        int material;
-        vec3 n = hit_normal(s, id, hp, material);
-        const DMaterial& m = s.materials[material];
-        uint32_t type = s.mode == MODE_ACC ? m.type : 0u;
+        const vec3 hp = hs.hp, n = hs.n;
+        const DMaterial& m = s.materials[hs.material];
+        const f4 mh = hs.mh;
+        const uint32_t type = hs.type;
         if (type == 2u) {
             GlassSplit g = shade_glass(m, ray, hp, n);
             bool refl_zero = is_zero(g.reflex_rate);
@@ -499,7 +510,7 @@ NR_HD void path_vertex_hit(PathStep& ps, const DScene& s, uint64_t seed, uint32_
         } else {
             // type 0 (any other type falls off the end of the reference's trace(): treated as Lambertian)
             u32x4 rn = rng_block(seed, pixel, sample, d, branch);
-            vec3 f; ps.next = shade_lambertian(ld3(m.diffuse_color), hp, n, u01(rn.x), u01(rn.y), f);
+            vec3 f; ps.next = shade_lambertian(mk3(mh.x, mh.y, mh.z), hp, n, u01(rn.x), u01(rn.y), f);
             ps.thr = thr * f; ps.action = PATH_CONTINUE;
             // NEE only where the continuation will really be traced: at the depth limit the reference returns the
             // ambient colour without looking for the light (AccPathTracer.cpp:122)
@@ -516,6 +527,12 @@ NR_HD void path_vertex_hit(PathStep& ps, const DScene& s, uint64_t seed, uint32_
             ps.radiance = add; ps.action = PATH_TERMINATE;
         }
     }
+}
+template <bool NEE>
+NR_HD void path_vertex_hit(PathStep& ps, const DScene& s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t d, uint32_t branch,
+                           const Ray& ray, vec3 thr, float t, int id, int glass_branch_mode) {
+    const HitSetup hs = hit_setup(s, ray, t, id);
+    path_vertex_shade<NEE>(ps, s, seed, pixel, sample, d, branch, ray, thr, hs, glass_branch_mode);
 }
 NR_HD void path_step_init(PathStep& ps, const Ray& ray, vec3 thr) {
     ps.action = PATH_TERMINATE; ps.radiance = mk3(0.f);

@@ -131,7 +131,7 @@ EmuScene* emu_create(const nrcu_scene* sc, int mode) {
     for (uint32_t i = 0; i < n; i++) build_prim(ps, i, mode == NRCU_MODE_RAYCAST, es->geom.data(), es->shade.data(), es->box.data(), es->bound.data(), es->meta.data(), es->export16.data());
     DScene& ds = es->ds;
     ds.prim_geom = es->geom.data(); ds.prim_shade = es->shade.data(); ds.prim_box = es->box.data(); ds.prim_meta = es->meta.data();
-    ds.materials = hp.materials.data(); ds.area_lights = hp.lights.data();
+    ds.materials = hp.materials.data(); ds.mat_head = hp.mat_head.data(); ds.area_lights = hp.lights.data();
     if (sc->ambient_type == NRCU_AMBIENT_ENVIRONMENT_MAP && sc->ambient_environment_map >= 0 && (uint32_t)sc->ambient_environment_map < sc->n_textures) {
         uint32_t ti = (uint32_t)sc->ambient_environment_map;
         size_t cnt = (size_t)sc->texture_width[ti] * sc->texture_height[ti];
