@@ -92,7 +92,7 @@ struct nrcu_ctx {
     uint32_t spp = 0;
     DScene ds{};
     // scene buffers
-    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, materials, mat_head, area_lights, env, env_tab;
+    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, big_rect, materials, mat_head, area_lights, env, env_tab;
     // scene-prep sources kept for nrcu_download_primitives
     DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
@@ -245,6 +245,7 @@ void nrcu_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t 
 // scene upload
 // ---------------------------------------------------------------------------------------------
 static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord);
+static bool film_rects() { static uint32_t v = env_u32("NRCU_FILM_RECTS", 1); return v != 0; }
 
 int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
     if (!ctx) return NRCU_ERR_INVALID;
@@ -412,6 +413,13 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     ctx->n_big = (uint32_t)n_big;
     DScene& ds = ctx->ds;
     ds.big_geom = ctx->big_geom.as<f4>(); ds.big_box = ctx->big_box.as<f4>(); ds.big_bound = ctx->big_bound.as<f4>(); ds.big_meta = ctx->big_meta.as<uint32_t>(); ds.n_big = (uint32_t)n_big;
+    // film rectangles of the wide primitives for the camera rays of a pinhole camera (big_list_mask_film); NRCU_FILM_RECTS=0: off
+    ds.big_rect = nullptr;
+    if (n_big > 0 && ds.cam.lens_radius == 0.f && film_rects()) {
+        CTX_CUDA(ctx->big_rect.ensure(sizeof(f4) * NRCU_MAX_BIG));
+        k_big_rects<<<1, NRCU_MAX_BIG, 0, st>>>(ds, ctx->big_rect.as<f4>()); CTX_LAUNCH_CHECK("k_big_rects");
+        ds.big_rect = ctx->big_rect.as<f4>();
+    }
     ds.nodes = nullptr; ds.leaf_prims = ctx->leaf_prims.as<uint32_t>(); ds.leaf_geom = ctx->leaf_geom.as<f4>(); ds.leaf_box = ctx->leaf_box.as<f4>();
     ds.root_ref = NRCU_REF_EMPTY; ds.bvh_lo = mk3(NRCU_INF); ds.bvh_hi = mk3(-NRCU_INF);
     ctx->bvh_nodes = 0;

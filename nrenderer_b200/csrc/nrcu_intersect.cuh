@@ -276,9 +276,7 @@ NR_HD void slab_center_extent(f4 c, f4 h, const RayPrep& rp, vec3 ainv, float no
 // tested; if it passes, it is also the closest of the gate-passing primitives (same t order, same lowest-id tie
 // rule).  Only when the winner fails its gate (zero-thickness box or a grazing hit) are the candidates walked
 // again with the gate applied per candidate.
-template <bool GATE>
-NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const f4* bound, const uint32_t* meta,
-                         const Ray& ray, const RayPrep& rp, vec3 ginv, float& best_t, int& best_id) {
+NR_HD uint32_t big_list_mask(const DScene& s, const f4* bound, const RayPrep& rp) {
     uint32_t mask = 0;
     const vec3 ainv = mk3(fabsf(rp.inv.x), fabsf(rp.inv.y), fabsf(rp.inv.z));
     for (uint32_t k = 0; k < s.n_big; k++) {
@@ -286,6 +284,12 @@ NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const f
         slab_center_extent(bound[2 * k], bound[2 * k + 1], rp, ainv, -rp.oinv.x, tn, tf);
         if (tn <= tf) mask |= 1u << k;
     }
+    return mask;
+}
+// pass 2 on a candidate mask (any superset of the primitives the ray hits gives the same answer)
+template <bool GATE>
+NR_HD void big_list_resolve(uint32_t mask, const f4* geom, const f4* box, const uint32_t* meta,
+                            const Ray& ray, vec3 ginv, float& best_t, int& best_id) {
     uint32_t kb = 0;
     for (uint32_t m = mask; m; m &= m - 1u) {
         uint32_t k = (uint32_t)ctz32(m);
@@ -300,6 +304,23 @@ NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const f
             prim_test<true>(ray, ginv, geom[3 * k], geom[3 * k + 1], geom[3 * k + 2], box + 2 * k, meta[k], best_t, best_id);
         }
     }
+}
+template <bool GATE>
+NR_HD void big_list_step(const DScene& s, const f4* geom, const f4* box, const f4* bound, const uint32_t* meta,
+                         const Ray& ray, const RayPrep& rp, vec3 ginv, float& best_t, int& best_id) {
+    big_list_resolve<GATE>(big_list_mask(s, bound, rp), geom, box, meta, ray, ginv, best_t, best_id);
+}
+// Camera rays of a pinhole camera (extension of pass 1, GPU only): every ray leaves the same point, so "can this pixel's
+// ray meet the primitive's padded bounds?" is a rectangle test in film coordinates - DScene::big_rect holds, per wide
+// primitive, the film-space bounding rectangle of its bounds' eight corners seen from the camera (k_big_rects, fp64, with
+// a margin; the whole film when a corner is not in front of the camera).  Four compares instead of a slab test.
+NR_HD uint32_t big_list_mask_film(const DScene& s, const f4* rect, float x, float y) {
+    uint32_t mask = 0;
+    for (uint32_t k = 0; k < s.n_big; k++) {
+        const f4 rc = rect[k];
+        if (x >= rc.x && x <= rc.y && y >= rc.z && y <= rc.w) mask |= 1u << k;
+    }
+    return mask;
 }
 // Can anything inside the BVH still beat best_t?  Conservative slab test against the padded BVH bounds.
 NR_HD bool bvh_reachable(const DScene& s, const RayPrep& rp, float best_t) {

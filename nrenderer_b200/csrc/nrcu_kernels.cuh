@@ -122,6 +122,46 @@ __device__ __forceinline__ bool stage1(const DScene& s, const BigList& bl, const
     hits[pos] = make_float2(best_t, __int_as_float(best_id));
     return bvh_reachable(s, rp, best_t);
 }
+// The same for a camera ray of film position (x, y): the candidates come from the film rectangles when the scene has them.
+template <bool GATE>
+__device__ __forceinline__ bool stage1_camera(const DScene& s, const BigList& bl, const f4* rects, const Ray& r, float x, float y, uint32_t pos, float2* hits) {
+    RayPrep rp = prep_ray(r);
+    float best_t = NRCU_INF; int best_id = -1;
+    const uint32_t mask = rects ? big_list_mask_film(s, rects, x, y) : big_list_mask(s, bl.bd, rp);
+    big_list_resolve<GATE>(mask, bl.g, bl.b, bl.m, r, gate_inverse(r, rp), best_t, best_id);
+    hits[pos] = make_float2(best_t, __int_as_float(best_id));
+    return bvh_reachable(s, rp, best_t);
+}
+// One thread per wide primitive: DScene::big_rect (see big_list_mask_film).  A film point (x, y) sends its ray along
+// A + x H + y V with A = lower_left - position; P - position = l (A + x H + y V) is solved for (l, l x, l y) by Cramer's rule.
+__global__ void k_big_rects(DScene s, f4* rect) {
+    const uint32_t k = threadIdx.x;
+    if (k >= s.n_big) return;
+    const double px = s.cam.position.x, py = s.cam.position.y, pz = s.cam.position.z;
+    const double A[3] = {s.cam.lower_left.x - px, s.cam.lower_left.y - py, s.cam.lower_left.z - pz};
+    const double H[3] = {s.cam.horizontal.x, s.cam.horizontal.y, s.cam.horizontal.z}, V[3] = {s.cam.vertical.x, s.cam.vertical.y, s.cam.vertical.z};
+    auto det3 = [](const double* a, const double* b, const double* c) {
+        return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+    };
+    const double det = det3(A, H, V);
+    const f4 bc = s.big_bound[2 * k], bh = s.big_bound[2 * k + 1];
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    bool whole = !(fabs(det) > 1e-300);
+    double scale = 0.0;
+    for (int c = 0; c < 8 && !whole; c++) {
+        const double q[3] = {(double)bc.x + ((c & 1) ? 1.0 : -1.0) * (double)bh.x - px, (double)bc.y + ((c & 2) ? 1.0 : -1.0) * (double)bh.y - py,
+                             (double)bc.z + ((c & 4) ? 1.0 : -1.0) * (double)bh.z - pz};
+        const double l = det3(q, H, V) / det, lx = det3(A, q, V) / det, ly = det3(A, H, q) / det;
+        scale = fmax(scale, fmax(fabs(l), fmax(fabs(lx), fabs(ly))));
+        if (!(l > 1e-6 * scale) || !(l == l)) { whole = true; break; }   // a corner beside or behind the camera: no finite rectangle
+        const double x = lx / l, y = ly / l;
+        x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
+    }
+    // margin: the fp32 ray direction of film point (x, y) differs from the exact one by a few 1e-7 of the film size
+    const double mg = 1e-3 * (1.0 + fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))));
+    if (whole || !(x0 <= x1) || !(y0 <= y1)) rect[k] = mk4(-NRCU_INF, NRCU_INF, -NRCU_INF, NRCU_INF);
+    else rect[k] = mk4((float)(x0 - mg), (float)(x1 + mg), (float)(y0 - mg), (float)(y1 + mg));
+}
 // Append the flagged lanes' queue positions to the survivor list with one atomic per warp.
 __device__ __forceinline__ void append_survivors(bool more, uint32_t pos, uint32_t* surv, uint32_t* n_surv) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -138,7 +178,12 @@ template <bool GATE, bool STAGE1>
 __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_slots, PathQueue q, f4* L, uint32_t* n_queue,
                                                float2* hits, uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter) {
     __shared__ BigList bl;
-    if (STAGE1) bl.load(s);
+    __shared__ f4 film_rect[NRCU_MAX_BIG];
+    if (STAGE1) {
+        if (s.big_rect) for (uint32_t k = threadIdx.x; k < s.n_big; k += blockDim.x) film_rect[k] = s.big_rect[k];
+        bl.load(s);
+    }
+    const f4* rects = s.big_rect ? film_rect : nullptr;
     const uint32_t npix = s.width * s.height;
     const uint32_t stride = gridDim.x * blockDim.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -153,12 +198,13 @@ __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_
             if (s.depth == 0) L[slot] = mk4(s.ambient.x, s.ambient.y, s.ambient.z, 0.f);   // trace(): currDepth == depth
             else {
                 L[slot] = mk4(0.f, 0.f, 0.f, 0.f);
-                Ray r = pt_camera_ray(s, seed, pixel, sample);
+                float fx, fy;
+                Ray r = pt_camera_ray(s, seed, pixel, sample, &fx, &fy);
                 q.a[slot] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
                 q.b[slot] = make_float2(r.d.y, r.d.z);
                 q.c[slot] = mk4(1.f, 1.f, 1.f, i2f((int)slot));
                 if (q.d) q.d[slot] = 0u;
-                if (STAGE1) more = stage1<GATE>(s, bl, r, slot, hits);
+                if (STAGE1) more = stage1_camera<GATE>(s, bl, rects, r, fx, fy, slot, hits);
             }
         }
         if (STAGE1) append_survivors(more, slot, surv, n_surv);

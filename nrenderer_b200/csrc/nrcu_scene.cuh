@@ -109,6 +109,7 @@ struct DScene {
     const f4* big_bound;          // 2 per wide primitive: padded true bounds as (centre, half extent) (conservative pre-test)
     const uint32_t* big_meta;     // (prim id << 2) | kind; planes first, then triangles, then spheres
     uint32_t n_big;
+    const f4* big_rect;           // per wide primitive: film rectangle (x0, x1, y0, y1) of its bounds seen from a pinhole camera; null: none
     vec3 bvh_lo, bvh_hi;          // padded bounds of everything inside the BVH (lo > hi when it is empty)
     // shading
     const DMaterial* materials;

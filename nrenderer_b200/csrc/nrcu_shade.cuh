@@ -31,13 +31,14 @@ NR_HD Ray raycast_camera_ray(const DScene& s, uint32_t p) {
 // Path tracers: U(-1,1)^2 jitter around the pixel corner (AccPathTracer.cpp:23-29) and the
 // UniformInCircle lens sample (accept iff x*2 + y*2 <= 1, sic).  The lens draws are skipped when
 // the lens radius is 0: the reference multiplies them by zero.
-NR_HD Ray pt_camera_ray(const DScene& s, uint64_t seed, uint32_t p, uint32_t sample) {
+NR_HD Ray pt_camera_ray(const DScene& s, uint64_t seed, uint32_t p, uint32_t sample, float* film_x = nullptr, float* film_y = nullptr) {
     u32x4 rn = rng_block(seed, p, sample, NRCU_STREAM_CAMERA, 0);
     float rx = 2.f * u01(rn.x) - 1.f, ry = 2.f * u01(rn.y) - 1.f;
     int w = (int)s.width, h = (int)s.height;
     int row = (int)(p / (uint32_t)w), j = (int)(p % (uint32_t)w), i = h - 1 - row;
     float x = ((float)j + rx) / (float)w;
     float y = ((float)i + ry) / (float)h;
+    if (film_x) { *film_x = x; *film_y = y; }
     vec3 offset = mk3(0.f);
     if (s.cam.lens_radius != 0.f) {
         float lx = 0.f, ly = 0.f;
