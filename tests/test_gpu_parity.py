@@ -632,3 +632,44 @@ def test_fused_regeneration_kernel_traces_the_same_paths():
             out[fused] = (np.load(path), [ln for ln in r.stdout.splitlines() if ln.startswith("RAYS")][0])
     assert out["0"][1] == out["1"][1] and out["0"][1].endswith(" 2")
     assert np.array_equal(out["0"][0].view(np.uint32), out["1"][0].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_kernel_variants_trace_the_same_paths():
+    """The default kernels of the second half of round 2 - k_shade_pool (dense shading rounds out of a per-warp ring),
+    queue regions (16 size counters per queue), k_big_balanced64 (two rays per lane) and the film-rectangle candidates of
+    the camera rays - change the ORDER in which paths are met, never a path: every combination of the switches renders the
+    bit-identical accumulation buffer and counts the same rays as the round-1 kernels (all switches off)."""
+    import subprocess, sys, textwrap, tempfile
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from conftest import load_scene
+        import nrenderer_b200 as nr
+        c = nr.Context(0)
+        fs = load_scene("bunny5k_cornel", width=160, height=90, samples_per_pixel=16, depth=20, cam_aspect=16 / 9)
+        c.upload(fs, 2)
+        acc = torch.zeros(90, 160, 4, device="cuda:0"); torch.cuda.synchronize()
+        st = c.render_accumulate(acc.data_ptr(), seed=9)
+        np.save(sys.argv[1], acc.cpu().numpy()); print("RAYS", st["rays"])
+    """ % (os.path.dirname(GOLDEN), os.path.dirname(os.path.dirname(GOLDEN))))
+    variants = {
+        "round1": dict(NRCU_SHADE_POOL="0", NRCU_QUEUE_REGIONS="1", NRCU_BIG_BALANCED="1", NRCU_FILM_RECTS="0"),
+        "default": {},
+        "pool_plain_queue": dict(NRCU_QUEUE_REGIONS="1"),
+        "regions_without_pool": dict(NRCU_SHADE_POOL="0", NRCU_QUEUE_REGIONS="32"),
+        "per_lane_stage1": dict(NRCU_BIG_BALANCED="0", NRCU_QUEUE_REGIONS="4"),
+        "one_wave": dict(NRCU_WAVES="1"),
+    }
+    with tempfile.TemporaryDirectory() as td:
+        out = {}
+        for name, env in variants.items():
+            path = os.path.join(td, name + ".npy")
+            r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
+            assert r.returncode == 0, (name, r.stderr[-2000:])
+            out[name] = (np.load(path), [ln for ln in r.stdout.splitlines() if ln.startswith("RAYS")][0])
+    ref = out["round1"]
+    assert ref[0][..., :3].sum() > 0
+    for name, (acc, rays) in out.items():
+        assert rays == ref[1], (name, rays, ref[1])
+        assert np.array_equal(acc.view(np.uint32), ref[0].view(np.uint32)), name

@@ -19,7 +19,7 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 SMS, SCHEDULERS = 148, 4
-PATHS_PER_WAVE = 32 * 1920 * 1080   # bench.py default workload (cfg3): 64 Mi path slots per wave -> 32 spp of 1080p
+PATHS_PER_WAVE = 32 * 1920 * 1080   # bench.py default workload (cfg3) captured with NRCU_WAVE_MSLOTS=128: 64 Mi path slots per wave -> 32 spp of 1080p
 KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -63,7 +63,7 @@ def main():
                     f"{d.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0):.2f},{d.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.1f},"
                     f"{d.get('dram__bytes_read.sum', 0):.0f},{d.get('dram__bytes_write.sum', 0):.0f}\n")
     ours = [d for d in launches if d["kernel"].startswith("k_")]
-    render = [d for d in ours if not d["kernel"].startswith(("k_bvh", "k_build", "k_mesh"))]
+    render = [d for d in ours if not d["kernel"].startswith(("k_bvh", "k_build", "k_mesh", "k_big_rects", "k_env"))]
     T = sum(d["gpu__time_duration.sum"] for d in render)
     agg = collections.OrderedDict()
     for d in render:
@@ -130,7 +130,7 @@ def main():
     summary["closest_hit_dram_bytes_per_step_equiv"] = round(ch_dram / max(sum(kernels[k]["launches"] for k in ch if k.startswith("k_raygen")), 1))   # per wave
     json.dump(summary, open(os.path.join(out_dir, f"{rnd}_summary.json"), "w"), indent=1)
     with open(os.path.join(out_dir, f"{rnd}_summary.md"), "w") as f:
-        f.write(f"# {rnd} profile summary (ncu, B200, `bench.py --steps 1 --warmup 1 --spp 128 --no-cpu-baseline --no-e2e --no-other-workloads`, first {len(launches)} launches; kernel sources {csrc_sha})\n\n")
+        f.write(f"# {rnd} profile summary (ncu, B200, `NRCU_WAVE_MSLOTS=128 bench.py --steps 1 --warmup 1 --spp 128 --no-cpu-baseline --no-e2e --no-other-workloads`, first {len(launches)} launches; kernel sources {csrc_sha})\n\n")
         f.write(f"Whole step: **{warp_inst_per_path:.1f} warp instructions and {dram_per_path:.0f} DRAM bytes per path sample**, {lane_complete / max(inst_complete, 1):.1f} active lanes per instruction "
                 f"(complete waves of the capture: {n_waves} x {PATHS_PER_WAVE} paths).\n\n")
         f.write("| kernel | launches | time (us) | share | warp-inst | lanes/inst | issue-active % | DRAM B/launch | DRAM GB/s |\n|---|---|---|---|---|---|---|---|---|\n")

@@ -17,7 +17,8 @@ def ncu_sass(rep, regex, skip):
     name = rows[0][1]
     hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
     hdr, data = rows[hi], rows[hi + 1:]
-    data = data[:len(data) // 2] if len(data) > 1 and data[0][1] == data[len(data) // 2][1] else data   # the CSV lists the kernel twice
+    rep_at = next((i for i in range(1, len(data)) if data[i] and data[i][0] == data[0][0]), None)   # the CSV lists the kernel twice
+    if rep_at: data = data[:rep_at]
     return name, hdr, data
 
 def line_table(mangled_hint):
@@ -49,6 +50,7 @@ def main():
     iL = hdr.index("stall_long_sb")
     if len(table) != len(data):
         print(f"warning: {len(table)} instructions in the library, {len(data)} in the report (different build?)")
+        if abs(len(table) - len(data)) > 2: sys.exit(1)
     src_cache = {}
     def text(f, ln):
         if f not in src_cache:
