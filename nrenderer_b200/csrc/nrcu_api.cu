@@ -92,7 +92,7 @@ struct nrcu_ctx {
     uint32_t spp = 0;
     DScene ds{};
     // scene buffers
-    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, big_rect, materials, mat_head, area_lights, env, env_tab;
+    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, big_rect, live_px, live_flag, live_count, materials, mat_head, area_lights, env, env_tab;
     // scene-prep sources kept for nrcu_download_primitives
     DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
@@ -245,6 +245,7 @@ void nrcu_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t 
 // scene upload
 // ---------------------------------------------------------------------------------------------
 static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord);
+static bool live_pixels() { static uint32_t v = env_u32("NRCU_LIVE_PIXELS", 1); return v != 0; }
 static bool film_rects() { static uint32_t v = env_u32("NRCU_FILM_RECTS", 1); return v != 0; }
 
 int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
@@ -347,6 +348,21 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
         if ((rc = build_bvh(ctx, n, hp.max_abs_coord)) != NRCU_OK) return rc;
     }
     pt.mark("build_bvh (incl. frees)");
+    // ---- live pixels: camera rays are only generated where they can meet something (DScene::live_px) ----------------
+    ds.live_px = nullptr; ds.live_flag = nullptr; ds.n_live = sc->width * sc->height;
+    if (mode != NRCU_MODE_RAYCAST && ds.big_rect && !ds.env_rgba && ds.depth > 0 && live_pixels()) {
+        const uint32_t npix = sc->width * sc->height;
+        CTX_CUDA(ctx->live_px.ensure(sizeof(uint32_t) * (size_t)std::max(npix, 1u)));
+        CTX_CUDA(ctx->live_flag.ensure((size_t)std::max(npix, 1u)));
+        CTX_CUDA(ctx->live_count.ensure(sizeof(uint32_t)));
+        k_live_flags<<<grid_for(npix, 256), 256, 0, ctx->stream>>>(ds, ctx->live_flag.as<unsigned char>()); CTX_LAUNCH_CHECK("k_live_flags");
+        k_live_compact<<<1, 1024, 0, ctx->stream>>>(ctx->live_flag.as<unsigned char>(), npix, ctx->live_px.as<uint32_t>(), ctx->live_count.as<uint32_t>()); CTX_LAUNCH_CHECK("k_live_compact");
+        uint32_t n_live = npix;
+        CTX_CUDA(cudaMemcpyAsync(&n_live, ctx->live_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (n_live < npix) { ds.live_px = ctx->live_px.as<uint32_t>(); ds.live_flag = ctx->live_flag.as<unsigned char>(); ds.n_live = n_live; }
+    }
+    pt.mark("live pixels");
     CTX_CUDA(cudaEventRecord(e1, ctx->stream));
     CTX_CUDA(cudaEventSynchronize(e1));
     CTX_CUDA(cudaEventElapsedTime(&ctx->ms_setup, e0, e1));
@@ -646,8 +662,10 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     // (k_big: 76 % issue-active) with CTAs of a latency-bound kernel of the other (k_shade: 45 %) and hide every
     // kernel's tail behind the other wave's work.  Measured on cfg3: 1 wave x 32 Mi 2.14, 2 x 64 Mi 2.68,
     // 4 x 64 Mi 2.71 Gpath-samples/s.  The accumulation order is fixed by events, so the image is bit-identical.
+    // camera rays exist for the live pixels only (DScene::live_px): a wave holds k x n_live queue entries and k x n_pixels radiance slots
+    const uint32_t nlive = ds.live_px ? ds.n_live : npix;
     const bool explicit_k = params && params->samples_per_wave != 0;
-    uint32_t k = explicit_k ? params->samples_per_wave : std::max<uint32_t>(1, wave_slots_target() / npix);
+    uint32_t k = explicit_k ? params->samples_per_wave : std::max<uint32_t>(1, wave_slots_target() / std::max(nlive, 1u));
     k = std::min<uint32_t>(k, std::max<uint32_t>(1, s1 - s0));
     if ((uint64_t)k * npix > 0x7fffffffull) k = std::max<uint32_t>(1, (uint32_t)(0x7fffffffull / npix));
     int NP = glass_branch ? 1 : std::max(1, std::min<int>(concurrent_waves(), (int)(s1 - s0)));
@@ -659,10 +677,10 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     if (!explicit_k && !glass_branch) k = std::max<uint32_t>(1, std::min<uint32_t>(k, (s1 - s0 + (uint32_t)NP * wave_min_groups() - 1) / ((uint32_t)NP * wave_min_groups())));
     NP = std::max(1, std::min<int>(NP, (int)((s1 - s0 + k - 1) / k)));   // also with no samples at all: one (idle) wave set
     const unsigned share = (unsigned)NP;
-    uint32_t slots = k * npix;
+    uint32_t slots = k * npix, qslots = k * nlive;   // radiance slots / bounce-0 queue entries of a wave
     // branching glass mode: room for 4 rays per path slot, and never less than 4 Mi entries (small frames at many bounces)
     auto branch_capacity = [](uint32_t sl) { return (uint32_t)std::min<uint64_t>(0x7fffffffull, std::max<uint64_t>((uint64_t)sl * 4, 4ull << 20)); };
-    uint32_t capacity = glass_branch ? branch_capacity(slots) : slots;
+    uint32_t capacity = glass_branch ? branch_capacity(qslots) : qslots;
     // Queue regions (QRegions in nrcu_kernels.cuh): K counters per queue instead of one.  Region r of the queue that enters
     // bounce d + 1 receives the survivors of the input blocks pb = r (mod K), at most ceil(blocks / K) x 32 entries, so the
     // array extent grows by at most 32 K entries per bounce: `slack`.  The branching glass mode keeps the plain queue
@@ -685,8 +703,8 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             for (DevBuf* bfr : all) bfr->release();
         }
         k = std::max<uint32_t>(1, k / 2);
-        slots = k * npix;
-        capacity = glass_branch ? branch_capacity(slots) : slots;
+        slots = k * npix; qslots = k * nlive;
+        capacity = glass_branch ? branch_capacity(qslots) : qslots;
     }
     cudaStream_t S[NRCU_MAX_WAVES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
     if (NP > 1) {
@@ -744,7 +762,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             Pipe& pp = P[p];
             pp.w0 = g0 + (uint32_t)p * k; pp.live = pp.w0 < s1;
             if (!pp.live) continue;
-            pp.kw = std::min(k, s1 - pp.w0); pp.n_slots = pp.kw * npix;
+            pp.kw = std::min(k, s1 - pp.w0); pp.n_slots = pp.kw * nlive;
             cudaStream_t st = pp.st;
             CTX_CUDA(cudaMemsetAsync(pp.cnt + CNT_QUEUE0, 0, cnt_bytes - sizeof(uint32_t) * CNT_QUEUE0, st));
             const unsigned gen_grid = std::min<unsigned>(grid_for(pp.n_slots, 256), (unsigned)sms * 8);
@@ -842,7 +860,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             Pipe& pp = P[p];
             if (!pp.live) continue;
             if (NP > 1 && acc_recorded) CTX_CUDA(cudaStreamWaitEvent(pp.st, ctx->ev_acc, 0));
-            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw, pp.d_qn, pp.d_qr, K, nee ? pp.d_nshadow : nullptr, (uint32_t)CS, ds.depth, NRCU_RC_A);
+            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw, pp.d_qn, pp.d_qr, K, nee ? pp.d_nshadow : nullptr, (uint32_t)CS, ds.depth, NRCU_RC_A, ds.live_flag, npix - nlive);
             CTX_LAUNCH_CHECK("k_accumulate");
             if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_acc, pp.st)); acc_recorded = true; }
         }
@@ -868,7 +886,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         stats->rays = rays; stats->paths = (uint64_t)npix * (s1 - s0);
         stats->kernel_launches = ctx->launches - launches0;
         stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
-        stats->max_queue = glass_branch ? h_cnt[CNT_HIGH_WATER] : std::min<uint32_t>(slots, npix * (s1 - s0));   // without branching the bounce-0 queue is the largest
+        stats->max_queue = glass_branch ? h_cnt[CNT_HIGH_WATER] : std::min<uint32_t>(qslots, nlive * (s1 - s0));   // without branching the bounce-0 queue is the largest
         stats->scheduler = NRCU_SCHED_WAVES; stats->iterations = bounce_rounds; stats->wave_retries = wave_retries;
         return check_overflow(ctx);
     }

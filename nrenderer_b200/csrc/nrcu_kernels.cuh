@@ -134,9 +134,16 @@ __device__ __forceinline__ bool stage1_camera(const DScene& s, const BigList& bl
 }
 // One thread per wide primitive: DScene::big_rect (see big_list_mask_film).  A film point (x, y) sends its ray along
 // A + x H + y V with A = lower_left - position; P - position = l (A + x H + y V) is solved for (l, l x, l y) by Cramer's rule.
+__device__ f4 film_rect_of_box(const DScene& s, const double lo[3], const double hi[3]);
 __global__ void k_big_rects(DScene s, f4* rect) {
     const uint32_t k = threadIdx.x;
     if (k >= s.n_big) return;
+    const f4 bc = s.big_bound[2 * k], bh = s.big_bound[2 * k + 1];
+    const double lo[3] = {(double)bc.x - (double)bh.x, (double)bc.y - (double)bh.y, (double)bc.z - (double)bh.z};
+    const double hi[3] = {(double)bc.x + (double)bh.x, (double)bc.y + (double)bh.y, (double)bc.z + (double)bh.z};
+    rect[k] = film_rect_of_box(s, lo, hi);
+}
+__device__ f4 film_rect_of_box(const DScene& s, const double lo[3], const double hi[3]) {
     const double px = s.cam.position.x, py = s.cam.position.y, pz = s.cam.position.z;
     const double A[3] = {s.cam.lower_left.x - px, s.cam.lower_left.y - py, s.cam.lower_left.z - pz};
     const double H[3] = {s.cam.horizontal.x, s.cam.horizontal.y, s.cam.horizontal.z}, V[3] = {s.cam.vertical.x, s.cam.vertical.y, s.cam.vertical.z};
@@ -144,13 +151,11 @@ __global__ void k_big_rects(DScene s, f4* rect) {
         return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
     };
     const double det = det3(A, H, V);
-    const f4 bc = s.big_bound[2 * k], bh = s.big_bound[2 * k + 1];
     double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
     bool whole = !(fabs(det) > 1e-300);
     double scale = 0.0;
     for (int c = 0; c < 8 && !whole; c++) {
-        const double q[3] = {(double)bc.x + ((c & 1) ? 1.0 : -1.0) * (double)bh.x - px, (double)bc.y + ((c & 2) ? 1.0 : -1.0) * (double)bh.y - py,
-                             (double)bc.z + ((c & 4) ? 1.0 : -1.0) * (double)bh.z - pz};
+        const double q[3] = {((c & 1) ? hi[0] : lo[0]) - px, ((c & 2) ? hi[1] : lo[1]) - py, ((c & 4) ? hi[2] : lo[2]) - pz};
         const double l = det3(q, H, V) / det, lx = det3(A, q, V) / det, ly = det3(A, H, q) / det;
         scale = fmax(scale, fmax(fabs(l), fmax(fabs(lx), fabs(ly))));
         if (!(l > 1e-6 * scale) || !(l == l)) { whole = true; break; }   // a corner beside or behind the camera: no finite rectangle
@@ -159,8 +164,65 @@ __global__ void k_big_rects(DScene s, f4* rect) {
     }
     // margin: the fp32 ray direction of film point (x, y) differs from the exact one by a few 1e-7 of the film size
     const double mg = 1e-3 * (1.0 + fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))));
-    if (whole || !(x0 <= x1) || !(y0 <= y1)) rect[k] = mk4(-NRCU_INF, NRCU_INF, -NRCU_INF, NRCU_INF);
-    else rect[k] = mk4((float)(x0 - mg), (float)(x1 + mg), (float)(y0 - mg), (float)(y1 + mg));
+    if (whole || !(x0 <= x1) || !(y0 <= y1)) return mk4(-NRCU_INF, NRCU_INF, -NRCU_INF, NRCU_INF);
+    return mk4((float)(x0 - mg), (float)(x1 + mg), (float)(y0 - mg), (float)(y1 + mg));
+}
+// Live pixels (DScene::live_px): a pixel is live iff the film footprint of its jittered samples - the pixel corner +- one
+// pixel, AccPathTracer.cpp:23-29 - overlaps the film rectangle of a wide primitive, of the BVH's bounds or of an area light
+// (closestHitLight is asked for every ray, AccPathTracer.cpp:128).  One thread per pixel; the rectangles are set up per block.
+#define NRCU_LIVE_RECTS (NRCU_MAX_BIG + 1 + 32)
+__global__ void __launch_bounds__(256) k_live_flags(DScene s, unsigned char* flag) {
+    __shared__ f4 rc[NRCU_LIVE_RECTS];
+    __shared__ uint32_t n_rc, all_live;
+    if (threadIdx.x == 0) { n_rc = 0; all_live = s.n_area_lights > 32u ? 1u : 0u; }
+    __syncthreads();
+    const uint32_t n_jobs = s.n_big + 1u + min(s.n_area_lights, 32u);
+    if (threadIdx.x < n_jobs) {
+        f4 r = mk4(NRCU_INF, -NRCU_INF, NRCU_INF, -NRCU_INF);   // empty
+        bool have = true;
+        if (threadIdx.x < s.n_big) r = s.big_rect[threadIdx.x];
+        else if (threadIdx.x == s.n_big) {
+            if (s.root_ref == NRCU_REF_EMPTY) have = false;
+            else {
+                const double lo[3] = {s.bvh_lo.x, s.bvh_lo.y, s.bvh_lo.z}, hi[3] = {s.bvh_hi.x, s.bvh_hi.y, s.bvh_hi.z};
+                r = film_rect_of_box(s, lo, hi);
+            }
+        } else {   // a light quad p + a u + b v: the box of its four corners (record layout: nrcu_host_prep.hpp)
+            const f4* L = s.area_lights + NRCU_LIGHT_F4 * (size_t)(threadIdx.x - s.n_big - 1u);
+            const f4 l0 = L[0], l1 = L[1], lu = L[4], lv = L[5];
+            const double p[3] = {l0.w, l1.x, l1.y}, u[3] = {lu.x, lu.y, lu.z}, v[3] = {lv.x, lv.y, lv.z};
+            double lo[3], hi[3];
+            for (int k = 0; k < 3; k++) {
+                const double c0 = p[k], c1 = p[k] + u[k], c2 = p[k] + v[k], c3 = p[k] + u[k] + v[k];
+                const double pad = 1e-4 * (1.0 + fabs(c0) + fabs(u[k]) + fabs(v[k]));
+                lo[k] = fmin(fmin(c0, c1), fmin(c2, c3)) - pad; hi[k] = fmax(fmax(c0, c1), fmax(c2, c3)) + pad;
+            }
+            r = film_rect_of_box(s, lo, hi);
+        }
+        if (have) rc[atomicAdd(&n_rc, 1u)] = r;
+    }
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.width * s.height) return;
+    const int w = (int)s.width, h = (int)s.height;
+    const int row = (int)(p / (uint32_t)w), j = (int)(p % (uint32_t)w), i = h - 1 - row;   // pt_camera_ray's pixel coordinates
+    const float fx0 = ((float)j - 1.f) / (float)w, fx1 = ((float)j + 1.f) / (float)w, fy0 = ((float)i - 1.f) / (float)h, fy1 = ((float)i + 1.f) / (float)h;
+    bool live = all_live != 0u;
+    for (uint32_t k = 0; k < n_rc && !live; k++) live = fx1 >= rc[k].x && fx0 <= rc[k].y && fy1 >= rc[k].z && fy0 <= rc[k].w;
+    flag[p] = live ? 1 : 0;
+}
+// flags -> ascending list of the live pixels (one block: per-thread ranges, a scan of the range counts)
+__global__ void __launch_bounds__(1024) k_live_compact(const unsigned char* flag, uint32_t npix, uint32_t* list, uint32_t* n_live) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (npix + 1023u) / 1024u, lo = min(npix, threadIdx.x * per), hi = min(npix, lo + per);
+    uint32_t c = 0;
+    for (uint32_t p = lo; p < hi; p++) c += flag[p];
+    part[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int t = 0; t < 1024; t++) { const uint32_t v = part[t]; part[t] = run; run += v; } *n_live = run; }
+    __syncthreads();
+    uint32_t at = part[threadIdx.x];
+    for (uint32_t p = lo; p < hi; p++) if (flag[p]) list[at++] = p;
 }
 // Append the flagged lanes' queue positions to the survivor list with one atomic per warp.
 __device__ __forceinline__ void append_survivors(bool more, uint32_t pos, uint32_t* surv, uint32_t* n_surv) {
@@ -190,24 +252,29 @@ __global__ void __launch_bounds__(256) k_raygen(DScene s, uint64_t seed, uint32_
         *n_queue = s.depth == 0 ? 0u : n_slots;   // every slot starts one path: the bounce-0 queue is dense
         if (STAGE1 && s.depth != 0 && ray_counter) atomicAdd(ray_counter, (unsigned long long)n_slots);
     }
+    // queue entry i = sample_in_wave * n_live + j holds the camera ray of live pixel j; its radiance slot is
+    // sample_in_wave * n_pixels + pixel (dead pixels have no entries and no slots written: DScene::live_px)
+    const uint32_t n_live = s.live_px ? s.n_live : npix;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_slots; base += stride) {   // warp-uniform trip count
-        const uint32_t slot = base + threadIdx.x;
+        const uint32_t i = base + threadIdx.x;
         bool more = false;
-        if (slot < n_slots) {
-            uint32_t pixel = slot % npix, sample = sample0 + slot / npix;
+        if (i < n_slots) {
+            const uint32_t j = i % n_live, sw = i / n_live;
+            const uint32_t pixel = s.live_px ? s.live_px[j] : j, sample = sample0 + sw;
+            const uint32_t slot = sw * npix + pixel;
             if (s.depth == 0) L[slot] = mk4(s.ambient.x, s.ambient.y, s.ambient.z, 0.f);   // trace(): currDepth == depth
             else {
                 L[slot] = mk4(0.f, 0.f, 0.f, 0.f);
                 float fx, fy;
                 Ray r = pt_camera_ray(s, seed, pixel, sample, &fx, &fy);
-                q.a[slot] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
-                q.b[slot] = make_float2(r.d.y, r.d.z);
-                q.c[slot] = mk4(1.f, 1.f, 1.f, i2f((int)slot));
-                if (q.d) q.d[slot] = 0u;
-                if (STAGE1) more = stage1_camera<GATE>(s, bl, rects, r, fx, fy, slot, hits);
+                q.a[i] = mk4(r.o.x, r.o.y, r.o.z, r.d.x);
+                q.b[i] = make_float2(r.d.y, r.d.z);
+                q.c[i] = mk4(1.f, 1.f, 1.f, i2f((int)slot));
+                if (q.d) q.d[i] = 0u;
+                if (STAGE1) more = stage1_camera<GATE>(s, bl, rects, r, fx, fy, i, hits);
             }
         }
-        if (STAGE1) append_survivors(more, slot, surv, n_surv);
+        if (STAGE1) append_survivors(more, i, surv, n_surv);
     }
 }
 
@@ -1366,10 +1433,12 @@ __global__ void k_clamp_count(uint32_t* n_ptr, uint32_t capacity, uint32_t* high
 // through one closest-hit query - so thread 0 adds those counters up here instead of every warp of the closest-hit kernels
 // sending an atomic per 32 rays.
 __global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k, uint32_t n_samples,
-                             const uint32_t* qn, const uint32_t* qr, uint32_t regions, const uint32_t* nshadow, uint32_t counter_stride, uint32_t depth, unsigned long long* ray_counter) {
+                             const uint32_t* qn, const uint32_t* qr, uint32_t regions, const uint32_t* nshadow, uint32_t counter_stride, uint32_t depth, unsigned long long* ray_counter,
+                             const unsigned char* live_flag, uint32_t n_dead) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0 && ray_counter) {
-        unsigned long long rays = 0;
+        // the camera rays of the dead pixels are closest-hit queries too - answered by the film rectangles (nothing can be hit)
+        unsigned long long rays = depth ? (unsigned long long)n_dead * k : 0ull;
         for (uint32_t d = 0; d < depth; d++) {
             // bounce 0's queue is dense (qn[0]); with regions > 1 the queue entering bounce d >= 1 is counted per region in qr
             if (d == 0 || regions <= 1) rays += qn[(size_t)counter_stride * d];
@@ -1380,9 +1449,11 @@ __global__ void k_accumulate(const f4* L, f4* accum, uint32_t npix, uint32_t k, 
     }
     if (p >= npix) return;
     f4 acc = accum[p];
-    for (uint32_t s = 0; s < k; s++) {
-        f4 v = L[(size_t)s * npix + p];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z;
+    if (!live_flag || live_flag[p]) {   // a dead pixel's samples are black and its radiance slots were never written
+        for (uint32_t s = 0; s < k; s++) {
+            f4 v = L[(size_t)s * npix + p];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z;
+        }
     }
     acc.w += (float)n_samples;
     accum[p] = acc;

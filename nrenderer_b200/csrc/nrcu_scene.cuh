@@ -111,6 +111,12 @@ struct DScene {
     uint32_t n_big;
     const f4* big_rect;           // per wide primitive: film rectangle (x0, x1, y0, y1) of its bounds seen from a pinhole camera; null: none
     vec3 bvh_lo, bvh_hi;          // padded bounds of everything inside the BVH (lo > hi when it is empty)
+    // LIVE PIXELS (GPU only, pinhole camera, no environment map): the pixels whose camera rays can meet anything at all - a wide
+    // primitive's bounds, the BVH's bounds or a light - listed in pixel order; the others render black whatever is sampled, so
+    // no camera ray is generated for them.  null: every pixel is live (n_live = width * height).
+    const uint32_t* live_px;
+    const unsigned char* live_flag;   // per pixel, for the accumulation (dead pixels have no radiance slots written)
+    uint32_t n_live;
     // shading
     const DMaterial* materials;
     const f4* mat_head;           // per material: (diffuseColor / pi  - Lambertian.cpp:30, the same fp32 division -, type bits): one gather for the common case
