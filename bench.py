@@ -399,6 +399,8 @@ def cuda_arm(args):
     st = step(True) or {}
     barrier()
     agg = {k: st.get(k, 0) * args.steps for k in ("rays", "paths", "kernel_launches", "ms_trace", "ms_shade", "ms_stage2", "iterations")}
+    # camera rays of the dead pixels (nrcu_stats.dead_pixels): closest-hit queries answered by the film rectangles, no ray traced
+    agg["untraced"] = st.get("dead_pixels", 0) * (st.get("paths", 0) // max(1, w * h)) * args.steps
     sched = st.get("scheduler", 0)
     coll_iso = 0.0
     if world > 1:   # the exchange step on its own: all ranks start together, 10 repetitions
@@ -415,14 +417,14 @@ def cuda_arm(args):
         step(False)          # leave the frame of the workload in rgba again
         barrier()
     t = torch.tensor([ms, agg["ms_trace"], agg["ms_shade"], agg["ms_stage2"], coll_ms, coll_iso], dtype=torch.float64, device=dev)
-    sums = torch.tensor([agg["rays"], agg["paths"], agg["kernel_launches"], sched], dtype=torch.float64, device=dev)
+    sums = torch.tensor([agg["rays"], agg["paths"], agg["kernel_launches"], sched, agg["untraced"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         mx = sums.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         sums[3] = mx[3]
     ms, ms_trace, ms_shade, ms_stage2, coll_ms, coll_iso = t.tolist()
-    rays, paths, launches, sched = sums.tolist()
+    rays, paths, launches, sched, untraced = sums.tolist()
     launches += args.steps * (1 if rank == 0 else 0)   # resolve
     value = paths / (ms * 1e-3) * 1e-6
     scheduler = {1: "waves", 2: "regen"}.get(int(sched), "?")
@@ -503,7 +505,7 @@ def cuda_arm(args):
         e2e["unavailable"] = str(ex)[:400]
     e2e["clocks"] = sampler2.stop()
 
-    roof, roof_hbm = rooflines(args.workload, paths, rays, ms, clocks, world, scheduler)
+    roof, roof_hbm = rooflines(args.workload, paths, rays - untraced, ms, clocks, world, scheduler)   # algorithmic bytes: traced rays only
     line = {
         "metric": "Mpath-samples/s", "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -513,6 +515,9 @@ def cuda_arm(args):
                    "l2": "256 MB flush buffer written between steps; the path state of a step (~5 GB) exceeds the 126 MB L2",
                    "glass_mode": "stochastic", "seed": args.seed, "scheduler": scheduler},
         "mrays_per_s": rays / (ms * 1e-3) * 1e-6, "rays_per_path": rays / max(paths, 1),
+        "mrays_traced_per_s": (rays - untraced) / (ms * 1e-3) * 1e-6, "rays_traced_per_path": (rays - untraced) / max(paths, 1),
+        "rays_note": "rays = closest-hit queries answered, as the reference counts them (one per trace() call); rays_traced leaves out the camera rays of "
+                     "the pixels whose film footprint misses every primitive's bounds and every light: those are answered without generating a ray",
         "kernel_ms": {"closest_hit": ms_trace / args.steps, "of_which_bvh_traversal": ms_stage2 / args.steps, "shade": ms_shade / args.steps,
                       "note": "per-kernel CUDA-event spans summed over the concurrent streams: they overlap, so they add up to more than ms_per_step"},
         "iterations_per_step": agg["iterations"] / args.steps,

@@ -226,7 +226,8 @@ typedef struct nrcu_render_params {
 
 typedef struct nrcu_stats {
     uint64_t paths;            /* path samples rendered (w*h*samples in the slice) */
-    uint64_t rays;             /* closest-hit queries + shadow rays actually traced (device counter) */
+    uint64_t rays;             /* closest-hit queries + shadow rays answered (device counters): traced through the kernels, or - the
+                                  camera rays of `dead_pixels` - answered by the film rectangles without a ray (they can hit nothing) */
     uint64_t kernel_launches;  /* launches of this library's kernels during the call */
     float ms_total;            /* CUDA-event time of the whole call on the context's stream */
     float ms_trace;            /* NRCU_FLAG_KERNEL_TIMES: time inside the closest-hit kernels: k_raygen (camera rays + fused stage 1), k_big, k_trace* */
@@ -239,7 +240,8 @@ typedef struct nrcu_stats {
     uint32_t scheduler;        /* nrcu_scheduler that ran (WAVES or REGEN) */
     uint32_t iterations;       /* REGEN: stage-1/stage-2/shade rounds; WAVES: waves x bounces */
     uint32_t wave_retries;     /* branching glass mode: waves re-rendered with fewer samples because the queue overflowed */
-    uint32_t reserved;
+    uint32_t dead_pixels;      /* pixels whose camera rays cannot meet a primitive's bounds or a light (pinhole camera, no environment
+                                  map): no ray is generated for their samples; rays - dead_pixels * samples = rays traced */
 } nrcu_stats;
 
 /* --- lifetime ------------------------------------------------------------------------- */

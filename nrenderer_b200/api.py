@@ -43,7 +43,7 @@ class NrcuStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_setup", C.c_float),
                 ("bvh_nodes", C.c_uint32), ("n_primitives", C.c_uint32), ("max_queue", C.c_uint32), ("ms_stage2", C.c_float),
-                ("scheduler", C.c_uint32), ("iterations", C.c_uint32), ("wave_retries", C.c_uint32), ("reserved", C.c_uint32)]
+                ("scheduler", C.c_uint32), ("iterations", C.c_uint32), ("wave_retries", C.c_uint32), ("dead_pixels", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -354,11 +354,18 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
         const uint32_t npix = sc->width * sc->height;
         CTX_CUDA(ctx->live_px.ensure(sizeof(uint32_t) * (size_t)std::max(npix, 1u)));
         CTX_CUDA(ctx->live_flag.ensure((size_t)std::max(npix, 1u)));
-        CTX_CUDA(ctx->live_count.ensure(sizeof(uint32_t)));
-        k_live_flags<<<grid_for(npix, 256), 256, 0, ctx->stream>>>(ds, ctx->live_flag.as<unsigned char>()); CTX_LAUNCH_CHECK("k_live_flags");
-        k_live_compact<<<1, 1024, 0, ctx->stream>>>(ctx->live_flag.as<unsigned char>(), npix, ctx->live_px.as<uint32_t>(), ctx->live_count.as<uint32_t>()); CTX_LAUNCH_CHECK("k_live_compact");
+        const unsigned nb = grid_for(npix, 256);
+        CTX_CUDA(ctx->live_count.ensure(sizeof(uint32_t) * ((size_t)nb + 1)));   // [0] the total, [1 + b] block counts -> block offsets
+        uint32_t* const cnt = ctx->live_count.as<uint32_t>();
+        // the film rectangles of the BVH's bounds and of the lights go behind those of the wide primitives (same buffer)
+        f4* const rects = ctx->big_rect.as<f4>();
+        const uint32_t n_lights = std::min<uint32_t>(ds.n_area_lights, NRCU_LIVE_LIGHTS), n_rect = ds.n_big + 1u + n_lights;
+        k_scene_rects<<<1, 64, 0, ctx->stream>>>(ds, rects); CTX_LAUNCH_CHECK("k_scene_rects");
+        k_live_flags<<<nb, 256, 0, ctx->stream>>>(ds, rects, n_rect, ds.n_area_lights > NRCU_LIVE_LIGHTS ? 1 : 0, ctx->live_flag.as<unsigned char>(), cnt + 1); CTX_LAUNCH_CHECK("k_live_flags");
+        k_live_scan<<<1, 1024, 0, ctx->stream>>>(cnt + 1, nb, cnt); CTX_LAUNCH_CHECK("k_live_scan");
+        k_live_scatter<<<nb, 256, 0, ctx->stream>>>(ctx->live_flag.as<unsigned char>(), npix, cnt + 1, ctx->live_px.as<uint32_t>()); CTX_LAUNCH_CHECK("k_live_scatter");
         uint32_t n_live = npix;
-        CTX_CUDA(cudaMemcpyAsync(&n_live, ctx->live_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CUDA(cudaMemcpyAsync(&n_live, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CUDA(cudaStreamSynchronize(ctx->stream));
         if (n_live < npix) { ds.live_px = ctx->live_px.as<uint32_t>(); ds.live_flag = ctx->live_flag.as<unsigned char>(); ds.n_live = n_live; }
     }
@@ -432,7 +439,7 @@ static int build_bvh(nrcu_ctx* ctx, uint32_t n, float max_abs_coord) {
     // film rectangles of the wide primitives for the camera rays of a pinhole camera (big_list_mask_film); NRCU_FILM_RECTS=0: off
     ds.big_rect = nullptr;
     if (n_big > 0 && ds.cam.lens_radius == 0.f && film_rects()) {
-        CTX_CUDA(ctx->big_rect.ensure(sizeof(f4) * NRCU_MAX_BIG));
+        CTX_CUDA(ctx->big_rect.ensure(sizeof(f4) * NRCU_LIVE_RECTS));   // + the BVH's bounds and the lights (live pixels)
         k_big_rects<<<1, NRCU_MAX_BIG, 0, st>>>(ds, ctx->big_rect.as<f4>()); CTX_LAUNCH_CHECK("k_big_rects");
         ds.big_rect = ctx->big_rect.as<f4>();
     }
@@ -888,6 +895,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
         stats->ms_setup = ctx->ms_setup; stats->bvh_nodes = ctx->bvh_nodes; stats->n_primitives = ds.n_prims;
         stats->max_queue = glass_branch ? h_cnt[CNT_HIGH_WATER] : std::min<uint32_t>(qslots, nlive * (s1 - s0));   // without branching the bounce-0 queue is the largest
         stats->scheduler = NRCU_SCHED_WAVES; stats->iterations = bounce_rounds; stats->wave_retries = wave_retries;
+        stats->dead_pixels = ds.depth ? npix - nlive : 0u;
         return check_overflow(ctx);
     }
     return NRCU_OK;

@@ -169,60 +169,80 @@ __device__ f4 film_rect_of_box(const DScene& s, const double lo[3], const double
 }
 // Live pixels (DScene::live_px): a pixel is live iff the film footprint of its jittered samples - the pixel corner +- one
 // pixel, AccPathTracer.cpp:23-29 - overlaps the film rectangle of a wide primitive, of the BVH's bounds or of an area light
-// (closestHitLight is asked for every ray, AccPathTracer.cpp:128).  One thread per pixel; the rectangles are set up per block.
-#define NRCU_LIVE_RECTS (NRCU_MAX_BIG + 1 + 32)
-__global__ void __launch_bounds__(256) k_live_flags(DScene s, unsigned char* flag) {
-    __shared__ f4 rc[NRCU_LIVE_RECTS];
-    __shared__ uint32_t n_rc, all_live;
-    if (threadIdx.x == 0) { n_rc = 0; all_live = s.n_area_lights > 32u ? 1u : 0u; }
-    __syncthreads();
-    const uint32_t n_jobs = s.n_big + 1u + min(s.n_area_lights, 32u);
-    if (threadIdx.x < n_jobs) {
-        f4 r = mk4(NRCU_INF, -NRCU_INF, NRCU_INF, -NRCU_INF);   // empty
-        bool have = true;
-        if (threadIdx.x < s.n_big) r = s.big_rect[threadIdx.x];
-        else if (threadIdx.x == s.n_big) {
-            if (s.root_ref == NRCU_REF_EMPTY) have = false;
-            else {
-                const double lo[3] = {s.bvh_lo.x, s.bvh_lo.y, s.bvh_lo.z}, hi[3] = {s.bvh_hi.x, s.bvh_hi.y, s.bvh_hi.z};
-                r = film_rect_of_box(s, lo, hi);
-            }
-        } else {   // a light quad p + a u + b v: the box of its four corners (record layout: nrcu_host_prep.hpp)
-            const f4* L = s.area_lights + NRCU_LIGHT_F4 * (size_t)(threadIdx.x - s.n_big - 1u);
-            const f4 l0 = L[0], l1 = L[1], lu = L[4], lv = L[5];
-            const double p[3] = {l0.w, l1.x, l1.y}, u[3] = {lu.x, lu.y, lu.z}, v[3] = {lv.x, lv.y, lv.z};
-            double lo[3], hi[3];
-            for (int k = 0; k < 3; k++) {
-                const double c0 = p[k], c1 = p[k] + u[k], c2 = p[k] + v[k], c3 = p[k] + u[k] + v[k];
-                const double pad = 1e-4 * (1.0 + fabs(c0) + fabs(u[k]) + fabs(v[k]));
-                lo[k] = fmin(fmin(c0, c1), fmin(c2, c3)) - pad; hi[k] = fmax(fmax(c0, c1), fmax(c2, c3)) + pad;
-            }
+// (closestHitLight is asked for every ray, AccPathTracer.cpp:128).
+#define NRCU_LIVE_LIGHTS 32
+#define NRCU_LIVE_RECTS (NRCU_MAX_BIG + 1 + NRCU_LIVE_LIGHTS)
+// rect[n_big] = the BVH's bounds, rect[n_big + 1 + i] = light i (empty rectangles where there is nothing); one thread each
+__global__ void k_scene_rects(DScene s, f4* rect) {
+    const uint32_t t = threadIdx.x;
+    if (t > min(s.n_area_lights, (uint32_t)NRCU_LIVE_LIGHTS)) return;
+    f4 r = mk4(NRCU_INF, -NRCU_INF, NRCU_INF, -NRCU_INF);   // empty
+    if (t == 0) {
+        if (s.root_ref != NRCU_REF_EMPTY) {
+            const double lo[3] = {s.bvh_lo.x, s.bvh_lo.y, s.bvh_lo.z}, hi[3] = {s.bvh_hi.x, s.bvh_hi.y, s.bvh_hi.z};
             r = film_rect_of_box(s, lo, hi);
         }
-        if (have) rc[atomicAdd(&n_rc, 1u)] = r;
+    } else {   // a light quad p + a u + b v: the box of its four corners (record layout: nrcu_host_prep.hpp)
+        const f4* L = s.area_lights + NRCU_LIGHT_F4 * (size_t)(t - 1u);
+        const f4 l0 = L[0], l1 = L[1], lu = L[4], lv = L[5];
+        const double p[3] = {l0.w, l1.x, l1.y}, u[3] = {lu.x, lu.y, lu.z}, v[3] = {lv.x, lv.y, lv.z};
+        double lo[3], hi[3];
+        for (int k = 0; k < 3; k++) {
+            const double c0 = p[k], c1 = p[k] + u[k], c2 = p[k] + v[k], c3 = p[k] + u[k] + v[k];
+            const double pad = 1e-4 * (1.0 + fabs(c0) + fabs(u[k]) + fabs(v[k]));
+            lo[k] = fmin(fmin(c0, c1), fmin(c2, c3)) - pad; hi[k] = fmax(fmax(c0, c1), fmax(c2, c3)) + pad;
+        }
+        r = film_rect_of_box(s, lo, hi);
     }
+    rect[s.n_big + t] = r;
+}
+// one thread per pixel: flag + the number of live pixels of the block (for the ordered compaction)
+__global__ void __launch_bounds__(256) k_live_flags(DScene s, const f4* rect, uint32_t n_rect, int all_live, unsigned char* flag, uint32_t* block_count) {
+    __shared__ f4 rc[NRCU_LIVE_RECTS];
+    for (uint32_t k = threadIdx.x; k < n_rect; k += blockDim.x) rc[k] = rect[k];
     __syncthreads();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= s.width * s.height) return;
-    const int w = (int)s.width, h = (int)s.height;
-    const int row = (int)(p / (uint32_t)w), j = (int)(p % (uint32_t)w), i = h - 1 - row;   // pt_camera_ray's pixel coordinates
-    const float fx0 = ((float)j - 1.f) / (float)w, fx1 = ((float)j + 1.f) / (float)w, fy0 = ((float)i - 1.f) / (float)h, fy1 = ((float)i + 1.f) / (float)h;
-    bool live = all_live != 0u;
-    for (uint32_t k = 0; k < n_rc && !live; k++) live = fx1 >= rc[k].x && fx0 <= rc[k].y && fy1 >= rc[k].z && fy0 <= rc[k].w;
-    flag[p] = live ? 1 : 0;
+    bool live = false;
+    if (p < s.width * s.height) {
+        const int w = (int)s.width, h = (int)s.height;
+        const int row = (int)(p / (uint32_t)w), j = (int)(p % (uint32_t)w), i = h - 1 - row;   // pt_camera_ray's pixel coordinates
+        const float fx0 = ((float)j - 1.f) / (float)w, fx1 = ((float)j + 1.f) / (float)w, fy0 = ((float)i - 1.f) / (float)h, fy1 = ((float)i + 1.f) / (float)h;
+        live = all_live != 0;
+        for (uint32_t k = 0; k < n_rect && !live; k++) live = fx1 >= rc[k].x && fx0 <= rc[k].y && fy1 >= rc[k].z && fy0 <= rc[k].w;
+        flag[p] = live ? 1 : 0;
+    }
+    const int c = __syncthreads_count(live ? 1 : 0);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = (uint32_t)c;
 }
-// flags -> ascending list of the live pixels (one block: per-thread ranges, a scan of the range counts)
-__global__ void __launch_bounds__(1024) k_live_compact(const unsigned char* flag, uint32_t npix, uint32_t* list, uint32_t* n_live) {
+// exclusive scan of the block counts (one block; a thread owns a contiguous range) -> block offsets, total
+__global__ void __launch_bounds__(1024) k_live_scan(uint32_t* block_count, uint32_t n_blocks, uint32_t* n_live) {
     __shared__ uint32_t part[1024];
-    const uint32_t per = (npix + 1023u) / 1024u, lo = min(npix, threadIdx.x * per), hi = min(npix, lo + per);
+    const uint32_t per = (n_blocks + 1023u) / 1024u, lo = min(n_blocks, threadIdx.x * per), hi = min(n_blocks, lo + per);
     uint32_t c = 0;
-    for (uint32_t p = lo; p < hi; p++) c += flag[p];
+    for (uint32_t b = lo; b < hi; b++) c += block_count[b];
     part[threadIdx.x] = c;
     __syncthreads();
-    if (threadIdx.x == 0) { uint32_t run = 0; for (int t = 0; t < 1024; t++) { const uint32_t v = part[t]; part[t] = run; run += v; } *n_live = run; }
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {   // Hillis-Steele inclusive scan
+        const uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - c;
+    for (uint32_t b = lo; b < hi; b++) { const uint32_t v = block_count[b]; block_count[b] = run; run += v; }
+    if (threadIdx.x == 1023u) *n_live = part[1023];
+}
+// live pixels of a block, in pixel order, behind the block's offset
+__global__ void __launch_bounds__(256) k_live_scatter(const unsigned char* flag, uint32_t npix, const uint32_t* block_offset, uint32_t* list) {
+    __shared__ uint32_t warp_base[8];
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const bool live = p < npix && flag[p];
+    const uint32_t m = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) warp_base[wib] = __popc(m);
     __syncthreads();
-    uint32_t at = part[threadIdx.x];
-    for (uint32_t p = lo; p < hi; p++) if (flag[p]) list[at++] = p;
+    uint32_t base = block_offset[blockIdx.x];
+    for (uint32_t k = 0; k < wib; k++) base += warp_base[k];
+    if (live) list[base + __popc(m & ((1u << lane) - 1u))] = p;
 }
 // Append the flagged lanes' queue positions to the survivor list with one atomic per warp.
 __device__ __forceinline__ void append_survivors(bool more, uint32_t pos, uint32_t* surv, uint32_t* n_surv) {

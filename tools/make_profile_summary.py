@@ -19,7 +19,7 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 SMS, SCHEDULERS = 148, 4
-PATHS_PER_WAVE = 32 * 1920 * 1080   # bench.py default workload (cfg3) captured with NRCU_WAVE_MSLOTS=128: 64 Mi path slots per wave -> 32 spp of 1080p
+PATHS_PER_WAVE = 128 * 1920 * 1080   # path samples of one FRAME of the capture command (bench.py default workload cfg3 at --spp 128)
 KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -63,7 +63,7 @@ def main():
                     f"{d.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0):.2f},{d.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.1f},"
                     f"{d.get('dram__bytes_read.sum', 0):.0f},{d.get('dram__bytes_write.sum', 0):.0f}\n")
     ours = [d for d in launches if d["kernel"].startswith("k_")]
-    render = [d for d in ours if not d["kernel"].startswith(("k_bvh", "k_build", "k_mesh", "k_big_rects", "k_env"))]
+    render = [d for d in ours if not d["kernel"].startswith(("k_bvh", "k_build", "k_mesh", "k_big_rects", "k_env", "k_live", "k_scene_rects"))]
     T = sum(d["gpu__time_duration.sum"] for d in render)
     agg = collections.OrderedDict()
     for d in render:
@@ -81,8 +81,10 @@ def main():
                           dram_bytes_per_launch=round(a["dram"] / a["launches"]), dram_gbs=round(a["dram"] / (a["time_us"] * 1e-6) * 1e-9, 1))
     # warp instructions of the complete waves in the capture (everything up to the last k_accumulate), per path sample:
     # a wave of the bench workload is 32 samples of 1920 x 1080 pixels
-    last_acc = max((i for i, d in enumerate(render) if d["kernel"].startswith("k_accumulate")), default=-1)
-    n_waves = sum(1 for d in render if d["kernel"].startswith("k_accumulate"))
+    # complete frames of the capture: everything up to the last k_resolve; a frame of the capture command is 128 spp of 1920 x 1080
+    # (the number of waves per frame depends on the live-pixel count, so the unit of work is the frame, not the wave)
+    last_acc = max((i for i, d in enumerate(render) if d["kernel"].startswith("k_resolve")), default=-1)
+    n_waves = sum(1 for d in render if d["kernel"].startswith("k_resolve"))
     inst_complete = sum(d.get("smsp__inst_executed.sum", 0) for d in render[:last_acc + 1])
     warp_inst_per_path = inst_complete / (n_waves * PATHS_PER_WAVE) if n_waves else None
     dram_complete = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in render[:last_acc + 1])
@@ -132,7 +134,7 @@ def main():
     with open(os.path.join(out_dir, f"{rnd}_summary.md"), "w") as f:
         f.write(f"# {rnd} profile summary (ncu, B200, `NRCU_WAVE_MSLOTS=128 bench.py --steps 1 --warmup 1 --spp 128 --no-cpu-baseline --no-e2e --no-other-workloads`, first {len(launches)} launches; kernel sources {csrc_sha})\n\n")
         f.write(f"Whole step: **{warp_inst_per_path:.1f} warp instructions and {dram_per_path:.0f} DRAM bytes per path sample**, {lane_complete / max(inst_complete, 1):.1f} active lanes per instruction "
-                f"(complete waves of the capture: {n_waves} x {PATHS_PER_WAVE} paths).\n\n")
+                f"(complete frames of the capture: {n_waves} x {PATHS_PER_WAVE} path samples).\n\n")
         f.write("| kernel | launches | time (us) | share | warp-inst | lanes/inst | issue-active % | DRAM B/launch | DRAM GB/s |\n|---|---|---|---|---|---|---|---|---|\n")
         for k, a in sorted(kernels.items(), key=lambda kv: -kv[1]["time_us"]):
             f.write(f"| `{k}` | {a['launches']} | {a['time_us']:.0f} | {a['share']*100:.1f} % | {a['warp_inst']/1e6:.0f} M | {a['threads_per_inst']} | {a['issue_active_pct']} | {a['dram_bytes_per_launch']/1e6:.1f} M | {a['dram_gbs']} |\n")
