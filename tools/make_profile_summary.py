@@ -146,17 +146,22 @@ def main():
         f.write("\nFull captures (`ncu --set full`, one launch each, early bounces of the first waves):\n\n| kernel | time us | regs | lanes/inst | issue % | warps active % | L1 hit % | L2 hit % | L1 GB/s (% of peak) | L2 GB/s (% of peak) | DRAM R MB | DRAM W MB | DRAM GB/s (of 6549.8) | long-scoreboard stall |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         U = {k: units[hdr.index(k)] for k in KEEP if k in hdr}
         def mb(h, k):
-            v = float(h.get(k, 0) or 0)
+            try: v = float(str(h.get(k, 0) or 0).replace(',', ''))
+            except ValueError: v = 0.0
             return v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(U.get(k, "byte"), 1e-6)
         def us(h, k):
-            v = float(h.get(k, 0) or 0)
+            try: v = float(str(h.get(k, 0) or 0).replace(',', ''))
+            except ValueError: v = 0.0
             return v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(U.get(k, "us"), 1.0)
         for h in hot:
             g = lambda k: h.get(k, "")
+            def fl(x):
+                try: return float(str(x).replace(',', ''))
+                except ValueError: return 0.0
             f.write(f"| `{h['kernel']}` | {us(h, 'gpu__time_duration.sum'):.1f} | {g('launch__registers_per_thread')} | {g('smsp__thread_inst_executed_per_inst_executed.ratio')} | "
-                    f"{float(g('smsp__issue_active.avg.pct_of_peak_sustained_active') or 0):.1f} | {float(g('sm__warps_active.avg.pct_of_peak_sustained_active') or 0):.1f} | "
-                    f"{float(g('l1tex__t_sector_hit_rate.pct') or 0):.1f} | {float(g('lts__t_sector_hit_rate.pct') or 0):.1f} | {float(g('SM_B.TriageCompute.l1tex__t_sectors.sum') or 0) * 32e-9 / max(us(h, 'gpu__time_duration.sum') * 1e-6, 1e-12):.0f} ({float(g('l1tex__throughput.avg.pct_of_peak_sustained_elapsed') or 0):.0f} %) | {float(g('lts__t_sectors.sum') or 0) * 32e-9 / max(us(h, 'gpu__time_duration.sum') * 1e-6, 1e-12):.0f} ({float(g('lts__throughput.avg.pct_of_peak_sustained_elapsed') or 0):.0f} %) | {mb(h, 'dram__bytes_read.sum'):.1f} | {mb(h, 'dram__bytes_write.sum'):.1f} | {(mb(h, 'dram__bytes_read.sum') + mb(h, 'dram__bytes_write.sum')) / max(us(h, 'gpu__time_duration.sum'), 1e-9) * 1e3:.0f} ({(mb(h, 'dram__bytes_read.sum') + mb(h, 'dram__bytes_write.sum')) / max(us(h, 'gpu__time_duration.sum'), 1e-9) * 1e3 / 6549.8 * 100:.0f} %) | "
-                    f"{float(g('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio') or 0):.2f} |\n")
+                    f"{fl(g('smsp__issue_active.avg.pct_of_peak_sustained_active')):.1f} | {fl(g('sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | "
+                    f"{fl(g('l1tex__t_sector_hit_rate.pct')):.1f} | {fl(g('lts__t_sector_hit_rate.pct')):.1f} | {fl(g('SM_B.TriageCompute.l1tex__t_sectors.sum')) * 32e-9 / max(us(h, 'gpu__time_duration.sum') * 1e-6, 1e-12):.0f} ({fl(g('l1tex__throughput.avg.pct_of_peak_sustained_elapsed')):.0f} %) | {fl(g('lts__t_sectors.sum')) * 32e-9 / max(us(h, 'gpu__time_duration.sum') * 1e-6, 1e-12):.0f} ({fl(g('lts__throughput.avg.pct_of_peak_sustained_elapsed')):.0f} %) | {mb(h, 'dram__bytes_read.sum'):.1f} | {mb(h, 'dram__bytes_write.sum'):.1f} | {(mb(h, 'dram__bytes_read.sum') + mb(h, 'dram__bytes_write.sum')) / max(us(h, 'gpu__time_duration.sum'), 1e-9) * 1e3:.0f} ({(mb(h, 'dram__bytes_read.sum') + mb(h, 'dram__bytes_write.sum')) / max(us(h, 'gpu__time_duration.sum'), 1e-9) * 1e3 / 6549.8 * 100:.0f} %) | "
+                    f"{fl(g('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio')):.2f} |\n")
     print(open(os.path.join(out_dir, f"{rnd}_summary.md")).read())
 
 
