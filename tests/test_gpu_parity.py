@@ -651,7 +651,7 @@ def test_kernel_variants_trace_the_same_paths():
         c.upload(fs, 2)
         acc = torch.zeros(90, 160, 4, device="cuda:0"); torch.cuda.synchronize()
         st = c.render_accumulate(acc.data_ptr(), seed=9)
-        np.save(sys.argv[1], acc.cpu().numpy()); print("RAYS", st["rays"])
+        np.save(sys.argv[1], acc.cpu().numpy()); print("RAYS", st["rays"]); print("DEAD", st["dead_pixels"])
     """ % (os.path.dirname(GOLDEN), os.path.dirname(os.path.dirname(GOLDEN))))
     variants = {
         "round1": dict(NRCU_SHADE_POOL="0", NRCU_QUEUE_REGIONS="1", NRCU_BIG_BALANCED="1", NRCU_FILM_RECTS="0"),
@@ -660,6 +660,8 @@ def test_kernel_variants_trace_the_same_paths():
         "regions_without_pool": dict(NRCU_SHADE_POOL="0", NRCU_QUEUE_REGIONS="32"),
         "per_lane_stage1": dict(NRCU_BIG_BALANCED="0", NRCU_QUEUE_REGIONS="4"),
         "one_wave": dict(NRCU_WAVES="1"),
+        "every_pixel_live": dict(NRCU_LIVE_PIXELS="0"),
+        "no_film_rectangles": dict(NRCU_FILM_RECTS="0"),
     }
     with tempfile.TemporaryDirectory() as td:
         out = {}
@@ -667,9 +669,16 @@ def test_kernel_variants_trace_the_same_paths():
             path = os.path.join(td, name + ".npy")
             r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
             assert r.returncode == 0, (name, r.stderr[-2000:])
-            out[name] = (np.load(path), [ln for ln in r.stdout.splitlines() if ln.startswith("RAYS")][0])
+            out[name] = (np.load(path), [ln for ln in r.stdout.splitlines() if ln.startswith("RAYS")][0],
+                         int([ln for ln in r.stdout.splitlines() if ln.startswith("DEAD")][0].split()[1]))
     ref = out["round1"]
     assert ref[0][..., :3].sum() > 0
-    for name, (acc, rays) in out.items():
+    for name, (acc, rays, dead) in out.items():
         assert rays == ref[1], (name, rays, ref[1])
         assert np.array_equal(acc.view(np.uint32), ref[0].view(np.uint32)), name
+    # the 16:9 view of the square room has pixels that can see neither geometry nor the light: no camera rays for them
+    # (their samples are counted as answered queries, so the ray counts above agree), and they are black in every variant
+    assert out["round1"][2] == 0 and out["every_pixel_live"][2] == 0 and out["no_film_rectangles"][2] == 0
+    dead = out["default"][2]
+    assert 0.2 * 160 * 90 < dead < 0.6 * 160 * 90, dead
+    assert (ref[0][..., :3].reshape(-1, 3).sum(1) == 0).sum() >= dead
