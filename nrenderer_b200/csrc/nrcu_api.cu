@@ -92,7 +92,7 @@ struct nrcu_ctx {
     uint32_t spp = 0;
     DScene ds{};
     // scene buffers
-    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, big_rect, live_px, live_flag, live_count, materials, mat_head, area_lights, env, env_tab;
+    DevBuf prim_geom, prim_shade, prim_box, prim_bound, prim_meta, nodes, leaf_prims, leaf_geom, leaf_box, big_geom, big_box, big_bound, big_meta, big_rect, live_px, dead_px, live_flag, live_count, materials, mat_head, area_lights, env, env_tab;
     // scene-prep sources kept for nrcu_download_primitives
     DevBuf src_a, src_b, sph_pos, sph_rad, sph_mat, tri_v, tri_n, tri_mat, pl_n, pl_p, pl_u, pl_v, pl_mat,
         mesh_voff, mesh_ioff, mesh_pos, mesh_idx, mesh_mat;
@@ -349,8 +349,8 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
     }
     pt.mark("build_bvh (incl. frees)");
     // ---- live pixels: camera rays are only generated where they can meet something (DScene::live_px) ----------------
-    ds.live_px = nullptr; ds.live_flag = nullptr; ds.n_live = sc->width * sc->height;
-    if (mode != NRCU_MODE_RAYCAST && ds.big_rect && !ds.env_rgba && ds.depth > 0 && live_pixels()) {
+    ds.live_px = nullptr; ds.live_flag = nullptr; ds.n_live = sc->width * sc->height; ds.dead_px = nullptr; ds.dead_env = 0;
+    if (mode != NRCU_MODE_RAYCAST && ds.big_rect && ds.depth > 0 && live_pixels()) {
         const uint32_t npix = sc->width * sc->height;
         CTX_CUDA(ctx->live_px.ensure(sizeof(uint32_t) * (size_t)std::max(npix, 1u)));
         CTX_CUDA(ctx->live_flag.ensure((size_t)std::max(npix, 1u)));
@@ -363,11 +363,19 @@ int nrcu_upload_scene(nrcu_ctx* ctx, const nrcu_scene* sc, int mode) {
         k_scene_rects<<<1, 64, 0, ctx->stream>>>(ds, rects); CTX_LAUNCH_CHECK("k_scene_rects");
         k_live_flags<<<nb, 256, 0, ctx->stream>>>(ds, rects, n_rect, ds.n_area_lights > NRCU_LIVE_LIGHTS ? 1 : 0, ctx->live_flag.as<unsigned char>(), cnt + 1); CTX_LAUNCH_CHECK("k_live_flags");
         k_live_scan<<<1, 1024, 0, ctx->stream>>>(cnt + 1, nb, cnt); CTX_LAUNCH_CHECK("k_live_scan");
-        k_live_scatter<<<nb, 256, 0, ctx->stream>>>(ctx->live_flag.as<unsigned char>(), npix, cnt + 1, ctx->live_px.as<uint32_t>()); CTX_LAUNCH_CHECK("k_live_scatter");
+        k_live_scatter<<<nb, 256, 0, ctx->stream>>>(ctx->live_flag.as<unsigned char>(), npix, cnt + 1, ctx->live_px.as<uint32_t>(), 1); CTX_LAUNCH_CHECK("k_live_scatter");
+        const bool dead_env = ds.env_rgba && mode == NRCU_MODE_ACC;   // dead pixels see the environment map (k_env_dead)
+        if (dead_env) {
+            CTX_CUDA(ctx->dead_px.ensure(sizeof(uint32_t) * (size_t)std::max(npix, 1u)));
+            k_live_scatter<<<nb, 256, 0, ctx->stream>>>(ctx->live_flag.as<unsigned char>(), npix, cnt + 1, ctx->dead_px.as<uint32_t>(), 0); CTX_LAUNCH_CHECK("k_live_scatter");
+        }
         uint32_t n_live = npix;
         CTX_CUDA(cudaMemcpyAsync(&n_live, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTX_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (n_live < npix) { ds.live_px = ctx->live_px.as<uint32_t>(); ds.live_flag = ctx->live_flag.as<unsigned char>(); ds.n_live = n_live; }
+        if (n_live < npix) {
+            ds.live_px = ctx->live_px.as<uint32_t>(); ds.live_flag = ctx->live_flag.as<unsigned char>(); ds.n_live = n_live;
+            if (dead_env) { ds.dead_px = ctx->dead_px.as<uint32_t>(); ds.dead_env = 1; }
+        }
     }
     pt.mark("live pixels");
     CTX_CUDA(cudaEventRecord(e1, ctx->stream));
@@ -789,6 +797,11 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             if (gate) k_raygen<true, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, NRCU_RC_K);
             else k_raygen<false, true><<<gen_grid, 256, 0, st>>>(ds, seed, pp.w0, pp.n_slots, pp.q[0], pp.L, pp.d_qn, pp.hb, pp.surv, pp.d_nsurv, NRCU_RC_K);
             CTX_LAUNCH_CHECK("k_raygen");
+            if (ds.dead_env && ds.depth > 0 && pp.kw * (npix - nlive) > 0) {   // environment map: the dead pixels' samples are the map along the camera ray
+                const uint32_t n_entries = pp.kw * (npix - nlive);
+                k_env_dead<<<std::min<unsigned>(grid_for(n_entries, 256), (unsigned)sms * 8), 256, 0, st>>>(ds, seed, pp.w0, n_entries, pp.L);
+                CTX_LAUNCH_CHECK("k_env_dead");
+            }
             if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); ev_i += 2; }   // booked as closest-hit time: stage 1 of bounce 0 is most of this kernel
         }
         // ---- bounces: stage 1 (k_big; bounce 0's ran inside k_raygen), stage 2 (k_trace*) on the survivors, k_shade ---
@@ -878,7 +891,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
             Pipe& pp = P[p];
             if (!pp.live) continue;
             if (NP > 1 && acc_recorded) CTX_CUDA(cudaStreamWaitEvent(pp.st, ctx->ev_acc, 0));
-            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw, pp.d_qn, pp.d_qr, K, nee ? pp.d_nshadow : nullptr, (uint32_t)CS, ds.depth, NRCU_RC_A, ds.live_flag, npix - nlive);
+            k_accumulate<<<grid_for(npix, 256), 256, 0, pp.st>>>(pp.L, d_accum, npix, pp.kw, pp.kw, pp.d_qn, pp.d_qr, K, nee ? pp.d_nshadow : nullptr, (uint32_t)CS, ds.depth, NRCU_RC_A, ds.dead_env ? nullptr : ds.live_flag, npix - nlive);
             CTX_LAUNCH_CHECK("k_accumulate");
             if (NP > 1) { CTX_CUDA(cudaEventRecord(ctx->ev_acc, pp.st)); acc_recorded = true; }
         }

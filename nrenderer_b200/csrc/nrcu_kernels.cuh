@@ -232,17 +232,30 @@ __global__ void __launch_bounds__(1024) k_live_scan(uint32_t* block_count, uint3
     for (uint32_t b = lo; b < hi; b++) { const uint32_t v = block_count[b]; block_count[b] = run; run += v; }
     if (threadIdx.x == 1023u) *n_live = part[1023];
 }
-// live pixels of a block, in pixel order, behind the block's offset
-__global__ void __launch_bounds__(256) k_live_scatter(const unsigned char* flag, uint32_t npix, const uint32_t* block_offset, uint32_t* list) {
+// live pixels of a block, in pixel order, behind the block's offset (want = 0: the dead pixels; block b then holds
+// min(256, npix - 256 b) - live count of them, so its offset is 256 b - the live offset)
+__global__ void __launch_bounds__(256) k_live_scatter(const unsigned char* flag, uint32_t npix, const uint32_t* block_offset, uint32_t* list, int want) {
     __shared__ uint32_t warp_base[8];
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const bool live = p < npix && flag[p];
+    const bool live = p < npix && (flag[p] != 0) == (want != 0);
     const uint32_t m = __ballot_sync(0xffffffffu, live);
     if (lane == 0) warp_base[wib] = __popc(m);
     __syncthreads();
-    uint32_t base = block_offset[blockIdx.x];
+    uint32_t base = want ? block_offset[blockIdx.x] : blockIdx.x * blockDim.x - block_offset[blockIdx.x];
     for (uint32_t k = 0; k < wib; k++) base += warp_base[k];
     if (live) list[base + __popc(m & ((1u << lane) - 1u))] = p;
+}
+// Environment-map scenes: the camera rays of the dead pixels leave the scene for certain, so their radiance is the map along
+// the ray (path_vertex's miss branch at bounce 0: throughput 1) - written straight into the radiance slot, one thread per
+// (dead pixel, sample of the wave); no queue entry, no closest-hit query, no shading pass.
+__global__ void __launch_bounds__(256) k_env_dead(DScene s, uint64_t seed, uint32_t sample0, uint32_t n_entries, f4* L) {
+    const uint32_t npix = s.width * s.height, n_dead = npix - s.n_live;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += gridDim.x * blockDim.x) {
+        const uint32_t j = i % n_dead, sw = i / n_dead, pixel = s.dead_px[j];
+        const Ray r = pt_camera_ray(s, seed, pixel, sample0 + sw);
+        const vec3 e = mk3(1.f, 1.f, 1.f) * env_lookup(s, r.d);
+        L[(size_t)sw * npix + pixel] = mk4(e.x, e.y, e.z, 0.f);
+    }
 }
 // Append the flagged lanes' queue positions to the survivor list with one atomic per warp.
 __device__ __forceinline__ void append_survivors(bool more, uint32_t pos, uint32_t* surv, uint32_t* n_surv) {

@@ -117,6 +117,10 @@ struct DScene {
     const uint32_t* live_px;
     const unsigned char* live_flag;   // per pixel, for the accumulation (dead pixels have no radiance slots written)
     uint32_t n_live;
+    // with an environment map (AccPathTracer mode) the dead pixels are not black: their samples look the map up along the
+    // camera ray.  That is done at once, one thread per (dead pixel, sample), without a queue entry (k_env_dead).
+    const uint32_t* dead_px;          // the dead pixels in pixel order (null unless dead_env)
+    uint32_t dead_env;
     // shading
     const DMaterial* materials;
     const f4* mat_head;           // per material: (diffuseColor / pi  - Lambertian.cpp:30, the same fp32 division -, type bits): one gather for the common case
