@@ -670,13 +670,13 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
     if (s1 < s0) { ctx->error = "sample_end < sample_begin"; return NRCU_ERR_INVALID; }
     const uint64_t seed = params ? params->seed : 0;
     const int glass_branch = params && params->glass_mode == NRCU_GLASS_BRANCH;
-    // Wave size: k samples of every pixel; NRCU_WAVE_MSLOTS (default 128 Mi, ~15 GB of the 180 GB HBM) path slots
-    // are in flight, split over NRCU_WAVES (default 2) waves that run side by side on their own streams with
-    // full-size persistent grids.  Bigger waves amortise the latency floor of the deep bounces (few rays, ~50 us per
-    // persistent launch); concurrent waves let the SMs interleave CTAs of an issue-bound kernel of one wave
-    // (k_big: 76 % issue-active) with CTAs of a latency-bound kernel of the other (k_shade: 45 %) and hide every
-    // kernel's tail behind the other wave's work.  Measured on cfg3: 1 wave x 32 Mi 2.14, 2 x 64 Mi 2.68,
-    // 4 x 64 Mi 2.71 Gpath-samples/s.  The accumulation order is fixed by events, so the image is bit-identical.
+    // Wave size: k samples of every live pixel; NRCU_WAVE_MSLOTS (default 256 Mi, ~29 GB of the 180 GB HBM) queue entries
+    // are in flight, split over NRCU_WAVES (default 2) waves that run side by side on their own streams with full-size
+    // persistent grids.  Bigger waves amortise the latency floor of the deep bounces (few rays; the longest single
+    // traversal ends every stage-2 launch on a nearly idle machine), and the second wave's kernels run in those tails.
+    // Measured on cfg3 (profiles/r2_history.md): one wave 3.0, two 3.4 Gpath-samples/s before the live pixels; round 1, with
+    // the shading kernel waiting for its slot atomics, 2.14 against 2.68.  The accumulation order is fixed by events, so the
+    // image does not depend on the number of waves.
     // camera rays exist for the live pixels only (DScene::live_px): a wave holds k x n_live queue entries and k x n_pixels radiance slots
     const uint32_t nlive = ds.live_px ? ds.n_live : npix;
     const bool explicit_k = params && params->samples_per_wave != 0;
@@ -838,7 +838,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i + 3, ev_i + 1, 2}); }
 #define NRCU_SHADE(N, B) k_shade<N, B><<<shade_grid, 256, 0, st>>>(ds, seed, d, glass_branch, pp.w0, qi, rin, pp.hb, qo, cnt_out, logk, capacity + slack, pp.L, pp.qs, pp.d_nshadow + CS * d)
                 if (shade_pool() && !nee && !glass_branch)
-                    k_shade_pool<false><<<shade_grid, 256, 0, st>>>(ds, seed, d, pp.w0, qi, rin, pp.hb, qo, cnt_out, logk, capacity + slack, pp.L);
+                    k_shade_pool<<<shade_grid, 256, 0, st>>>(ds, seed, d, pp.w0, qi, rin, pp.hb, qo, cnt_out, logk, capacity + slack, pp.L);
                 else
 #if NRCU_OPT_BRANCH_TEMPLATE
                 if (glass_branch) { if (nee) NRCU_SHADE(true, true); else NRCU_SHADE(false, true); }

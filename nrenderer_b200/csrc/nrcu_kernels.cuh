@@ -1062,7 +1062,6 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
 #ifndef NRCU_POOL_PREFETCH_LATE
 #define NRCU_POOL_PREFETCH_LATE 2
 #endif
-template <bool DUMMY>
 __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_pool(DScene s, uint64_t seed, uint32_t d, uint32_t sample0,
                                                                        PathQueue qi, QRegions rin, const float2* hits,
                                                                        PathQueue qo, uint32_t* n_out_ptr, uint32_t out_logk, uint32_t out_capacity, f4* L) {
