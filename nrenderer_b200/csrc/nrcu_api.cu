@@ -224,7 +224,7 @@ static int check_overflow(nrcu_ctx* ctx) {
     CTX_CUDA(cudaMemset(ctx->overflow.p, 0, sizeof(h)));
     char buf[256];
     if (h[0]) std::snprintf(buf, sizeof(buf), "BVH traversal stack overflow: %u entries did not fit %d-entry stacks; hits may have been missed", h[0], ctx->ds.stack_limit);
-    else std::snprintf(buf, sizeof(buf), "ray queue overflow in the branching glass mode: %u rays did not fit even at one sample per wave", h[1]);
+    else std::snprintf(buf, sizeof(buf), "ray queue overflow: %u rays did not fit their queue (branching glass mode: even at one sample per wave)", h[1]);
     ctx->error = buf;
     return NRCU_ERR_OVERFLOW;
 }
@@ -630,7 +630,7 @@ static void launch_stage2(nrcu_ctx* ctx, cudaStream_t st, unsigned share, const 
 template <bool GATE>
 static void launch_closest_hit(nrcu_ctx* ctx, cudaStream_t st, unsigned share, const DScene& ds, PathQueue q, const uint32_t* n_ptr, float2* hits, uint32_t* surv,
                                uint32_t* n_surv, uint32_t* fetch, unsigned long long* rays, int* launches) {
-    k_big<GATE><<<(unsigned)sm_count(ctx->device) * (share > 1 ? dual_big() : 8), 256, 0, st>>>(ds, q, QRegions{n_ptr, 0u, 1u}, hits, surv, n_surv, rays);
+    k_big<GATE><<<(unsigned)sm_count(ctx->device) * (share > 1 ? dual_big() : 8), 256, 0, st>>>(ds, q, QRegions{n_ptr, 0u, 1u, 0xffffffffu}, hits, surv, n_surv, rays);
     (*launches)++;
     if (ds.root_ref == NRCU_REF_EMPTY) return;
     launch_stage2<GATE>(ctx, st, share, ds, q, hits, surv, n_surv, fetch, rays);
@@ -812,7 +812,8 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                 cudaStream_t st = pp.st;
                 PathQueue qi = pp.q[d & 1], qo = pp.q[(d + 1) & 1];
                 // the queue entering bounce 0 is dense (one counter, written by k_raygen); later queues come in K regions
-                const QRegions rin = (K > 1 && d > 0) ? QRegions{pp.d_qr + CS * K * d, logk, (uint32_t)CS} : QRegions{pp.d_qn + CS * d, 0u, (uint32_t)CS};
+                const uint32_t max_blocks = (capacity + slack) / 32u;
+                const QRegions rin = (K > 1 && d > 0) ? QRegions{pp.d_qr + CS * K * d, logk, (uint32_t)CS, max_blocks} : QRegions{pp.d_qn + CS * d, 0u, (uint32_t)CS, max_blocks};
                 uint32_t* const cnt_out = K > 1 ? pp.d_qr + CS * K * (d + 1) : pp.d_qn + CS * (d + 1);
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
                 if (d > 0) {
@@ -822,8 +823,8 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                         else k_big_balanced64<false><<<g64, 32 * NRCU_BIG64_WARPS, 0, st>>>(ds, qi, rin, pp.hb, pp.surv, pp.d_nsurv + CS * d);
                     }
                     else if (big_balanced()) {
-                        if (gate) k_big_balanced<true, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, rin.cnt, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u, rin.logk, rin.cs);
-                        else k_big_balanced<false, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, rin.cnt, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u, rin.logk, rin.cs);
+                        if (gate) k_big_balanced<true, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, rin.cnt, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u, rin.logk, rin.cs, rin.max_blocks);
+                        else k_big_balanced<false, false><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, qi, rin.cnt, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K, 0u, rin.logk, rin.cs, rin.max_blocks);
                     }
                     else if (gate) k_big<true><<<big_grid, 256, 0, st>>>(ds, qi, rin, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
                     else k_big<false><<<big_grid, 256, 0, st>>>(ds, qi, rin, pp.hb, pp.surv, pp.d_nsurv + CS * d, NRCU_RC_K);
@@ -1057,8 +1058,8 @@ static int render_regen(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                     else k_regen_init<false><<<gen_grid, 256, 0, st>>>(ds, seed, s0, n_samples, pp.lane0, pp.n_slots, pp.q, pp.lacc, pp.hits, pp.surv, n_surv);
                     CTX_LAUNCH_CHECK("k_regen_init");
                 } else {
-                    if (gate) k_big_balanced<true, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots, 0u, 1u);
-                    else k_big_balanced<false, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots, 0u, 1u);
+                    if (gate) k_big_balanced<true, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots, 0u, 1u, 0xffffffffu);
+                    else k_big_balanced<false, true><<<big_grid, 32 * NRCU_BIGB_WARPS, 0, st>>>(ds, pp.q, flags_prev, pp.hits, pp.surv, n_surv, nullptr, pp.n_slots, 0u, 1u, 0xffffffffu);
                     CTX_LAUNCH_CHECK("k_big_balanced (slots)");
                 }
                 if (timing) { cudaEventRecord(pool_event(ctx, ev_i + 1), st); spans.push_back({ev_i, ev_i + 1, 0}); }

@@ -86,14 +86,14 @@ struct PathQueue { f4* a; float2* b; f4* c; uint32_t* d; };
 // software pipeline intact; a block's live lanes are those below its region's count.  The regions receive every K-th
 // block's survivors and stay equally long up to a few blocks, so the only dead lanes are those of the last blocks.
 // K = 1 is the plain compacted queue.
-struct QRegions { const uint32_t* cnt; uint32_t logk, cs; };   // count of region r at cnt[r * cs]
+struct QRegions { const uint32_t* cnt; uint32_t logk, cs, max_blocks; };   // count of region r at cnt[r * cs]; the array holds max_blocks blocks
 // lane r keeps region r's count; returns the number of 32-entry blocks the queue spans in the array
 __device__ __forceinline__ uint32_t regions_begin(const QRegions& qr, uint32_t lane, uint32_t& my_cnt) {
     my_cnt = lane < (1u << qr.logk) ? qr.cnt[(size_t)lane * qr.cs] : 0u;
     const uint32_t b = (my_cnt + 31u) >> 5;
     uint32_t ext = b ? ((b - 1u) << qr.logk) + lane + 1u : 0u;   // region r's last block sits at array block (b - 1) K + r
     for (int o = 16; o > 0; o >>= 1) ext = max(ext, __shfl_xor_sync(0xffffffffu, ext, o));
-    return ext;
+    return min(ext, qr.max_blocks);   // a producer that ran out of room has counted what it dropped (DScene::overflow); never read past the array
 }
 // is lane `lane` of array block pb a live entry?
 __device__ __forceinline__ bool region_live(const QRegions& qr, uint32_t my_cnt, uint32_t pb, uint32_t lane) {
@@ -382,7 +382,7 @@ __device__ __forceinline__ bool regen_anyone_alive(const uint32_t* flags) {
 template <bool GATE, bool SLOTS>
 __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS, NRCU_BIGB_MINB) k_big_balanced(DScene s, PathQueue q, const uint32_t* n_ptr, float2* hits,
                                                                        uint32_t* surv, uint32_t* n_surv, unsigned long long* ray_counter, uint32_t n_fixed,
-                                                                       uint32_t in_logk, uint32_t in_cs) {
+                                                                       uint32_t in_logk, uint32_t in_cs, uint32_t in_max_blocks) {
     __shared__ BigList bl;
     __shared__ unsigned short pairs[NRCU_BIGB_WARPS][32 * NRCU_MAX_BIG];
     __shared__ float rays[NRCU_BIGB_WARPS][6][32];
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(32 * NRCU_BIGB_WARPS, NRCU_BIGB_MINB) k_big_ba
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     // the wavefront's queue comes in regions (QRegions above); the slot array of the regeneration scheduler is one dense range
-    const QRegions rin = {n_ptr, SLOTS ? 0u : in_logk, in_cs};
+    const QRegions rin = {n_ptr, SLOTS ? 0u : in_logk, in_cs, in_max_blocks};
     uint32_t my_cnt = 0;
     const uint32_t n = SLOTS ? n_fixed : regions_begin(rin, lane, my_cnt) * 32u;   // array extent in entries (whole blocks)
     unsigned short* my_pairs = pairs[wib];
@@ -1029,7 +1029,7 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade(DScene s, uint64
             qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
             qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)(slot | ((NEE && ps.next_skips_light) ? 0x80000000u : 0u))));
             if (BRANCH) qo.d[pos1] = branch;
-        }
+        } else if (n_out >= 1 && !BRANCH) atomicAdd(s.overflow + 1, 1u);   // without branching the queue cannot outgrow its array: counted, never silent (branching: k_clamp_count)
         if (BRANCH && n_out == 2 && pos2 < out_capacity) {   // glass branch mode only
             qo.a[pos2] = mk4(ps.next2.o.x, ps.next2.o.y, ps.next2.o.z, ps.next2.d.x);
             qo.b[pos2] = make_float2(ps.next2.d.y, ps.next2.d.z);
@@ -1142,7 +1142,7 @@ __global__ void __launch_bounds__(256, NRCU_SHADE_MINB) k_shade_pool(DScene s, u
             qo.a[pos1] = mk4(ps.next.o.x, ps.next.o.y, ps.next.o.z, ps.next.d.x);
             qo.b[pos1] = make_float2(ps.next.d.y, ps.next.d.z);
             qo.c[pos1] = mk4(ps.thr.x, ps.thr.y, ps.thr.z, i2f((int)slot));
-        }
+        } else if (n_out) atomicAdd(s.overflow + 1, 1u);   // cannot happen (the regions' slack bounds the extent); counted, never silent
     };
     load_entry(warp_global);
     for (uint32_t pb = warp_global; pb < nblocks; pb += warps_total) {
