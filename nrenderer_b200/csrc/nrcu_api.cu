@@ -556,13 +556,15 @@ static int ensure_wave(nrcu_ctx* ctx, int set, uint32_t slots, uint32_t capacity
     const size_t S = (size_t)wave_skew_kb() << 10;
     DevBuf* bufs[] = {&w.qa[0], &w.qb[0], &w.qc[0], &w.qa[1], &w.qb[1], &w.qc[1], &w.hits, &w.surv, &w.L};
     for (size_t j = 0; j < sizeof(bufs) / sizeof(bufs[0]); j++) bufs[j]->skew = (j + 1 + 9 * (size_t)set) * S;
+    // the kernels read the queues in whole blocks of 32 entries (lanes past the live count load entries nobody uses): pad
+    const size_t padded = (size_t)capacity + 32;
     for (int k = 0; k < 2; k++) {
-        CTX_CUDA(w.qa[k].ensure(sizeof(f4) * (size_t)capacity));
-        CTX_CUDA(w.qb[k].ensure(sizeof(float2) * (size_t)capacity));
-        CTX_CUDA(w.qc[k].ensure(sizeof(f4) * (size_t)capacity));
+        CTX_CUDA(w.qa[k].ensure(sizeof(f4) * padded));
+        CTX_CUDA(w.qb[k].ensure(sizeof(float2) * padded));
+        CTX_CUDA(w.qc[k].ensure(sizeof(f4) * padded));
     }
-    CTX_CUDA(w.hits.ensure(sizeof(float2) * (size_t)capacity));
-    if (branch_bits) for (int k = 0; k < 2; k++) CTX_CUDA(w.qd[k].ensure(sizeof(uint32_t) * (size_t)capacity));
+    CTX_CUDA(w.hits.ensure(sizeof(float2) * padded));
+    if (branch_bits) for (int k = 0; k < 2; k++) CTX_CUDA(w.qd[k].ensure(sizeof(uint32_t) * padded));
     if (shadow_queue) {   // NEE: shadow rays of one bounce (ray, contribution + slot, light index)
         CTX_CUDA(w.sa.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(w.sb.ensure(sizeof(float2) * (size_t)capacity));
         CTX_CUDA(w.sc.ensure(sizeof(f4) * (size_t)capacity)); CTX_CUDA(w.sd.ensure(sizeof(uint32_t) * (size_t)capacity));
@@ -812,7 +814,7 @@ static int render_waves(nrcu_ctx* ctx, const nrcu_render_params* params, f4* d_a
                 cudaStream_t st = pp.st;
                 PathQueue qi = pp.q[d & 1], qo = pp.q[(d + 1) & 1];
                 // the queue entering bounce 0 is dense (one counter, written by k_raygen); later queues come in K regions
-                const uint32_t max_blocks = (capacity + slack) / 32u;
+                const uint32_t max_blocks = (capacity + slack + 31u) / 32u;   // the arrays are padded to whole blocks (ensure_wave)
                 const QRegions rin = (K > 1 && d > 0) ? QRegions{pp.d_qr + CS * K * d, logk, (uint32_t)CS, max_blocks} : QRegions{pp.d_qn + CS * d, 0u, (uint32_t)CS, max_blocks};
                 uint32_t* const cnt_out = K > 1 ? pp.d_qr + CS * K * (d + 1) : pp.d_qn + CS * (d + 1);
                 if (timing) cudaEventRecord(pool_event(ctx, ev_i), st);
